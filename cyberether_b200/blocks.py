@@ -1,0 +1,158 @@
+"""Block wiring on the b200 provider — mirrors Block::Impl::moduleCreate / moduleExposeOutput
+(src/block_impl.cc:30-90) for the blocks that call the hot path.
+
+`SpectrumEngine` follows src/domains/dsp/spectrum_engine/block_impl.cc:120-217. With `fused=True`
+(default) the per-cycle part of the chain (multiply -> fft -> amplitude -> [range]) is ONE module
+(`spectral_chain`, one kernel); window -> invert stay separate static modules that settle after the
+first cycle exactly as in the reference (block_tests.cc:103-122). `fused=False` wires the reference's
+module sequence one-to-one on this provider (cast, window, invert, reshape, multiply, fft, amplitude,
+range) — same outputs, one kernel per module.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+from .jetstream import (Module, Result, SynchronousScheduler, Tensor, TensorLink, build_module, _error,
+                        resolve_signal_axes)
+
+
+class Block:
+    TYPE = ""
+    DEFAULTS: Dict[str, object] = {}
+
+    def __init__(self, device: str = "cuda", runtime: str = "native", provider: str = "b200", **config):
+        unknown = set(config) - set(self.DEFAULTS)
+        if unknown:
+            raise TypeError(f"unknown config field(s) for block '{self.TYPE}': {sorted(unknown)}")
+        self.config = dict(self.DEFAULTS)
+        self.config.update(config)
+        self.device, self.runtime, self.provider = device, runtime, provider
+        self.name = ""
+        self.modules: Dict[str, Module] = {}
+        self.inputs: Dict[str, TensorLink] = {}
+        self.outputs: Dict[str, TensorLink] = {}
+        self.scheduler: Optional[SynchronousScheduler] = None
+        self.state = "none"
+
+    # -- Block::Impl helpers
+    def module_create(self, name: str, type_: str, config: Optional[dict], inputs: Dict[str, TensorLink]) -> Result:
+        module = build_module(type_, self.device, self.runtime, self.provider)
+        full = f"{self.name}:{name}"
+        result = module.create(full, config, inputs)
+        if result != Result.SUCCESS:
+            return result
+        self.modules[name] = module
+        return self.scheduler.add(module)
+
+    def module_get_output(self, name: str, port: str) -> TensorLink:
+        return self.modules[name].outputs[port]
+
+    def module_expose_output(self, port: str, name: str, module_port: str) -> Result:
+        self.outputs[port] = self.modules[name].outputs[module_port]
+        return Result.SUCCESS
+
+    # -- lifecycle
+    def create(self, name: str, inputs: Dict[str, Tensor], scheduler: Optional[SynchronousScheduler] = None) -> Result:
+        self.name = name
+        self.scheduler = scheduler or SynchronousScheduler(self.device)
+        self.inputs = {}
+        for port, tensor in inputs.items():
+            link = tensor if isinstance(tensor, TensorLink) else TensorLink(tensor=tensor)
+            self.inputs[port] = link
+        result = self.create_impl()
+        self.state = "created" if result == Result.SUCCESS else "errored"
+        if result != Result.SUCCESS:
+            self.destroy()
+        return result
+
+    def create_impl(self) -> Result:
+        raise NotImplementedError
+
+    def compute(self) -> Result:
+        return self.scheduler.compute()
+
+    def output(self, port: str) -> Tensor:
+        return self.outputs[port].tensor
+
+    def destroy(self) -> Result:
+        for module in list(self.modules.values()):
+            if self.scheduler is not None:
+                self.scheduler.modules.pop(module.name, None)
+            module.destroy()
+        if self.scheduler is not None and self.scheduler.runtime is not None:
+            self.scheduler.runtime.destroy()
+        self.modules = {}
+        return Result.SUCCESS
+
+    def metrics(self) -> Dict[str, tuple]:
+        """`runtime:<module>` -> (cycles, last compute ms), like the reference block metrics."""
+        return {f"runtime:{k}": (m.cycles, m.compute_time_ms) for k, m in self.modules.items()}
+
+
+class SpectrumEngine(Block):
+    """`spectrum_engine` — include/jetstream/domains/dsp/spectrum_engine/block.hh:8-16."""
+    TYPE = "spectrum_engine"
+    DEFAULTS = {"enableAgc": False, "enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0, "fused": True}
+
+    def create_impl(self) -> Result:
+        port = self.inputs.get("buffer")
+        if port is None or not port.resolved():
+            return Result.INCOMPLETE
+        tensor = port.tensor
+        if tensor.dtype not in ("F32", "CF32"):
+            return _error("[BLOCK_SPECTRUM_ENGINE] Input must have data type F32 or CF32.")
+        axes = resolve_signal_axes(tensor)
+        if axes is None:
+            return _error("[BLOCK_SPECTRUM_ENGINE] Input signal axis metadata is invalid.")
+        if self.config["enableAgc"]:
+            return _error("[BLOCK_SPECTRUM_ENGINE_B200] enableAgc is not implemented by this provider "
+                          "(out of scope, SURVEY.md §2.2).")
+        axis = axes.sample
+        size = tensor.shape[axis]
+
+        r = self.module_create("cast_input", "cast", {"outputType": "CF32"}, {"buffer": port})
+        if r != Result.SUCCESS:
+            return r
+        complex_input = self.module_get_output("cast_input", "buffer")
+
+        r = self.module_create("window", "window", {"size": size}, {})
+        if r != Result.SUCCESS:
+            return r
+        r = self.module_create("invert", "invert", None, {"signal": self.module_get_output("window", "window")})
+        if r != Result.SUCCESS:
+            return r
+
+        if self.config["fused"] and axis == tensor.rank - 1:
+            r = self.module_create("spectral_chain", "spectral_chain",
+                                   {"enableScale": bool(self.config["enableScale"]),
+                                    "rangeMin": float(self.config["rangeMin"]),
+                                    "rangeMax": float(self.config["rangeMax"])},
+                                   {"buffer": complex_input, "window": self.module_get_output("invert", "signal")})
+            if r != Result.SUCCESS:
+                return r
+            return self.module_expose_output("buffer", "spectral_chain", "buffer")
+
+        shape = [size if d == axis else 1 for d in range(tensor.rank)]
+        r = self.module_create("reshape_window", "reshape", {"shape": str(shape)},
+                               {"buffer": self.module_get_output("invert", "signal")})
+        if r != Result.SUCCESS:
+            return r
+        reshaped = self.module_get_output("reshape_window", "buffer")
+        reshaped.tensor.set_attribute("sampleAxis", axis)
+        r = self.module_create("multiply", "multiply", None, {"a": complex_input, "b": reshaped})
+        if r != Result.SUCCESS:
+            return r
+        r = self.module_create("fft", "fft", {"forward": True}, {"signal": self.module_get_output("multiply", "product")})
+        if r != Result.SUCCESS:
+            return r
+        r = self.module_create("amplitude", "amplitude", None, {"signal": self.module_get_output("fft", "signal")})
+        if r != Result.SUCCESS:
+            return r
+        if self.config["enableScale"]:
+            r = self.module_create("range", "range", {"min": float(self.config["rangeMin"]),
+                                                      "max": float(self.config["rangeMax"])},
+                                   {"signal": self.module_get_output("amplitude", "signal")})
+            if r != Result.SUCCESS:
+                return r
+            return self.module_expose_output("buffer", "range", "signal")
+        return self.module_expose_output("buffer", "amplitude", "signal")

@@ -1,0 +1,415 @@
+// fft module + fused spectral chain entry points.
+//   * n == 4096            : fft4096_kernel (TMA-staged, single pass, registers + smem exchange)
+//   * other n = 2^k <= 16384: fft_generic_kernel (Stockham autosort radix-4/2 in shared memory,
+//                             one CTA-slice per row, same fused prologue/epilogue policies)
+// Replaces pocketfft::c2c (src/domains/dsp/fft/module_impl_native_cpu.cc:129-140) / cuFFT
+// (src/domains/dsp/fft/module_impl_native_cuda.cc:321-333,433) and, for the chain, the module
+// sequence of src/domains/dsp/spectrum_engine/block_impl.cc:120-217.
+#include <cmath>
+#include <vector>
+
+#include "fft4096.cuh"
+
+namespace b200 {
+
+// ---- generic power-of-two kernel ------------------------------------------------------------
+// Stockham autosort, in place with register staging: every pass reads its inputs into registers,
+// barriers, writes the permuted outputs back. Pass with sub-transform size Ns, radix R:
+//   j in [0, n/R), k = j mod Ns, u_t = buf[j + t n/R] * W_{R Ns}^{k t}, y = DFT_R(u),
+//   buf[((j - k) * R + k) + t Ns] = y_t.
+template <int MODE, int WIN, int BPT>
+__global__ void __launch_bounds__(1024) fft_generic_kernel(const FftParams p, const int log2n, const int tpr,
+                                                          const int rows_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* const sm = reinterpret_cast<float2*>(smem_raw);
+    const uint32_t n = p.n;
+    const uint32_t lane = threadIdx.x % tpr;
+    const uint32_t slot = threadIdx.x / tpr;
+    float2* const buf = sm + static_cast<size_t>(slot) * n;
+    const uint64_t groups = (p.rows + rows_per_cta - 1) / rows_per_cta;
+
+    for (uint64_t group = blockIdx.x; group < groups; group += gridDim.x) {
+        const uint64_t row = group * rows_per_cta + slot;
+        const bool valid = row < p.rows;
+
+        if (valid) {
+            const float2* const src = p.in + row * n;
+            for (uint32_t j = lane; j < n; j += tpr) {
+                float2 x = ldg_stream_f2(src + j);
+                if constexpr (MODE == MODE_C2C) {
+                    if (p.inverse) {
+                        x = make_float2(x.y, x.x);
+                    }
+                }
+                if constexpr (WIN == WIN_REAL) {
+                    x = apply_window<WIN>(x, p.win_re[j], make_float2(0.f, 0.f));
+                } else if constexpr (WIN == WIN_COMPLEX) {
+                    x = apply_window<WIN>(x, 0.f, p.win_c[j]);
+                }
+                buf[j] = x;
+            }
+        }
+        __syncthreads();
+
+        uint32_t log2ns = 0;
+        if (log2n & 1) {
+            // radix-2 pass (Ns = 1: no twiddles)
+            const uint32_t total = n >> 1;
+            float2 r[2 * BPT][2];
+#pragma unroll
+            for (int b = 0; b < 2 * BPT; ++b) {
+                const uint32_t j = lane + b * tpr;
+                if (j < total) {
+                    r[b][0] = buf[j];
+                    r[b][1] = buf[j + total];
+                    bfly2(r[b][0], r[b][1]);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < 2 * BPT; ++b) {
+                const uint32_t j = lane + b * tpr;
+                if (j < total) {
+                    buf[2 * j] = r[b][0];
+                    buf[2 * j + 1] = r[b][1];
+                }
+            }
+            __syncthreads();
+            log2ns = 1;
+        }
+        for (; log2ns < static_cast<uint32_t>(log2n); log2ns += 2) {
+            const uint32_t total = n >> 2;
+            const uint32_t ns = 1u << log2ns;
+            const uint32_t shift = log2n - 2 - log2ns;  // W_{4Ns}^{e} = W_n^{e << shift}
+            float2 r[BPT][4];
+#pragma unroll
+            for (int b = 0; b < BPT; ++b) {
+                const uint32_t j = lane + b * tpr;
+                if (j < total) {
+                    const uint32_t k = j & (ns - 1);
+                    r[b][0] = buf[j];
+                    r[b][1] = buf[j + total];
+                    r[b][2] = buf[j + 2 * total];
+                    r[b][3] = buf[j + 3 * total];
+                    if (k != 0) {
+                        r[b][1] = cmul(r[b][1], p.twiddle[k << shift]);
+                        r[b][2] = cmul(r[b][2], p.twiddle[(2 * k) << shift]);
+                        r[b][3] = cmul(r[b][3], p.twiddle[(3 * k) << shift]);
+                    }
+                    bfly4(r[b][0], r[b][1], r[b][2], r[b][3]);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < BPT; ++b) {
+                const uint32_t j = lane + b * tpr;
+                if (j < total) {
+                    const uint32_t k = j & (ns - 1);
+                    const uint32_t j0 = ((j - k) << 2) + k;
+                    buf[j0] = r[b][0];
+                    buf[j0 + ns] = r[b][1];
+                    buf[j0 + 2 * ns] = r[b][2];
+                    buf[j0 + 3 * ns] = r[b][3];
+                }
+            }
+            __syncthreads();
+        }
+
+        if (valid) {
+            if constexpr (MODE == MODE_C2C) {
+                float2* const dst = static_cast<float2*>(p.out) + row * n;
+                for (uint32_t j = lane; j < n; j += tpr) {
+                    float2 X = buf[j];
+                    if (p.inverse) {
+                        X = make_float2(X.y, X.x);
+                    }
+                    stg_stream_f2(dst + j, X);
+                }
+            } else {
+                float* const dst = static_cast<float*>(p.out) + row * n;
+                for (uint32_t j = lane; j < n; j += tpr) {
+                    stg_stream_f1(dst + j, spectral_epilogue<MODE>(buf[j], p));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- launch logic ------------------------------------------------------------------------------
+
+constexpr uint64_t kMaxGenericN = 16384;
+
+static bool fft_size_supported(const uint64_t n) { return is_pow2(n) && n >= 2 && n <= kMaxGenericN; }
+
+template <int MODE, int WIN>
+static int launch_4096(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    auto kernel = fft4096_kernel<MODE, WIN>;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft4096SmemBytes));
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
+    const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
+    kernel<<<grid, kFft4096Threads, kFft4096SmemBytes, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+template <int MODE, int WIN, int BPT>
+static int launch_generic_bpt(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    const int log2n = ilog2(p.n);
+    int tpr = static_cast<int>(p.n / (4 * BPT));
+    if (tpr < 1) {
+        tpr = 1;
+    }
+    int rows_per_cta = tpr >= 256 ? 1 : 256 / tpr;
+    if (static_cast<uint64_t>(rows_per_cta) > p.rows) {
+        rows_per_cta = static_cast<int>(p.rows);
+    }
+    const int threads = tpr * rows_per_cta;
+    const size_t smem = static_cast<size_t>(rows_per_cta) * p.n * sizeof(float2);
+    auto kernel = fft_generic_kernel<MODE, WIN, BPT>;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem > 48 * 1024 ? smem : 48 * 1024)));
+    int per_sm = 1;
+    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) {
+        per_sm = 1;
+    }
+    const uint64_t groups = (p.rows + rows_per_cta - 1) / rows_per_cta;
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * per_sm;
+    const unsigned grid = static_cast<unsigned>(groups < cap ? groups : cap);
+    kernel<<<grid, threads, smem, stream>>>(p, log2n, tpr, rows_per_cta);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+template <int MODE, int WIN>
+static int launch_fft(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    if (p.rows == 0) {
+        return B200_SUCCESS;
+    }
+    if (p.n == kFft4096N && (reinterpret_cast<uintptr_t>(p.in) & 15u) == 0) {
+        return launch_4096<MODE, WIN>(ctx, p, stream);
+    }
+    if (p.n <= 1024) {
+        return launch_generic_bpt<MODE, WIN, 1>(ctx, p, stream);
+    }
+    if (p.n == 2048) {
+        return launch_generic_bpt<MODE, WIN, 2>(ctx, p, stream);
+    }
+    return launch_generic_bpt<MODE, WIN, 4>(ctx, p, stream);
+}
+
+static int make_twiddle_table(b200_ctx* ctx, const uint64_t n, float2** out) {
+    std::vector<float2> host(n);
+    const double kTwoPi = 6.283185307179586476925286766559;
+    for (uint64_t j = 0; j < n; ++j) {
+        const double a = -kTwoPi * static_cast<double>(j) / static_cast<double>(n);
+        host[j] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(std::sin(a)));
+    }
+    void* dev = nullptr;
+    if (b200_malloc(ctx, n * sizeof(float2), &dev) != B200_SUCCESS) {
+        return B200_ERROR;
+    }
+    const cudaError_t e = cudaMemcpy(dev, host.data(), n * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(dev);
+        return fail("twiddle upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = static_cast<float2*>(dev);
+    return B200_SUCCESS;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_fft_plan {
+    b200_ctx* ctx;
+    uint64_t n;
+    uint64_t batch;
+    float2* twiddle;
+};
+
+struct b200_chain_plan {
+    b200_ctx* ctx;
+    uint64_t n;
+    uint64_t max_batch;
+    float2* twiddle;
+    float* win_re;    // non-null: window is purely real
+    float2* win_c;    // non-null: general complex window
+    const char* variant;
+};
+
+extern "C" {
+
+int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan** plan) {
+    B200_REQUIRE(ctx && plan, "b200_fft_plan_c2c: null argument");
+    *plan = nullptr;
+    B200_REQUIRE(n >= 1, "b200_fft_plan_c2c: transform length must be positive");
+    B200_REQUIRE(n == 1 || fft_size_supported(n),
+                 "b200_fft_plan_c2c: n=%llu unsupported (power of two up to %llu in this build)",
+                 static_cast<unsigned long long>(n), static_cast<unsigned long long>(kMaxGenericN));
+    DeviceGuard guard(ctx);
+    float2* tw = nullptr;
+    if (n > 1 && make_twiddle_table(ctx, n, &tw) != B200_SUCCESS) {
+        return B200_ERROR;
+    }
+    *plan = new b200_fft_plan{ctx, n, batch, tw};
+    return B200_SUCCESS;
+}
+
+int b200_fft_exec(b200_fft_plan* plan, const b200_cf32* in, b200_cf32* out, int forward, b200_stream stream) {
+    B200_REQUIRE(plan, "b200_fft_exec: null plan");
+    if (plan->batch == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(in && out, "b200_fft_exec: null buffer");
+    DeviceGuard guard(plan->ctx);
+    if (plan->n == 1) {
+        if (in != out) {
+            B200_CUDA_CHECK(cudaMemcpyAsync(out, in, plan->batch * sizeof(float2), cudaMemcpyDeviceToDevice,
+                                            as_stream(stream)));
+        }
+        return B200_SUCCESS;
+    }
+    FftParams p{};
+    p.in = reinterpret_cast<const float2*>(in);
+    p.out = out;
+    p.rows = plan->batch;
+    p.n = static_cast<uint32_t>(plan->n);
+    p.inverse = forward ? 0 : 1;
+    p.twiddle = plan->twiddle;
+    return launch_fft<MODE_C2C, WIN_NONE>(plan->ctx, p, as_stream(stream));
+}
+
+int b200_fft_plan_destroy(b200_fft_plan* plan) {
+    if (!plan) {
+        return B200_SUCCESS;
+    }
+    DeviceGuard guard(plan->ctx);
+    cudaFree(plan->twiddle);
+    delete plan;
+    return B200_SUCCESS;
+}
+
+int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const b200_cf32* window_dev,
+                           b200_chain_plan** plan) {
+    B200_REQUIRE(ctx && plan, "b200_chain_plan_create: null argument");
+    *plan = nullptr;
+    B200_REQUIRE(fft_size_supported(n),
+                 "b200_chain_plan_create: n=%llu unsupported (power of two, 2..%llu in this build)",
+                 static_cast<unsigned long long>(n), static_cast<unsigned long long>(kMaxGenericN));
+    DeviceGuard guard(ctx);
+    auto* pl = new b200_chain_plan{ctx, n, max_batch, nullptr, nullptr, nullptr, ""};
+    if (make_twiddle_table(ctx, n, &pl->twiddle) != B200_SUCCESS) {
+        delete pl;
+        return B200_ERROR;
+    }
+    if (window_dev) {
+        // The window is a settled STATIC_OUTPUT tensor: inspect it once.
+        std::vector<float2> host(n);
+        cudaError_t e = cudaMemcpy(host.data(), window_dev, n * sizeof(float2), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            b200_chain_plan_destroy(pl);
+            return fail("b200_chain_plan_create: window download failed: %s", cudaGetErrorString(e));
+        }
+        bool real = true;
+        for (uint64_t i = 0; i < n; ++i) {
+            real = real && host[i].y == 0.0f;
+        }
+        void* dev = nullptr;
+        if (real) {
+            std::vector<float> re(n);
+            for (uint64_t i = 0; i < n; ++i) {
+                re[i] = host[i].x;
+            }
+            if (b200_malloc(ctx, n * sizeof(float), &dev) != B200_SUCCESS) {
+                b200_chain_plan_destroy(pl);
+                return B200_ERROR;
+            }
+            e = cudaMemcpy(dev, re.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+            pl->win_re = static_cast<float*>(dev);
+        } else {
+            if (b200_malloc(ctx, n * sizeof(float2), &dev) != B200_SUCCESS) {
+                b200_chain_plan_destroy(pl);
+                return B200_ERROR;
+            }
+            e = cudaMemcpy(dev, host.data(), n * sizeof(float2), cudaMemcpyHostToDevice);
+            pl->win_c = static_cast<float2*>(dev);
+        }
+        if (e != cudaSuccess) {
+            b200_chain_plan_destroy(pl);
+            return fail("b200_chain_plan_create: window upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    pl->variant = n == kFft4096N ? "fft4096_kernel<tma,radix16x3>" : "fft_generic_kernel<stockham4>";
+    *plan = pl;
+    return B200_SUCCESS;
+}
+
+const char* b200_chain_plan_variant(const b200_chain_plan* plan) { return plan ? plan->variant : ""; }
+
+int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch, float amp_coeff,
+                    int enable_range, float scale, float offset, b200_stream stream) {
+    B200_REQUIRE(plan, "b200_chain_exec: null plan");
+    if (batch == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(x && out, "b200_chain_exec: null buffer");
+    DeviceGuard guard(plan->ctx);
+    FftParams p{};
+    p.in = reinterpret_cast<const float2*>(x);
+    p.out = out;
+    p.rows = batch;
+    p.n = static_cast<uint32_t>(plan->n);
+    p.twiddle = plan->twiddle;
+    p.win_re = plan->win_re;
+    p.win_c = plan->win_c;
+    // dB = 20 * (Y * log10(2)) + coeff
+    const double kDbPerLog2 = 20.0 * 0.3010299956639812;
+    p.amp_scale = static_cast<float>(kDbPerLog2);
+    p.amp_coeff = amp_coeff;
+    if (enable_range) {
+        // 0.5 + 0.5 tanh(z), z = 4 ((dB s + o) - 0.5)  ==  1 / (1 + 2^(-2 z log2(e)))
+        const double kLog2e = 1.4426950408889634;
+        const double a = -8.0 * kLog2e * static_cast<double>(scale);
+        const double b = -8.0 * kLog2e * (static_cast<double>(offset) - 0.5);
+        if (scale == 0.0f) {  // RangeImplNativeCpu::kernelF32: scale == 0 -> 0.5 everywhere
+            p.k1 = 0.0f;
+            p.k0 = 0.0f;
+            p.zero_value = 0.5f;
+        } else {
+            p.k1 = static_cast<float>(a * kDbPerLog2);
+            p.k0 = static_cast<float>(a * static_cast<double>(amp_coeff) + b);
+            p.zero_value = 0.0f;
+        }
+    }
+    const cudaStream_t s = as_stream(stream);
+    const int win = plan->win_re ? WIN_REAL : (plan->win_c ? WIN_COMPLEX : WIN_NONE);
+#define B200_CHAIN_DISPATCH(MODE)                                                   \
+    switch (win) {                                                                  \
+        case WIN_REAL: return launch_fft<MODE, WIN_REAL>(plan->ctx, p, s);          \
+        case WIN_COMPLEX: return launch_fft<MODE, WIN_COMPLEX>(plan->ctx, p, s);    \
+        default: return launch_fft<MODE, WIN_NONE>(plan->ctx, p, s);                \
+    }
+    if (enable_range) {
+        B200_CHAIN_DISPATCH(MODE_AMP_RANGE)
+    } else {
+        B200_CHAIN_DISPATCH(MODE_AMP)
+    }
+#undef B200_CHAIN_DISPATCH
+}
+
+int b200_chain_plan_destroy(b200_chain_plan* plan) {
+    if (!plan) {
+        return B200_SUCCESS;
+    }
+    DeviceGuard guard(plan->ctx);
+    cudaFree(plan->twiddle);
+    cudaFree(plan->win_re);
+    cudaFree(plan->win_c);
+    delete plan;
+    return B200_SUCCESS;
+}
+
+}  // extern "C"

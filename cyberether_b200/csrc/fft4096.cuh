@@ -1,0 +1,264 @@
+// Single-pass 4096-point CF32 FFT kernel with fused prologue/epilogue — the B200 replacement for
+// the spectrum_engine module chain (src/domains/dsp/spectrum_engine/block_impl.cc:120-217) and,
+// in MODE_C2C, for the 4096-point `fft` module.
+//
+// Design:
+//   * persistent CTAs (2 per SM, 256 threads), one 4096-point row at a time per CTA;
+//   * each row (32 KiB) is staged into shared memory by ONE TMA bulk copy (cp.async.bulk +
+//     mbarrier complete_tx), kStages-deep ring so HBM reads run ahead of the math;
+//   * 4096 = 16 x 16 x 16: three radix-16 passes held entirely in registers (16 points/thread),
+//     two shared-memory exchanges done IN the row's own staging buffer (no extra smem), all
+//     exchange accesses bank-conflict-free (XOR swizzle on the second one);
+//   * window multiply on the way in, |X| -> dB -> range on the way out, in registers;
+//   * HBM traffic = 8 B/sample in + 4 B/sample out (MODE_AMP*), nothing else.
+//
+// Index algebra (validated against numpy in tests/test_index_algebra.py):
+//   n = 256a + t (t = 16b + c),  k = k0 + 16 k1 + 256 k2
+//   pass 1  thread t        : Y1[k0] = sum_a x[256a + t] W16^(a k0);  *= W4096^(t k0)  -> smem[256 k0 + t]
+//   pass 2  thread 16k0 + c : Y2[k1] = sum_b smem[256 k0 + 16 b + c] W16^(b k1); *= W256^(c k1)
+//                                                                      -> smem[272 k1 + 17 k0 + c]
+//   pass 3  thread k0+16k1  : X[k0 + 16 k1 + 256 k2] = sum_c smem[272 k1 + 17 k0 + c] W16^(c k2)
+#pragma once
+
+#include "fft_common.cuh"
+
+namespace b200 {
+
+constexpr int kFft4096N = 4096;
+constexpr int kFft4096Threads = 256;
+constexpr int kFft4096Stages = 3;
+constexpr int kFft4096RowBytes = kFft4096N * 8;
+// A stage holds the 32 KiB row; the second exchange uses a padded [16][16][17] layout (34816 B).
+constexpr int kFft4096StageBytes = 16 * 272 * 8;
+constexpr int kFft4096SmemBytes = kFft4096Stages * kFft4096StageBytes + 64;
+
+// ---- mbarrier / TMA (bulk async copy) PTX wrappers ------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (complete_tx::bytes).
+__device__ __forceinline__ void tma_load_row(void* smem_dst, const void* gmem_src, const uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// Thread-constant twiddle powers w^1, w^2, w^3 (lo) and w^4, w^8, w^12 (hi); w^k = hi[k>>2] * lo[k&3].
+struct TwiddleSet {
+    float2 lo[3];
+    float2 hi[3];
+};
+
+__device__ __forceinline__ TwiddleSet load_twiddles(const float2* __restrict__ table, const uint32_t base) {
+    // table[j] = W4096^j; powers of w = W4096^base. base * 12 < 4096 is guaranteed by the callers.
+    TwiddleSet s;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        s.lo[m] = table[base * (m + 1)];
+        s.hi[m] = table[base * 4 * (m + 1)];
+    }
+    return s;
+}
+
+// v[dft16_pos(k)] *= w^k for k = 1..15.
+__device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const TwiddleSet& s) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+        float2 x = v[dft16_pos(k)];
+        if ((k & 3) != 0) {
+            x = cmul(x, s.lo[(k & 3) - 1]);
+        }
+        if ((k >> 2) != 0) {
+            x = cmul(x, s.hi[(k >> 2) - 1]);
+        }
+        v[dft16_pos(k)] = x;
+    }
+}
+
+template <int MODE, int WIN>
+__global__ void __launch_bounds__(kFft4096Threads, 2) fft4096_kernel(const FftParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kFft4096Stages * kFft4096StageBytes);
+
+    const uint32_t t = threadIdx.x;
+    const uint64_t first = blockIdx.x;
+    const uint64_t stride = gridDim.x;
+    const uint32_t my_rows =
+        first < p.rows ? static_cast<uint32_t>((p.rows - first + stride - 1) / stride) : 0u;
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kFft4096Stages; ++s) {
+            mbar_init(&full[s], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const float2* next_src = p.in + first * kFft4096N;   // thread 0: next row to request
+    const uint64_t src_step = stride * kFft4096N;
+    uint32_t issued = 0;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kFft4096Stages; ++s) {
+            if (issued < my_rows) {
+                mbar_expect_tx(&full[s], kFft4096RowBytes);
+                tma_load_row(smem_raw + s * kFft4096StageBytes, next_src, kFft4096RowBytes, &full[s]);
+                next_src += src_step;
+                ++issued;
+            }
+        }
+    }
+
+    // Thread-constant operands (persistent across rows).
+    const uint32_t lo4 = t & 15, hi4 = t >> 4;
+    const TwiddleSet tw1 = load_twiddles(p.twiddle, t);          // W4096^(t k0)
+    const TwiddleSet tw2 = load_twiddles(p.twiddle, 16 * lo4);   // W256^(c k1) = W4096^(16 c k1)
+
+    float wr[16];
+    if constexpr (WIN == WIN_REAL) {
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+            wr[a] = p.win_re[t + 256 * a];
+        }
+    }
+
+    // Per-thread byte offsets inside a stage buffer (element = 8 bytes).
+    //   pass 1 load / exchange-1 store : t + 256 a                       (a, k0 = register index)
+    //   exchange-1 load  (t = 16 k0 + c): 256 k0 + c + 16 b
+    //   exchange-2 store (t = 16 k0 + c): 17 k0 + c + 272 k1            (row pitch 17 / plane pitch 272:
+    //   exchange-2 load  (t = k0 + 16 k1): 17 k0 + 272 k1 + c             conflict-free, immediate offsets)
+    const uint32_t off_p1 = t * 8;
+    const uint32_t off_x1 = (256 * hi4 + lo4) * 8;
+    const uint32_t off_x2s = (17 * hi4 + lo4) * 8;
+    const uint32_t off_x2l = (17 * lo4 + 272 * hi4) * 8;
+
+    uint32_t stage = 0, parity = 0;
+    uint32_t refill_stage = 0;  // stage of the previous row (refilled after barrier (A))
+    unsigned char* out_ptr = static_cast<unsigned char*>(p.out) +
+                             (first * kFft4096N + t) * (MODE == MODE_C2C ? 8 : 4);
+    const uint64_t out_step = stride * kFft4096N * (MODE == MODE_C2C ? 8 : 4);
+
+    for (uint32_t i = 0; i < my_rows; ++i) {
+        unsigned char* const buf = smem_raw + stage * kFft4096StageBytes;
+        mbar_wait(&full[stage], parity);
+
+        // ---- pass 1 -------------------------------------------------------------------------
+        float2 v[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+            float2 x = *reinterpret_cast<const float2*>(buf + off_p1 + 2048 * a);
+            if constexpr (MODE == MODE_C2C) {
+                if (p.inverse) {
+                    x = make_float2(x.y, x.x);  // IFFT(x) = swap(FFT(swap(x)))
+                }
+            }
+            if constexpr (WIN == WIN_REAL) {
+                x = apply_window<WIN>(x, wr[a], make_float2(0.f, 0.f));
+            } else if constexpr (WIN == WIN_COMPLEX) {
+                x = apply_window<WIN>(x, 0.f, p.win_c[t + 256 * a]);
+            }
+            v[a] = x;
+        }
+        dft16(v);
+        apply_twiddles(v, tw1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            // this thread's own input slots: no hazard
+            *reinterpret_cast<float2*>(buf + off_p1 + 2048 * k) = v[dft16_pos(k)];
+        }
+        __syncthreads();  // (A)
+
+        // The previous row's buffer is free now (every thread finished its pass-3 reads before
+        // arriving at (A)): refill it with the row kStages-1 ahead.
+        if (t == 0 && i >= 1 && issued < my_rows) {
+            fence_proxy_async();
+            mbar_expect_tx(&full[refill_stage], kFft4096RowBytes);
+            tma_load_row(smem_raw + refill_stage * kFft4096StageBytes, next_src, kFft4096RowBytes,
+                         &full[refill_stage]);
+            next_src += src_step;
+            ++issued;
+        }
+
+        // ---- pass 2 -------------------------------------------------------------------------
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            v[b] = *reinterpret_cast<const float2*>(buf + off_x1 + 128 * b);
+        }
+        dft16(v);
+        apply_twiddles(v, tw2);
+        __syncthreads();  // (B) all exchange-1 reads done before exchange-2 writes
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            *reinterpret_cast<float2*>(buf + off_x2s + 2176 * k) = v[dft16_pos(k)];
+        }
+        __syncthreads();  // (C)
+
+        // ---- pass 3 -------------------------------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            v[c] = *reinterpret_cast<const float2*>(buf + off_x2l + 8 * c);
+        }
+        dft16(v);
+
+        // ---- epilogue: X[t + 256 k2] ---------------------------------------------------------
+        if constexpr (MODE == MODE_C2C) {
+            float2* const out = reinterpret_cast<float2*>(out_ptr);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                float2 X = v[dft16_pos(k)];
+                if (p.inverse) {
+                    X = make_float2(X.y, X.x);
+                }
+                stg_stream_f2(out + 256 * k, X);
+            }
+        } else {
+            float* const out = reinterpret_cast<float*>(out_ptr);
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                const float2 r = spectral_epilogue2<MODE>(v[dft16_pos(k)], v[dft16_pos(k + 1)], p);
+                stg_stream_f1(out + 256 * k, r.x);
+                stg_stream_f1(out + 256 * (k + 1), r.y);
+            }
+        }
+        out_ptr += out_step;
+
+        refill_stage = stage;
+        if (++stage == kFft4096Stages) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,1143 @@
+"""Host-side mirror of the reference's Module / Runtime / Scheduler interface for the DSP hot path.
+
+Same type strings, config fields, port names, taints, Result codes and error behaviour as the
+reference, so tests read like the reference's own module tests
+(`TestContext ctx("fft", ...); ctx.setConfig(...); ctx.setInput("signal", t); ctx.run()`,
+src/testing.cc:105-170). Every `compute_submit` is one call into libb200dsp through the C ABI
+(include/b200dsp.h); there is no CPU compute path here — tensors that are not on a CUDA device
+make compute fail with Result.ERROR.
+
+PyTorch is used for device memory and streams only (tensor allocation, H2D/D2H, current stream).
+
+Reference interfaces mirrored:
+  Module lifecycle / taints      include/jetstream/detail/module_impl.hh:31-116, include/jetstream/module.hh:53-63
+  Registry 4-key lookup          src/registry.cc:583-622
+  NativeCudaRuntime              src/runtime/native/cuda/impl.cc:35-118,185-272
+  SynchronousScheduler           src/scheduler_synchronous.cc:315-568,574-749
+  Signal axes                    src/memory/axis.cc:231-243
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import B200Error
+
+
+class Result(enum.IntEnum):  # include/jetstream/types.hh:19-30
+    SUCCESS = 0
+    ERROR = 1
+    WARNING = 2
+    FATAL = 3
+    SKIP = 4
+    YIELD = 5
+    RELOAD = 6
+    RECREATE = 7
+    TIMEOUT = 8
+    INCOMPLETE = 9
+
+
+class Taint(enum.IntFlag):  # include/jetstream/module.hh:53-63
+    CLEAN = 0
+    DISCONTIGUOUS = 1
+    CROSS_DEVICE = 2
+    STATELESS = 4
+    STATIC_OUTPUT = 8
+    SURFACE = 16
+
+
+_last_error = [""]
+
+
+def last_error() -> str:
+    return _last_error[0]
+
+
+def _error(msg: str) -> Result:
+    _last_error[0] = msg
+    return Result.ERROR
+
+
+DTYPES = {"F32": torch.float32, "CF32": torch.complex64}
+DTYPE_NAMES = {v: k for k, v in DTYPES.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# Backend context (one per device) — replaces Backend::State<DeviceType::CUDA>()
+# ---------------------------------------------------------------------------------------------
+
+class Context:
+    _instances: Dict[int, "Context"] = {}
+
+    def __init__(self, device_index: int):
+        self.lib = _native.load()
+        handle = ctypes.c_void_p()
+        _native.check(self.lib.b200_ctx_create(device_index, ctypes.byref(handle)))
+        self.handle = handle
+        self.device_index = device_index
+        sms = ctypes.c_int()
+        _native.check(self.lib.b200_ctx_sm_count(self.handle, ctypes.byref(sms)))
+        self.sm_count = sms.value
+
+    @classmethod
+    def get(cls, device) -> "Context":
+        index = torch.device(device).index
+        if index is None:
+            index = torch.cuda.current_device()
+        if index not in cls._instances:
+            cls._instances[index] = Context(index)
+        return cls._instances[index]
+
+
+def current_stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# Tensor (shape/dtype/attributes over shared device storage) — include/jetstream/memory/tensor.hh
+# ---------------------------------------------------------------------------------------------
+
+class Tensor:
+    """Handle over shared storage with signal-axis attributes (sampleAxis/batchAxis/channelAxis)."""
+
+    def __init__(self, data: Optional[torch.Tensor] = None, attributes: Optional[dict] = None):
+        self.data = data
+        self.attributes: Dict[str, object] = dict(attributes or {})
+
+    # -- construction
+    @staticmethod
+    def create(device, dtype: str, shape: Sequence[int]) -> "Tensor":
+        return Tensor(torch.zeros(tuple(int(s) for s in shape), dtype=DTYPES[dtype], device=device))
+
+    @staticmethod
+    def from_numpy(array: np.ndarray, device="cuda", **axes) -> "Tensor":
+        t = torch.from_numpy(np.ascontiguousarray(array))
+        if t.dtype not in DTYPE_NAMES:
+            raise TypeError(f"unsupported dtype {array.dtype}")
+        out = Tensor(t.to(device))
+        for key, value in axes.items():
+            if value is not None:
+                out.set_attribute(key, int(value))
+        return out
+
+    def clone(self) -> "Tensor":  # new handle, same storage (Tensor::clone)
+        return Tensor(self.data, self.attributes)
+
+    # -- introspection
+    def valid(self) -> bool:
+        return self.data is not None
+
+    @property
+    def shape(self) -> Tuple[int, ...]:
+        return tuple(self.data.shape)
+
+    @property
+    def rank(self) -> int:
+        return self.data.dim()
+
+    @property
+    def dtype(self) -> str:
+        return DTYPE_NAMES[self.data.dtype]
+
+    @property
+    def size(self) -> int:
+        return self.data.numel()
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def contiguous(self) -> bool:
+        return self.data.is_contiguous()
+
+    def ptr(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(self.data.data_ptr())
+
+    def numpy(self) -> np.ndarray:
+        return self.data.detach().cpu().numpy()
+
+    # -- attributes
+    def has_attribute(self, key: str) -> bool:
+        return key in self.attributes
+
+    def attribute(self, key: str):
+        return self.attributes[key]
+
+    def set_attribute(self, key: str, value) -> Result:
+        self.attributes[key] = value
+        return Result.SUCCESS
+
+    def remove_attribute(self, key: str) -> Result:
+        self.attributes.pop(key, None)
+        return Result.SUCCESS
+
+    def propagate_attributes(self, source: "Tensor") -> Result:
+        self.attributes = dict(source.attributes)
+        return Result.SUCCESS
+
+
+@dataclass
+class SignalAxes:
+    sample: Optional[int] = None
+    batch: Optional[int] = None
+    channel: Optional[int] = None
+
+
+def resolve_signal_axes(tensor: Tensor) -> Optional[SignalAxes]:
+    """ResolveSignalAxes (src/memory/axis.cc:231-243): rank-1 tensors default to sampleAxis=0;
+    axes must be in range and distinct; a sample axis is required."""
+    axes = SignalAxes()
+    for name in ("sample", "batch", "channel"):
+        key = name + "Axis"
+        if tensor.has_attribute(key):
+            value = tensor.attribute(key)
+            if not isinstance(value, int) or isinstance(value, bool):
+                return None
+            setattr(axes, name, value)
+    if axes.sample is None and tensor.rank == 1:
+        axes.sample = 0
+    seen = set()
+    for value in (axes.sample, axes.batch, axes.channel):
+        if value is None:
+            continue
+        if value < 0 or value >= tensor.rank or value in seen:
+            return None
+        seen.add(value)
+    if axes.sample is None:
+        return None
+    return axes
+
+
+@dataclass
+class TensorLink:  # include/jetstream/tensor_link.hh:22-32
+    tensor: Tensor = field(default_factory=Tensor)
+    producer: Optional[Tuple[str, str]] = None
+
+    def produced(self, module: str, port: str, tensor: Tensor):
+        self.producer = (module, port)
+        self.tensor = tensor
+
+    def resolved(self) -> bool:
+        return self.tensor.valid()
+
+
+# ---------------------------------------------------------------------------------------------
+# Module base + registry
+# ---------------------------------------------------------------------------------------------
+
+class Module:
+    """Module::Impl lifecycle: validate -> define -> (input checks) -> create; compute_submit per cycle."""
+
+    TYPE = ""
+    DEFAULTS: Dict[str, object] = {}
+    device_type = "cuda"
+    runtime_type = "native"
+    provider = "b200"
+
+    def __init__(self):
+        self.name = ""
+        self.config: Dict[str, object] = dict(self.DEFAULTS)
+        self.inputs: Dict[str, TensorLink] = {}
+        self.outputs: Dict[str, TensorLink] = {}
+        self.input_ports: List[str] = []
+        self.output_ports: List[str] = []
+        self.taint = Taint.CLEAN
+        self.state = "created-none"
+        self.cycles = 0
+        self.compute_time_ms = 0.0
+        # Where input-less modules allocate: the CUDA device when one is visible. On a CPU-only box the
+        # lifecycle (validate/define/create) still runs on host tensors, but compute_submit refuses.
+        self.alloc_device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+            else torch.device("cpu")
+
+    # -- hooks overridden by implementations
+    def validate(self) -> Result:
+        return Result.SUCCESS
+
+    def define(self) -> Result:
+        return Result.SUCCESS
+
+    def create_impl(self) -> Result:
+        return Result.SUCCESS
+
+    def destroy(self) -> Result:
+        return Result.SUCCESS
+
+    def reconfigure_impl(self, candidate: Dict[str, object]) -> Result:
+        return Result.RECREATE
+
+    def compute_initialize(self) -> Result:
+        return Result.SUCCESS
+
+    def compute_submit(self, stream: ctypes.c_void_p) -> Result:
+        return Result.SUCCESS
+
+    def compute_deinitialize(self) -> Result:
+        return Result.SUCCESS
+
+    # -- helpers
+    def define_taint(self, taint: Taint) -> Result:
+        self.taint = taint
+        return Result.SUCCESS
+
+    def define_interface_input(self, port: str) -> Result:
+        self.input_ports.append(port)
+        return Result.SUCCESS
+
+    def define_interface_output(self, port: str) -> Result:
+        self.output_ports.append(port)
+        return Result.SUCCESS
+
+    # -- Module::create (src/module.cc:47-212)
+    def create(self, name: str, config: Optional[Dict[str, object]], inputs: Dict[str, TensorLink]) -> Result:
+        self.name = name
+        unknown = set(config or {}) - set(self.DEFAULTS)
+        if unknown:
+            self.state = "errored"
+            return _error(f"[MODULE_{self.TYPE.upper()}] Unknown config field(s): {sorted(unknown)}")
+        self.config = dict(self.DEFAULTS)
+        self.config.update(config or {})
+        self.inputs = dict(inputs)
+        self.outputs = {}
+        self.input_ports, self.output_ports = [], []
+        for hook in (self.validate, self.define):
+            result = hook()
+            if result != Result.SUCCESS:
+                self.state = "errored"
+                self.outputs = {}
+                return result
+        # Input checks (src/module.cc:134-158): every declared input present and resolved, same
+        # device, contiguous unless DISCONTIGUOUS is declared.
+        for port in self.input_ports:
+            link = self.inputs.get(port)
+            if link is None or not link.resolved():
+                self.state = "incomplete"
+                _error(f"[MODULE] Input '{port}' of '{name}' is not connected.")
+                return Result.INCOMPLETE
+            if not (self.taint & Taint.DISCONTIGUOUS) and not link.tensor.contiguous():
+                self.state = "errored"
+                return _error(f"[MODULE] Input '{port}' of '{name}' is not contiguous.")
+        result = self.create_impl()
+        if result != Result.SUCCESS:
+            self.state = "errored"
+            self.outputs = {}
+            return result
+        self.state = "created"
+        return Result.SUCCESS
+
+    def reconfigure(self, candidate: Dict[str, object]) -> Result:
+        unknown = set(candidate) - set(self.DEFAULTS)
+        if unknown:
+            return _error(f"[MODULE_{self.TYPE.upper()}] Unknown config field(s): {sorted(unknown)}")
+        merged = dict(self.config)
+        merged.update(candidate)
+        result = self.reconfigure_impl(merged)
+        if result == Result.SUCCESS:
+            self.config = merged
+        return result
+
+
+_REGISTRY: Dict[Tuple[str, str, str, str], Callable[[], Module]] = {}
+
+
+def register_module(cls):
+    """JST_REGISTER_MODULE(impl, device, runtime, provider) — duplicates are rejected (src/registry.cc:241-251)."""
+    key = (cls.TYPE, cls.device_type, cls.runtime_type, cls.provider)
+    if key in _REGISTRY:
+        raise ValueError(f"duplicate module registration {key}")
+    _REGISTRY[key] = cls
+    return cls
+
+
+def build_module(type_: str, device: str = "cuda", runtime: str = "native", provider: str = "b200") -> Module:
+    """Registry::BuildModule: exact 4-key match (src/registry.cc:583-622)."""
+    key = (type_, device, runtime, provider)
+    if key not in _REGISTRY:
+        raise KeyError(f"no module registered for {key}")
+    return _REGISTRY[key]()
+
+
+def list_available_modules(type_: str) -> List[Tuple[str, str, str, str]]:
+    return [k for k in _REGISTRY if k[0] == type_]
+
+
+def _lib():
+    return _native.load()
+
+
+def _call(fn_name: str, *args) -> Result:
+    """One C-ABI call; maps a non-zero Result to the reference's error convention."""
+    rc = getattr(_lib(), fn_name)(*args)
+    if rc != 0:
+        _last_error[0] = _lib().b200_last_error().decode(errors="replace")
+        return Result(rc) if rc in Result._value2member_map_ else Result.ERROR
+    return Result.SUCCESS
+
+
+def _require_cuda(module: Module, *tensors: Tensor) -> Optional[Result]:
+    for t in tensors:
+        if t.device.type != "cuda":
+            return _error(f"[MODULE_{module.TYPE.upper()}_B200] tensor is on '{t.device}', not a CUDA device; "
+                          "this provider has no CPU path.")
+    return None
+
+
+def _u64_array(values: Sequence[int]):
+    return (ctypes.c_uint64 * len(values))(*[int(v) for v in values])
+
+
+# ---------------------------------------------------------------------------------------------
+# Modules on the hot path (type strings / config fields / ports: SURVEY.md Appendix C)
+# ---------------------------------------------------------------------------------------------
+
+@register_module
+class Window(Module):
+    """`window` — src/domains/dsp/window/module_impl.cc:8-36 (+ native_cpu.cc:20-37)."""
+    TYPE = "window"
+    DEFAULTS = {"size": 1024}
+
+    def validate(self):
+        if int(self.config["size"]) == 0:
+            return _error("[MODULE_WINDOW] Window size cannot be zero.")
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.STATIC_OUTPUT)
+        return self.define_interface_output("window")
+
+    def create_impl(self):
+        self.output = Tensor.create(self.alloc_device, "CF32", (int(self.config["size"]),))
+        self.output.set_attribute("sampleAxis", 0)
+        self.outputs["window"] = TensorLink()
+        self.outputs["window"].produced(self.name, "window", self.output)
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.output)
+        if err:
+            return err
+        ctx = Context.get(self.output.device)
+        return _call("b200_window_blackman_cf32", ctx.handle, self.output.ptr(), self.output.size, stream)
+
+
+@register_module
+class Invert(Module):
+    """`invert` — src/domains/dsp/invert/module_impl.cc + native_cpu.cc:78-103."""
+    TYPE = "invert"
+
+    def validate(self):
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        if t.dtype != "CF32":
+            return _error(f"[MODULE_INVERT_B200] Unsupported input data type: {t.dtype}.")
+        axes = resolve_signal_axes(t)
+        if axes is None:
+            return _error("[MODULE_INVERT] Input must contain valid signal axis metadata.")
+        self._axis = axes.sample
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.DISCONTIGUOUS | Taint.STATELESS)
+        self.define_interface_input("signal")
+        return self.define_interface_output("signal")
+
+    def create_impl(self):
+        self.input = self.inputs["signal"].tensor
+        if not self.input.contiguous():
+            return _error("[MODULE_INVERT_B200] Strided inputs are not supported by this provider yet.")
+        self.output = Tensor.create(self.input.device, "CF32", self.input.shape)
+        self.output.propagate_attributes(self.input)
+        self.outputs["signal"] = TensorLink()
+        self.outputs["signal"].produced(self.name, "signal", self.output)
+        shape = self.input.shape
+        self._outer = int(np.prod(shape[:self._axis], dtype=np.int64)) if self._axis > 0 else 1
+        self._n = shape[self._axis]
+        self._inner = int(np.prod(shape[self._axis + 1:], dtype=np.int64)) if self._axis + 1 < len(shape) else 1
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.output)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        return _call("b200_invert_cf32", ctx.handle, self.input.ptr(), self.output.ptr(), self._outer, self._n,
+                     self._inner, stream)
+
+
+def _parse_shape(text) -> Optional[List[int]]:
+    if isinstance(text, (list, tuple)):
+        return [int(v) for v in text]
+    body = str(text).strip()
+    if not (body.startswith("[") and body.endswith("]")):
+        return None
+    body = body[1:-1].strip()
+    if not body:
+        return []
+    try:
+        return [int(v) for v in body.split(",")]
+    except ValueError:
+        return None
+
+
+@register_module
+class Reshape(Module):
+    """`reshape` — zero-copy view (src/domains/core/reshape/module_impl.cc); bit-exact by construction."""
+    TYPE = "reshape"
+    DEFAULTS = {"shape": "[]"}
+
+    def define(self):
+        self.define_interface_input("buffer")
+        return self.define_interface_output("buffer")
+
+    def create_impl(self):
+        source = self.inputs["buffer"].tensor
+        shape = _parse_shape(self.config["shape"])
+        if shape is None or int(np.prod(shape, dtype=np.int64)) != source.size:
+            return _error(f"[MODULE_RESHAPE] Cannot reshape {source.shape} into {self.config['shape']}.")
+        self.output = Tensor(source.data.view(tuple(shape)), {})
+        # Attributes do not survive a reshape unless the rank is unchanged.
+        if len(shape) == source.rank:
+            self.output.propagate_attributes(source)
+        self.outputs["buffer"] = TensorLink()
+        self.outputs["buffer"].produced(self.name, "buffer", self.output)
+        return Result.SUCCESS
+
+
+@register_module
+class Cast(Module):
+    """`cast` — bypass (alias) when the dtype already matches (src/domains/core/cast/module_impl.cc:23,98-101);
+    F32 -> CF32 otherwise."""
+    TYPE = "cast"
+    DEFAULTS = {"outputType": "CF32"}
+
+    def validate(self):
+        if self.config["outputType"] not in ("CF32", "F32"):
+            return _error(f"[MODULE_CAST_B200] Unsupported output type '{self.config['outputType']}'.")
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.DISCONTIGUOUS | Taint.STATELESS)
+        self.define_interface_input("buffer")
+        return self.define_interface_output("buffer")
+
+    def create_impl(self):
+        self.input = self.inputs["buffer"].tensor
+        self.bypass = self.input.dtype == self.config["outputType"]
+        if self.bypass:
+            self.output = self.input.clone()
+        else:
+            if not (self.input.dtype == "F32" and self.config["outputType"] == "CF32"):
+                return _error(f"[MODULE_CAST_B200] Unsupported cast {self.input.dtype} -> {self.config['outputType']}.")
+            self.output = Tensor.create(self.input.device, "CF32", self.input.shape)
+            self.output.propagate_attributes(self.input)
+        self.outputs["buffer"] = TensorLink()
+        self.outputs["buffer"].produced(self.name, "buffer", self.output)
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        if self.bypass:
+            return Result.SUCCESS
+        err = _require_cuda(self, self.input, self.output)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        return _call("b200_cast_f32_cf32", ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size, stream)
+
+
+def merge_broadcast_signal_axes(a: Tensor, b: Tensor, rank: int) -> Dict[str, int]:
+    """Signal axes of a broadcast result: right-aligned union, `a` wins on conflicts."""
+    merged: Dict[str, int] = {}
+    for t in (b, a):
+        shift = rank - t.rank
+        for key in ("sampleAxis", "batchAxis", "channelAxis"):
+            if t.has_attribute(key):
+                merged[key] = int(t.attribute(key)) + shift
+    return merged
+
+
+@register_module
+class Multiply(Module):
+    """`multiply` — NumPy-style broadcast product (src/domains/core/multiply/module_impl.cc:28-112)."""
+    TYPE = "multiply"
+
+    def validate(self):
+        la, lb = self.inputs.get("a"), self.inputs.get("b")
+        self._plan = None
+        if not la or not lb or not la.resolved() or not lb.resolved():
+            return Result.SUCCESS
+        a, b = la.tensor, lb.tensor
+        if a.size == 0 or b.size == 0:
+            return Result.SUCCESS
+        if a.dtype != b.dtype:
+            return _error(f"[MODULE_MULTIPLY] Input data types differ: {a.dtype} vs {b.dtype}.")
+        rank = max(a.rank, b.rank, 1)
+        shape = [1] * rank
+        for i in range(rank):
+            da = a.shape[a.rank - 1 - i] if a.rank > i else 1
+            db = b.shape[b.rank - 1 - i] if b.rank > i else 1
+            if da != db and da != 1 and db != 1:
+                return _error(f"[MODULE_MULTIPLY] Input shapes {list(a.shape)} and {list(b.shape)} are not broadcastable.")
+            shape[rank - 1 - i] = max(da, db)
+        self._plan = tuple(shape)
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.DISCONTIGUOUS | Taint.STATELESS)
+        self.define_interface_output("product")
+        self.define_interface_input("a")
+        return self.define_interface_input("b")
+
+    def create_impl(self):
+        if self._plan is None:
+            return _error("[MODULE_MULTIPLY] Inputs are empty.")
+        self.a = self.inputs["a"].tensor
+        self.b = self.inputs["b"].tensor
+        shape = self._plan
+        self.view_a = self.a.data.broadcast_to(shape)
+        self.view_b = self.b.data.broadcast_to(shape)
+        self.c = Tensor.create(self.a.device, self.a.dtype, shape)
+        self.c.propagate_attributes(self.a)
+        self.c.attributes.update(merge_broadcast_signal_axes(self.a, self.b, len(shape)))
+        self.outputs["product"] = TensorLink()
+        self.outputs["product"].produced(self.name, "product", self.c)
+        self._shape = _u64_array(shape)
+        self._stride_a = _u64_array(self.view_a.stride())
+        self._stride_b = _u64_array(self.view_b.stride())
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.a, self.b, self.c)
+        if err:
+            return err
+        ctx = Context.get(self.a.device)
+        fn = "b200_multiply_cf32" if self.a.dtype == "CF32" else "b200_multiply_f32"
+        return _call(fn, ctx.handle, ctypes.c_void_p(self.view_a.data_ptr()), ctypes.c_void_p(self.view_b.data_ptr()),
+                     self.c.ptr(), len(self._plan), self._shape, self._stride_a, self._stride_b, stream)
+
+
+@register_module
+class MultiplyConstant(Module):
+    """`multiply_constant` — src/domains/core/multiply_constant/module_impl_native_cpu.cc:82-100."""
+    TYPE = "multiply_constant"
+    DEFAULTS = {"constant": 1.0}
+
+    def define(self):
+        self.define_interface_input("factor")
+        return self.define_interface_output("product")
+
+    def create_impl(self):
+        self.input = self.inputs["factor"].tensor
+        self.output = Tensor.create(self.input.device, self.input.dtype, self.input.shape)
+        self.output.propagate_attributes(self.input)
+        self.outputs["product"] = TensorLink()
+        self.outputs["product"].produced(self.name, "product", self.output)
+        return Result.SUCCESS
+
+    def reconfigure_impl(self, candidate):
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.output)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        fn = "b200_multiply_constant_cf32" if self.input.dtype == "CF32" else "b200_multiply_constant_f32"
+        return _call(fn, ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size,
+                     ctypes.c_float(float(self.config["constant"])), stream)
+
+
+@register_module
+class Fft(Module):
+    """`fft` — src/domains/dsp/fft/module_impl.cc:8-96; C2C along the sample axis, unnormalised."""
+    TYPE = "fft"
+    DEFAULTS = {"forward": True, "complexOutput": False}
+
+    def __init__(self):
+        super().__init__()
+        self._plan_handle = None
+
+    def validate(self):
+        self._axis = None
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        if t.dtype not in ("F32", "CF32"):
+            return _error(f"[MODULE_FFT_B200] Unsupported input data type: {t.dtype}.")
+        axes = resolve_signal_axes(t)
+        if axes is None:
+            return _error("[MODULE_FFT] Input must contain valid signal axis metadata.")
+        if t.dtype != "CF32":
+            return _error("[MODULE_FFT_B200] Real-input transforms (R2C / FFTPACK R2R) are not implemented by "
+                          "this provider yet; cast to CF32 first.")
+        if axes.sample != t.rank - 1:
+            return _error("[MODULE_FFT_B200] Transforms along a non-innermost axis are not implemented by this "
+                          "provider yet.")
+        self._axis = axes.sample
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.DISCONTIGUOUS | Taint.STATELESS)
+        self.define_interface_input("signal")
+        return self.define_interface_output("signal")
+
+    def create_impl(self):
+        self.input = self.inputs["signal"].tensor
+        if not self.input.contiguous():
+            return _error("[MODULE_FFT_B200] Strided inputs are not supported by this provider yet.")
+        self.output = Tensor.create(self.input.device, "CF32", self.input.shape)
+        self.output.propagate_attributes(self.input)
+        self.outputs["signal"] = TensorLink()
+        self.outputs["signal"].produced(self.name, "signal", self.output)
+        self._n = self.input.shape[self._axis]
+        self._batch = self.input.size // self._n
+        return Result.SUCCESS
+
+    def compute_initialize(self):
+        err = _require_cuda(self, self.input)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        handle = ctypes.c_void_p()
+        result = _call("b200_fft_plan_c2c", ctx.handle, self._n, self._batch, ctypes.byref(handle))
+        if result == Result.SUCCESS:
+            self._plan_handle = handle
+        return result
+
+    def compute_submit(self, stream):
+        if self._plan_handle is None:
+            result = self.compute_initialize()
+            if result != Result.SUCCESS:
+                return result
+        return _call("b200_fft_exec", self._plan_handle, self.input.ptr(), self.output.ptr(),
+                     1 if self.config["forward"] else 0, stream)
+
+    def compute_deinitialize(self):
+        if self._plan_handle is not None:
+            _call("b200_fft_plan_destroy", self._plan_handle)
+            self._plan_handle = None
+        return Result.SUCCESS
+
+    def destroy(self):
+        return self.compute_deinitialize()
+
+
+def amplitude_scaling_coeff(n: int) -> float:
+    """scalingCoeff = 20 * log10f(1 / (F32)N) (src/domains/dsp/amplitude/module_impl.cc:49-51), in F32."""
+    return float(np.float32(20.0) * np.log10(np.float32(1.0) / np.float32(n), dtype=np.float32))
+
+
+@register_module
+class Amplitude(Module):
+    """`amplitude` — src/domains/dsp/amplitude/module_impl.cc:8-66 (+ native_cpu.cc:73-99)."""
+    TYPE = "amplitude"
+
+    def validate(self):
+        self._norm = 1
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved():
+            return Result.SUCCESS
+        t = link.tensor
+        if t.size == 0:
+            return Result.SUCCESS
+        if t.dtype not in ("F32", "CF32"):
+            return _error(f"[MODULE_AMPLITUDE_B200] Unsupported input data type: {t.dtype}.")
+        sample = t.attribute("sampleAxis") if t.has_attribute("sampleAxis") else (0 if t.rank == 1 else None)
+        channel = t.attribute("channelAxis") if t.has_attribute("channelAxis") else None
+        if sample is None and channel is None:
+            return _error("[MODULE_AMPLITUDE] Input must contain sampleAxis or channelAxis metadata.")
+        if sample is not None:
+            if not (0 <= sample < t.rank):
+                return _error("[MODULE_AMPLITUDE] Input must contain valid signal axis metadata.")
+            self._norm = t.shape[sample]
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.DISCONTIGUOUS | Taint.STATELESS)
+        self.define_interface_input("signal")
+        return self.define_interface_output("signal")
+
+    def create_impl(self):
+        self.input = self.inputs["signal"].tensor
+        if not self.input.contiguous():
+            return _error("[MODULE_AMPLITUDE_B200] Strided inputs are not supported by this provider yet.")
+        self.scaling_coeff = amplitude_scaling_coeff(self._norm)
+        self.output = Tensor.create(self.input.device, "F32", self.input.shape)
+        self.output.propagate_attributes(self.input)
+        self.outputs["signal"] = TensorLink()
+        self.outputs["signal"].produced(self.name, "signal", self.output)
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.output)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        fn = "b200_amplitude_cf32" if self.input.dtype == "CF32" else "b200_amplitude_f32"
+        return _call(fn, ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size,
+                     ctypes.c_float(self.scaling_coeff), stream)
+
+
+def range_coefficients(lo: float, hi: float) -> Tuple[float, float]:
+    """RangeImpl::updateCoefficients (src/domains/core/range/module_impl.cc:51-63), F32 arithmetic."""
+    lower = np.float32(min(lo, hi))
+    upper = np.float32(max(lo, hi))
+    if lower == upper:
+        return 0.0, 0.5
+    scale = np.float32(1.0) / (upper - lower)
+    offset = -lower * scale
+    return float(scale), float(offset)
+
+
+@register_module
+class Range(Module):
+    """`range` (the chain's "Scale") — src/domains/core/range/module_impl.cc:7-63 (+ native_cpu.cc:67-82)."""
+    TYPE = "range"
+    DEFAULTS = {"min": -1.0, "max": 1.0}
+
+    def validate(self):
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        if link.tensor.dtype != "F32":
+            return _error(f"[MODULE_RANGE_B200] Unsupported data type '{link.tensor.dtype}'.")
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.DISCONTIGUOUS | Taint.STATELESS)
+        self.define_interface_output("signal")
+        return self.define_interface_input("signal")
+
+    def create_impl(self):
+        self.input = self.inputs["signal"].tensor
+        if not self.input.contiguous():
+            return _error("[MODULE_RANGE_B200] Strided inputs are not supported by this provider yet.")
+        self.scale, self.offset = range_coefficients(float(self.config["min"]), float(self.config["max"]))
+        self.output = Tensor.create(self.input.device, "F32", self.input.shape)
+        self.output.propagate_attributes(self.input)
+        self.outputs["signal"] = TensorLink()
+        self.outputs["signal"].produced(self.name, "signal", self.output)
+        return Result.SUCCESS
+
+    def reconfigure_impl(self, candidate):  # in-place (module_impl.cc:40-49)
+        self.scale, self.offset = range_coefficients(float(candidate["min"]), float(candidate["max"]))
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.output)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        return _call("b200_range_f32", ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size,
+                     ctypes.c_float(self.scale), ctypes.c_float(self.offset), stream)
+
+
+@register_module
+class SpectralChain(Module):
+    """`spectral_chain` — B200-only fused module: multiply(window) -> fft -> amplitude -> [range] in one
+    kernel (b200_chain_exec). It is what the `spectrum_engine` block creates on this provider instead of
+    the 9-module chain of src/domains/dsp/spectrum_engine/block_impl.cc:120-217. Inputs: `buffer`
+    (CF32, sample axis innermost) and `window` (CF32 [n], the settled window->invert output)."""
+    TYPE = "spectral_chain"
+    DEFAULTS = {"enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0}
+
+    def __init__(self):
+        super().__init__()
+        self._plan_handle = None
+
+    def validate(self):
+        link = self.inputs.get("buffer")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        if t.dtype != "CF32":
+            return _error("[MODULE_SPECTRAL_CHAIN_B200] Input must have data type CF32.")
+        axes = resolve_signal_axes(t)
+        if axes is None:
+            return _error("[MODULE_SPECTRAL_CHAIN_B200] Input signal axis metadata is invalid.")
+        if axes.sample != t.rank - 1:
+            return _error("[MODULE_SPECTRAL_CHAIN_B200] The sample axis must be the innermost axis.")
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.STATELESS)
+        self.define_interface_input("buffer")
+        self.define_interface_input("window")
+        return self.define_interface_output("buffer")
+
+    def create_impl(self):
+        self.input = self.inputs["buffer"].tensor
+        self.window = self.inputs["window"].tensor
+        self._n = self.input.shape[-1]
+        if self.window.dtype != "CF32" or self.window.size != self._n:
+            return _error("[MODULE_SPECTRAL_CHAIN_B200] Window must be CF32 with one tap per sample.")
+        self._batch = self.input.size // self._n
+        self.amp_coeff = amplitude_scaling_coeff(self._n)
+        self.scale, self.offset = range_coefficients(float(self.config["rangeMin"]), float(self.config["rangeMax"]))
+        self.output = Tensor.create(self.input.device, "F32", self.input.shape)
+        self.output.propagate_attributes(self.input)
+        self.outputs["buffer"] = TensorLink()
+        self.outputs["buffer"].produced(self.name, "buffer", self.output)
+        return Result.SUCCESS
+
+    def reconfigure_impl(self, candidate):
+        if bool(candidate["enableScale"]) != bool(self.config["enableScale"]):
+            return Result.RECREATE
+        self.scale, self.offset = range_coefficients(float(candidate["rangeMin"]), float(candidate["rangeMax"]))
+        return Result.SUCCESS
+
+    def _create_plan(self):
+        # The window input is a settled STATIC_OUTPUT tensor produced earlier in this same cycle on this
+        # same stream (window -> invert run before us): wait for it, then let the plan capture it.
+        err = _require_cuda(self, self.input, self.window)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        handle = ctypes.c_void_p()
+        torch.cuda.current_stream(self.input.device).synchronize()
+        result = _call("b200_chain_plan_create", ctx.handle, self._n, self._batch, self.window.ptr(),
+                       ctypes.byref(handle))
+        if result == Result.SUCCESS:
+            self._plan_handle = handle
+        return result
+
+    def compute_submit(self, stream):
+        if self._plan_handle is None:
+            result = self._create_plan()
+            if result != Result.SUCCESS:
+                return result
+        return _call("b200_chain_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), self._batch,
+                     ctypes.c_float(self.amp_coeff), 1 if self.config["enableScale"] else 0,
+                     ctypes.c_float(self.scale), ctypes.c_float(self.offset), stream)
+
+    def compute_deinitialize(self):
+        if self._plan_handle is not None:
+            _call("b200_chain_plan_destroy", self._plan_handle)
+            self._plan_handle = None
+        return Result.SUCCESS
+
+    def destroy(self):
+        return self.compute_deinitialize()
+
+
+# ---------------------------------------------------------------------------------------------
+# Runtime (per device x runtime segment) — src/runtime/native/cuda/impl.cc
+# ---------------------------------------------------------------------------------------------
+
+class NativeCudaRuntime:
+    """Owns one non-blocking stream, calls each module's compute_submit(stream) in order, records a
+    CUDA-event pair per module, synchronises the stream once per cycle (impl.cc:185-272)."""
+
+    def __init__(self, name: str, device="cuda"):
+        self.name = name
+        self.device = torch.device(device)
+        self.modules: List[Module] = []
+        self.stream: Optional[torch.cuda.Stream] = None
+        self._events: Dict[str, Tuple[torch.cuda.Event, torch.cuda.Event]] = {}
+
+    def create(self, modules: Sequence[Module]) -> Result:
+        self.modules = list(modules)
+        if self.device.type == "cuda" and torch.cuda.is_available():
+            self.stream = torch.cuda.Stream(self.device)
+            for m in self.modules:
+                self._events[m.name] = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            with torch.cuda.stream(self.stream):
+                for m in self.modules:
+                    result = m.compute_initialize()
+                    if result not in (Result.SUCCESS, Result.RELOAD):
+                        return result
+        return Result.SUCCESS
+
+    def destroy(self) -> Result:
+        for m in self.modules:
+            m.compute_deinitialize()
+        self.modules = []
+        return Result.SUCCESS
+
+    def compute(self, pending: Sequence[str], skipped: set, failed: set) -> Result:
+        if self.stream is None:
+            _error("[RUNTIME_NATIVE_CUDA_B200] No CUDA device available; this runtime has no CPU path.")
+            failed.update(m.name for m in self.modules)
+            return Result.ERROR
+        ran: List[Module] = []
+        overall = Result.SUCCESS
+        stream_ptr = ctypes.c_void_p(self.stream.cuda_stream)
+        with torch.cuda.stream(self.stream):
+            for m in self.modules:
+                if pending and m.name not in pending:
+                    continue
+                upstream_skipped = any(l.producer and l.producer[0] in skipped for l in m.inputs.values())
+                upstream_failed = any(l.producer and l.producer[0] in failed for l in m.inputs.values())
+                if upstream_failed:
+                    failed.add(m.name)
+                    continue
+                if upstream_skipped:
+                    skipped.add(m.name)
+                    continue
+                start, end = self._events[m.name]
+                start.record(self.stream)
+                result = m.compute_submit(stream_ptr)
+                end.record(self.stream)
+                if result in (Result.SUCCESS, Result.RELOAD):
+                    ran.append(m)
+                elif result == Result.SKIP:
+                    skipped.add(m.name)
+                elif result in (Result.YIELD, Result.TIMEOUT):
+                    overall = result
+                    break
+                else:
+                    failed.add(m.name)
+                    overall = Result.ERROR
+        self.stream.synchronize()
+        for m in ran:
+            start, end = self._events[m.name]
+            m.cycles += 1
+            m.compute_time_ms = start.elapsed_time(end)
+        return overall
+
+
+# ---------------------------------------------------------------------------------------------
+# Scheduler (synchronous) — src/scheduler_synchronous.cc
+# ---------------------------------------------------------------------------------------------
+
+class SynchronousScheduler:
+    """Kahn topological order over producer/consumer links, one runtime per (device, runtime) segment,
+    static settlement: STATIC_OUTPUT modules — and modules all of whose inputs are settled — run once."""
+
+    def __init__(self, device="cuda"):
+        self.device = device
+        self.modules: Dict[str, Module] = {}
+        self.order: List[Module] = []
+        self.settled: set = set()
+        self.runtime: Optional[NativeCudaRuntime] = None
+
+    def add(self, module: Module) -> Result:
+        if module.name in self.modules:
+            return _error(f"[SCHEDULER] Module '{module.name}' already present.")
+        self.modules[module.name] = module
+        return self._rebuild()
+
+    def remove(self, module: Module) -> Result:
+        self.modules.pop(module.name, None)
+        return self._rebuild()
+
+    def _rebuild(self) -> Result:
+        indegree = {name: 0 for name in self.modules}
+        consumers: Dict[str, List[str]] = {name: [] for name in self.modules}
+        for name, m in self.modules.items():
+            for link in m.inputs.values():
+                if link.producer and link.producer[0] in self.modules and link.producer[0] != name:
+                    indegree[name] += 1
+                    consumers[link.producer[0]].append(name)
+        ready = [n for n in self.modules if indegree[n] == 0]
+        order: List[str] = []
+        while ready:
+            n = ready.pop(0)
+            order.append(n)
+            for c in consumers[n]:
+                indegree[c] -= 1
+                if indegree[c] == 0:
+                    ready.append(c)
+        if len(order) != len(self.modules):
+            return _error("[SCHEDULER] Cycle detected in module graph.")
+        self.order = [self.modules[n] for n in order]
+        self.settled = set()
+        if self.runtime is not None:
+            self.runtime.destroy()
+        self.runtime = NativeCudaRuntime("segment0", self.device)
+        return self.runtime.create(self.order)
+
+    def is_static(self, module: Module) -> bool:
+        if module.taint & Taint.STATIC_OUTPUT:
+            return True
+        producers = [l.producer[0] for l in module.inputs.values() if l.producer]
+        if not producers or not all(p in self.modules for p in producers):
+            return False
+        return all(self.is_static(self.modules[p]) for p in producers)
+
+    def compute(self, failed: Optional[set] = None) -> Result:
+        failed = failed if failed is not None else set()
+        skipped: set = set()
+        pending = [m.name for m in self.order if m.name not in self.settled]
+        if not pending:
+            return Result.SUCCESS
+        result = self.runtime.compute(pending, skipped, failed)
+        for m in self.order:
+            if m.name in pending and m.name not in failed and m.name not in skipped and self.is_static(m):
+                self.settled.add(m.name)
+        return result
+
+
+# ---------------------------------------------------------------------------------------------
+# TestContext — src/testing.cc (one module, one runtime, CPU arrays in / out)
+# ---------------------------------------------------------------------------------------------
+
+class TestContext:
+    __test__ = False  # not a pytest class
+
+    def __init__(self, module_type: str, device: str = "cuda", runtime: str = "native", provider: str = "b200"):
+        self.module_type, self.device, self.runtime_type, self.provider = module_type, device, runtime, provider
+        self.inputs: Dict[str, Tensor] = {}
+        self.config: Dict[str, object] = {}
+        self.module: Optional[Module] = None
+        self.runtime: Optional[NativeCudaRuntime] = None
+        self.outputs: Dict[str, np.ndarray] = {}
+        self.output_tensors: Dict[str, Tensor] = {}
+
+    def set_input(self, name: str, array: np.ndarray, **axes):
+        target = self.device if (self.device != "cuda" or torch.cuda.is_available()) else "cpu"
+        self.inputs[name] = Tensor.from_numpy(array, device=target, **axes)
+
+    def set_config(self, **config):
+        self.config = dict(config)
+
+    def start(self) -> Result:
+        self.module = build_module(self.module_type, self.device, self.runtime_type, self.provider)
+        links = {}
+        for name, tensor in self.inputs.items():
+            link = TensorLink()
+            link.produced("test", name, tensor)
+            link.producer = None
+            links[name] = link
+        result = self.module.create("test", self.config, links)
+        if result != Result.SUCCESS:
+            return result
+        self.runtime = NativeCudaRuntime("test", self.device)
+        return self.runtime.create([self.module])
+
+    def compute(self) -> Result:
+        result = self.runtime.compute([], set(), set())
+        if result != Result.SUCCESS:
+            return result
+        for port, link in self.module.outputs.items():
+            self.output_tensors[port] = link.tensor
+            self.outputs[port] = link.tensor.numpy()
+        return Result.SUCCESS
+
+    def stop(self) -> Result:
+        if self.runtime:
+            self.runtime.destroy()
+            self.runtime = None
+        if self.module:
+            self.module.destroy()
+            self.module = None
+        return Result.SUCCESS
+
+    def run(self) -> Result:
+        result = self.start()
+        if result == Result.SUCCESS:
+            result = self.compute()
+        self.stop()
+        return result
+
+    def output(self, name: str) -> np.ndarray:
+        return self.outputs[name]

@@ -1,0 +1,141 @@
+/* libb200dsp — Blackwell (sm_100a) compute backend for the Jetstream DSP module compute() path.
+ *
+ * Pure C ABI: POD arguments only, no C++/torch types. Every entry point
+ *   - returns an int that follows the reference's `Result` numbering
+ *     (include/jetstream/types.hh:19-30): 0 SUCCESS, 1 ERROR, 3 FATAL;
+ *   - never throws, never synchronises the stream it is given (except the *_create/_destroy,
+ *     malloc/free and explicit *_synchronize calls), and never touches host copies of tensors;
+ *   - leaves ownership of every buffer with the caller (device pointers unless stated).
+ * `b200_last_error()` returns the thread-local text of the last failure — the string the
+ * reference-side shim forwards to JST_ERROR (include/jetstream/logger.hh).
+ *
+ * Each function names the reference interface (path:line under the reference tree) whose
+ * computeSubmit()/create() work it replaces. The reference-side binding is in INTEGRATION.md.
+ */
+#ifndef B200DSP_H
+#define B200DSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_SUCCESS 0
+#define B200_ERROR   1
+#define B200_FATAL   3
+
+typedef struct b200_ctx b200_ctx;                 /* one per device (replaces Backend::State<CUDA>) */
+typedef struct b200_fft_plan b200_fft_plan;
+typedef struct b200_chain_plan b200_chain_plan;
+typedef struct b200_fir_plan b200_fir_plan;
+typedef struct b200_fm_plan b200_fm_plan;
+typedef void* b200_stream;                        /* cudaStream_t; NULL = legacy default stream */
+typedef struct { float re, im; } b200_cf32;       /* CF32 = std::complex<float> layout */
+
+/* ---- backend / memory ------------------------------------------------------------------ */
+
+/* Library/ABI identification. */
+const char* b200_version(void);
+const char* b200_last_error(void);
+
+/* src/backend/devices/cuda/base.cc:9-149 (device discovery, one context per deviceId). */
+int b200_device_count(int* count);
+int b200_ctx_create(int device, b200_ctx** ctx);
+int b200_ctx_destroy(b200_ctx* ctx);
+int b200_ctx_device(const b200_ctx* ctx, int* device);
+int b200_ctx_sm_count(const b200_ctx* ctx, int* sms);
+
+/* src/memory/buffer_cuda.cc:31-124 (device allocation, zero-filled like cudaMemset at :119). */
+int b200_malloc(b200_ctx* ctx, uint64_t bytes, void** ptr);
+int b200_free(b200_ctx* ctx, void* ptr);
+/* Pinned host staging (the reference maps host tensors with cudaHostRegister, buffer_cuda.cc:188). */
+int b200_host_alloc(b200_ctx* ctx, uint64_t bytes, void** ptr);
+int b200_host_free(b200_ctx* ctx, void* ptr);
+/* Tensor::copyFrom, src/memory/buffer_cuda.cc:284-306. kind: 0 h2d, 1 d2h, 2 d2d. Async on stream. */
+int b200_memcpy(b200_ctx* ctx, void* dst, const void* src, uint64_t bytes, int kind, b200_stream stream);
+int b200_memset(b200_ctx* ctx, void* dst, int value, uint64_t bytes, b200_stream stream);
+
+/* src/runtime/native/cuda/impl.cc:35-118 (one non-blocking stream per runtime segment; sync at :244). */
+int b200_stream_create(b200_ctx* ctx, b200_stream* stream);
+int b200_stream_destroy(b200_ctx* ctx, b200_stream stream);
+int b200_stream_synchronize(b200_ctx* ctx, b200_stream stream);
+
+/* ---- module compute(): one call per reference computeSubmit() --------------------------- */
+
+/* window — src/domains/dsp/window/module_impl_native_cpu.cc:20-37.
+ * Blackman taps evaluated in F64, stored as CF32 (imag 0); n == 1 -> 1+0i. out: [n] CF32. */
+int b200_window_blackman_cf32(b200_ctx* ctx, b200_cf32* out, uint64_t n, b200_stream stream);
+
+/* invert — src/domains/dsp/invert/module_impl_native_cpu.cc:78-103.
+ * out = in * (-1)^k along an axis of even length `n` (k = axis coordinate), or the F64-evaluated
+ * phasor exp(j*2*pi*floor(n/2)*k/n) for odd n. Tensor viewed as [outer, n, inner], contiguous. */
+int b200_invert_cf32(b200_ctx* ctx, const b200_cf32* in, b200_cf32* out,
+                     uint64_t outer, uint64_t n, uint64_t inner, b200_stream stream);
+
+/* multiply — src/domains/core/multiply/module_impl_native_cpu.cc:86-100 with the NumPy broadcast
+ * plan of module_impl.cc:28-83. Strides are in ELEMENTS of the broadcast views (0 on broadcast
+ * dims), rank <= 8; c is contiguous row-major over `shape`. */
+int b200_multiply_cf32(b200_ctx* ctx, const b200_cf32* a, const b200_cf32* b, b200_cf32* c,
+                       int rank, const uint64_t* shape, const uint64_t* stride_a,
+                       const uint64_t* stride_b, b200_stream stream);
+int b200_multiply_f32(b200_ctx* ctx, const float* a, const float* b, float* c,
+                      int rank, const uint64_t* shape, const uint64_t* stride_a,
+                      const uint64_t* stride_b, b200_stream stream);
+
+/* multiply_constant — src/domains/core/multiply_constant/module_impl_native_cpu.cc:82-100. */
+int b200_multiply_constant_cf32(b200_ctx* ctx, const b200_cf32* in, b200_cf32* out, uint64_t count,
+                                float constant, b200_stream stream);
+int b200_multiply_constant_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count,
+                               float constant, b200_stream stream);
+
+/* fft — src/domains/dsp/fft/module_impl_native_cpu.cc:129-140 (pocketfft::c2c, scale 1.0 in both
+ * directions, forward sign exp(-j2*pi*kn/N)). Batched 1-D C2C over the last (contiguous) axis:
+ * in/out [batch, n] CF32; in == out allowed. Replaces cufftMakePlanMany64 + cufftExecC2C of
+ * src/domains/dsp/fft/module_impl_native_cuda.cc:321-333,433. */
+int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan** plan);
+int b200_fft_exec(b200_fft_plan* plan, const b200_cf32* in, b200_cf32* out, int forward,
+                  b200_stream stream);
+int b200_fft_plan_destroy(b200_fft_plan* plan);
+
+/* amplitude — src/domains/dsp/amplitude/module_impl_native_cpu.cc:73-99 with Backend::ApproxLog10
+ * (include/jetstream/backend/devices/cpu/helpers.hh:61-74): out = |x|==0 ? -inf :
+ * 20*ApproxLog10(|x|) + coeff, coeff = 20*log10f(1/N) (src/domains/dsp/amplitude/module_impl.cc:49-51).
+ * Same operation order as the reference, no FMA contraction: bit-identical for finite input. */
+int b200_amplitude_cf32(b200_ctx* ctx, const b200_cf32* in, float* out, uint64_t count, float coeff,
+                        b200_stream stream);
+int b200_amplitude_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, float coeff,
+                       b200_stream stream);
+
+/* range ("Scale") — src/domains/core/range/module_impl_native_cpu.cc:67-82:
+ * out = scale == 0 ? 0.5 : 0.5 + 0.5*tanhf(4*((in*scale + offset) - 0.5)); scale/offset from
+ * RangeImpl::updateCoefficients (src/domains/core/range/module_impl.cc:51-63). */
+int b200_range_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, float scale,
+                   float offset, b200_stream stream);
+
+/* cast F32 -> CF32 (imag 0) — src/domains/core/cast/module_impl_native_cpu.cc (CF32 input bypasses). */
+int b200_cast_f32_cf32(b200_ctx* ctx, const float* in, b200_cf32* out, uint64_t count, b200_stream stream);
+
+/* ---- fused spectral chain: the spectrum_engine block ------------------------------------ */
+
+/* Replaces the module sequence wired by SpectrumEngineImpl::create
+ * (src/domains/dsp/spectrum_engine/block_impl.cc:120-217): multiply(x, window) -> fft(forward) ->
+ * amplitude -> [range], in ONE kernel: x is read once (8 B/sample), the F32 result written once
+ * (4 B/sample). `window` is the [n] CF32 tensor the block's window->invert->reshape modules
+ * produce (already sign-flipped); it is captured at plan creation (static, settled output).
+ *   x   : [batch, n] CF32 contiguous, 16-byte aligned       out : [batch, n] F32
+ *   amp_coeff = 20*log10f(1/n); enable_range != 0 applies range(scale, offset).
+ * n must be a power of two, 8 <= n <= 65536 (n == 4096 runs the TMA-staged single-pass kernel). */
+int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const b200_cf32* window_dev,
+                           b200_chain_plan** plan);
+int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch,
+                    float amp_coeff, int enable_range, float scale, float offset, b200_stream stream);
+int b200_chain_plan_destroy(b200_chain_plan* plan);
+/* Name of the kernel variant exec() launches for this plan (for logs / profiles). */
+const char* b200_chain_plan_variant(const b200_chain_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* B200DSP_H */

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference CPU path (oracle/_ref/libjst_ref.so). Checker only."""
+    from oracle import ref as _ref
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libjst_ref.so not built (needs /root/reference at build time)")
+    return _ref
