@@ -20,7 +20,7 @@ namespace b200 {
 template <int MODE, int WIN, int BPT>
 __global__ void __launch_bounds__(1024) fft_generic_kernel(const FftParams p, const int log2n, const int tpr,
                                                           const int rows_per_cta) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* const sm = reinterpret_cast<float2*>(smem_raw);
     const uint32_t n = p.n;
     const uint32_t lane = threadIdx.x % tpr;
@@ -238,6 +238,13 @@ struct b200_chain_plan {
     float* win_re;    // non-null: window is purely real
     float2* win_c;    // non-null: general complex window
     const char* variant;
+    // Host-buffer pipeline (b200_chain_exec_host): kHostSlots device staging slots, three streams.
+    static constexpr int kHostSlots = 3;
+    uint64_t host_chunk_rows = 0;
+    float2* stage_in[kHostSlots] = {nullptr, nullptr, nullptr};
+    float* stage_out[kHostSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_h2d = nullptr, s_exec = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[kHostSlots] = {}, ev_exec[kHostSlots] = {}, ev_out[kHostSlots] = {};
 };
 
 extern "C" {
@@ -300,7 +307,14 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
                  "b200_chain_plan_create: n=%llu unsupported (power of two, 2..%llu in this build)",
                  static_cast<unsigned long long>(n), static_cast<unsigned long long>(kMaxGenericN));
     DeviceGuard guard(ctx);
-    auto* pl = new b200_chain_plan{ctx, n, max_batch, nullptr, nullptr, nullptr, ""};
+    auto* pl = new b200_chain_plan();
+    pl->ctx = ctx;
+    pl->n = n;
+    pl->max_batch = max_batch;
+    pl->twiddle = nullptr;
+    pl->win_re = nullptr;
+    pl->win_c = nullptr;
+    pl->variant = "";
     if (make_twiddle_table(ctx, n, &pl->twiddle) != B200_SUCCESS) {
         delete pl;
         return B200_ERROR;
@@ -349,16 +363,10 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
 
 const char* b200_chain_plan_variant(const b200_chain_plan* plan) { return plan ? plan->variant : ""; }
 
-int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch, float amp_coeff,
-                    int enable_range, float scale, float offset, b200_stream stream) {
-    B200_REQUIRE(plan, "b200_chain_exec: null plan");
-    if (batch == 0) {
-        return B200_SUCCESS;
-    }
-    B200_REQUIRE(x && out, "b200_chain_exec: null buffer");
-    DeviceGuard guard(plan->ctx);
+static int chain_launch(b200_chain_plan* plan, const float2* x, float* out, uint64_t batch, float amp_coeff,
+                        int enable_range, float scale, float offset, cudaStream_t s) {
     FftParams p{};
-    p.in = reinterpret_cast<const float2*>(x);
+    p.in = x;
     p.out = out;
     p.rows = batch;
     p.n = static_cast<uint32_t>(plan->n);
@@ -384,7 +392,6 @@ int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint6
             p.zero_value = 0.0f;
         }
     }
-    const cudaStream_t s = as_stream(stream);
     const int win = plan->win_re ? WIN_REAL : (plan->win_c ? WIN_COMPLEX : WIN_NONE);
 #define B200_CHAIN_DISPATCH(MODE)                                                   \
     switch (win) {                                                                  \
@@ -400,6 +407,90 @@ int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint6
 #undef B200_CHAIN_DISPATCH
 }
 
+int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch, float amp_coeff,
+                    int enable_range, float scale, float offset, b200_stream stream) {
+    B200_REQUIRE(plan, "b200_chain_exec: null plan");
+    if (batch == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(x && out, "b200_chain_exec: null buffer");
+    DeviceGuard guard(plan->ctx);
+    return chain_launch(plan, reinterpret_cast<const float2*>(x), out, batch, amp_coeff, enable_range, scale, offset,
+                        as_stream(stream));
+}
+
+int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* out_host, uint64_t batch,
+                         float amp_coeff, int enable_range, float scale, float offset, uint64_t chunk_rows) {
+    B200_REQUIRE(plan, "b200_chain_exec_host: null plan");
+    if (batch == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(x_host && out_host, "b200_chain_exec_host: null buffer");
+    DeviceGuard guard(plan->ctx);
+    if (chunk_rows == 0) {
+        chunk_rows = (128ull << 20) / (plan->n * sizeof(float2));  // 128 MiB of input per chunk
+        if (chunk_rows == 0) {
+            chunk_rows = 1;
+        }
+    }
+    if (chunk_rows > batch) {
+        chunk_rows = batch;
+    }
+    constexpr int kSlots = b200_chain_plan::kHostSlots;
+    if (plan->host_chunk_rows < chunk_rows) {
+        for (int i = 0; i < kSlots; ++i) {
+            cudaFree(plan->stage_in[i]);
+            cudaFree(plan->stage_out[i]);
+            plan->stage_in[i] = nullptr;
+            plan->stage_out[i] = nullptr;
+            B200_CUDA_CHECK(cudaMalloc(&plan->stage_in[i], chunk_rows * plan->n * sizeof(float2)));
+            B200_CUDA_CHECK(cudaMalloc(&plan->stage_out[i], chunk_rows * plan->n * sizeof(float)));
+        }
+        plan->host_chunk_rows = chunk_rows;
+    }
+    if (!plan->s_exec) {
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->s_h2d, cudaStreamNonBlocking));
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->s_exec, cudaStreamNonBlocking));
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < kSlots; ++i) {
+            B200_CUDA_CHECK(cudaEventCreateWithFlags(&plan->ev_in[i], cudaEventDisableTiming));
+            B200_CUDA_CHECK(cudaEventCreateWithFlags(&plan->ev_exec[i], cudaEventDisableTiming));
+            B200_CUDA_CHECK(cudaEventCreateWithFlags(&plan->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    const uint64_t chunks = (batch + chunk_rows - 1) / chunk_rows;
+    const float2* src = reinterpret_cast<const float2*>(x_host);
+    for (uint64_t c = 0; c < chunks; ++c) {
+        const int slot = static_cast<int>(c % kSlots);
+        const uint64_t row0 = c * chunk_rows;
+        const uint64_t rows = batch - row0 < chunk_rows ? batch - row0 : chunk_rows;
+        // H2D: the slot's input buffer is free once the kernel of chunk c - kSlots has run.
+        if (c >= kSlots) {
+            B200_CUDA_CHECK(cudaStreamWaitEvent(plan->s_h2d, plan->ev_exec[slot], 0));
+        }
+        B200_CUDA_CHECK(cudaMemcpyAsync(plan->stage_in[slot], src + row0 * plan->n, rows * plan->n * sizeof(float2),
+                                        cudaMemcpyHostToDevice, plan->s_h2d));
+        B200_CUDA_CHECK(cudaEventRecord(plan->ev_in[slot], plan->s_h2d));
+        // Kernel: needs the input, and the slot's output buffer drained by the D2H of chunk c - kSlots.
+        B200_CUDA_CHECK(cudaStreamWaitEvent(plan->s_exec, plan->ev_in[slot], 0));
+        if (c >= kSlots) {
+            B200_CUDA_CHECK(cudaStreamWaitEvent(plan->s_exec, plan->ev_out[slot], 0));
+        }
+        if (chain_launch(plan, plan->stage_in[slot], plan->stage_out[slot], rows, amp_coeff, enable_range, scale,
+                         offset, plan->s_exec) != B200_SUCCESS) {
+            return B200_ERROR;
+        }
+        B200_CUDA_CHECK(cudaEventRecord(plan->ev_exec[slot], plan->s_exec));
+        // D2H
+        B200_CUDA_CHECK(cudaStreamWaitEvent(plan->s_d2h, plan->ev_exec[slot], 0));
+        B200_CUDA_CHECK(cudaMemcpyAsync(out_host + row0 * plan->n, plan->stage_out[slot], rows * plan->n * sizeof(float),
+                                        cudaMemcpyDeviceToHost, plan->s_d2h));
+        B200_CUDA_CHECK(cudaEventRecord(plan->ev_out[slot], plan->s_d2h));
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(plan->s_d2h));
+    return B200_SUCCESS;
+}
+
 int b200_chain_plan_destroy(b200_chain_plan* plan) {
     if (!plan) {
         return B200_SUCCESS;
@@ -408,6 +499,20 @@ int b200_chain_plan_destroy(b200_chain_plan* plan) {
     cudaFree(plan->twiddle);
     cudaFree(plan->win_re);
     cudaFree(plan->win_c);
+    for (int i = 0; i < b200_chain_plan::kHostSlots; ++i) {
+        cudaFree(plan->stage_in[i]);
+        cudaFree(plan->stage_out[i]);
+        if (plan->s_exec) {
+            cudaEventDestroy(plan->ev_in[i]);
+            cudaEventDestroy(plan->ev_exec[i]);
+            cudaEventDestroy(plan->ev_out[i]);
+        }
+    }
+    if (plan->s_exec) {
+        cudaStreamDestroy(plan->s_h2d);
+        cudaStreamDestroy(plan->s_exec);
+        cudaStreamDestroy(plan->s_d2h);
+    }
     delete plan;
     return B200_SUCCESS;
 }

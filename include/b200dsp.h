@@ -125,11 +125,19 @@ int b200_cast_f32_cf32(b200_ctx* ctx, const float* in, b200_cf32* out, uint64_t 
  * produce (already sign-flipped); it is captured at plan creation (static, settled output).
  *   x   : [batch, n] CF32 contiguous, 16-byte aligned       out : [batch, n] F32
  *   amp_coeff = 20*log10f(1/n); enable_range != 0 applies range(scale, offset).
- * n must be a power of two, 8 <= n <= 65536 (n == 4096 runs the TMA-staged single-pass kernel). */
+ * n must be a power of two, 2 <= n <= 16384 in this build (n == 4096 runs the TMA-staged single-pass
+ * kernel, other sizes the shared-memory Stockham kernel with the same fused prologue/epilogue). */
 int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const b200_cf32* window_dev,
                            b200_chain_plan** plan);
 int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch,
                     float amp_coeff, int enable_range, float scale, float offset, b200_stream stream);
+/* Same computation for HOST-resident tensors (what the reference's TestContext hands a CUDA module:
+ * host memory mapped onto the device, src/testing.cc:136, src/memory/buffer_cuda.cc:188). x_host and
+ * out_host should be pinned (b200_host_alloc) for full PCIe rate. The batch is cut into chunks of
+ * `chunk_rows` rows (0 = 128 MiB of input) and pipelined H2D -> kernel -> D2H on three streams with three
+ * device staging slots. SYNCHRONOUS: returns when out_host is complete. */
+int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* out_host, uint64_t batch,
+                         float amp_coeff, int enable_range, float scale, float offset, uint64_t chunk_rows);
 int b200_chain_plan_destroy(b200_chain_plan* plan);
 /* Name of the kernel variant exec() launches for this plan (for logs / profiles). */
 const char* b200_chain_plan_variant(const b200_chain_plan* plan);

@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE — numpy restatement ("port") of the reference CPU algorithms on the hot path.
+
+Each function restates one reference `computeSubmit()` and cites it (paths under the reference tree,
+CyberEther/Jetstream v1.9.1). Arithmetic is carried out in the same precision and operation order as
+the reference (np.float32 scalars/arrays; F64 where the reference uses F64).
+
+Pinning: tests/test_oracle.py checks every function here against (i) the UNMODIFIED reference built by
+oracle/build_ref.sh (oracle/_ref/libjst_ref.so, when present), (ii) the golden vectors under tests/golden/
+generated from that library by tests/golden/generate.py, and (iii) the reference's own known-answer
+module tests restated in tests/test_reference_known_answers.py. Parity is therefore pinned.
+
+The FFT: the reference calls the vendored header-only pocketfft (src/domains/dsp/fft/pocketfft.hh) in
+single precision; numpy >= 2.0 ships the same pocketfft C++ templates and keeps complex64 in single
+precision, so `np.fft.fft` on complex64 input is the restatement of pocketfft::c2c.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+JST_PI = 3.14159265358979323846
+
+
+def window(n: int) -> np.ndarray:
+    """src/domains/dsp/window/module_impl_native_cpu.cc:20-37 — Blackman taps in F64, stored CF32."""
+    if n == 1:
+        return np.array([1 + 0j], dtype=np.complex64)
+    i = np.arange(n, dtype=np.float64)
+    tap = 0.42 - 0.50 * np.cos(2.0 * JST_PI * i / (n - 1)) + 0.08 * np.cos(4.0 * JST_PI * i / (n - 1))
+    return tap.astype(np.float32).astype(np.complex64)
+
+
+def invert(x: np.ndarray, axis: int = -1) -> np.ndarray:
+    """src/domains/dsp/invert/module_impl_native_cpu.cc:78-103 — (-1)^k along `axis` (even length), or the
+    F64-evaluated phasor exp(j 2 pi floor(N/2) k / N) for odd lengths."""
+    x = np.asarray(x, dtype=np.complex64)
+    n = x.shape[axis]
+    k = np.arange(n)
+    shape = [1] * x.ndim
+    shape[axis] = n
+    if n % 2 == 0:
+        sign = np.where(k % 2 == 1, F32(-1), F32(1)).astype(np.float32).reshape(shape)
+        return (x * sign).astype(np.complex64)   # exact sign flip
+    phase = 2.0 * JST_PI * float(n // 2) * k.astype(np.float64) / float(n)
+    w = (np.cos(phase).astype(np.float32) + 1j * np.sin(phase).astype(np.float32)).astype(np.complex64)
+    return multiply(x, w.reshape(shape))
+
+
+def multiply(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """src/domains/core/multiply/module_impl_native_cpu.cc:86-100 — NumPy-style broadcast product.
+    CF32: (ac - bd, ad + bc), every product and sum individually rounded to F32 (no FMA)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.dtype == np.complex64:
+        ar, ai = a.real.astype(np.float32), a.imag.astype(np.float32)
+        br, bi = np.asarray(b.real, np.float32), np.asarray(b.imag, np.float32)
+        re = (ar * br).astype(np.float32) - (ai * bi).astype(np.float32)
+        im = (ar * bi).astype(np.float32) + (ai * br).astype(np.float32)
+        out = np.empty(np.broadcast_shapes(a.shape, b.shape), dtype=np.complex64)
+        out.real = re
+        out.imag = im
+        return out
+    return (a.astype(np.float32) * b.astype(np.float32)).astype(np.float32)
+
+
+def fft(x: np.ndarray, forward: bool = True, axis: int = -1) -> np.ndarray:
+    """src/domains/dsp/fft/module_impl_native_cpu.cc:129-140 — pocketfft::c2c, scale 1.0 both ways."""
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    if forward:
+        return np.fft.fft(x, axis=axis).astype(np.complex64)
+    return (np.fft.ifft(x, axis=axis, norm="forward")).astype(np.complex64)
+
+
+def approx_log10(x: np.ndarray) -> np.ndarray:
+    """Backend::ApproxLog10, include/jetstream/backend/devices/cpu/helpers.hh:61-74 (F32, step by step)."""
+    f, e = np.frexp(np.abs(x).astype(np.float32))
+    f = f.astype(np.float32)
+    y = np.full_like(f, F32(1.23149591368684))
+    y = (y * f).astype(np.float32)
+    y = (y + F32(-4.11852516267426)).astype(np.float32)
+    y = (y * f).astype(np.float32)
+    y = (y + F32(6.02197014179219)).astype(np.float32)
+    y = (y * f).astype(np.float32)
+    y = (y + F32(-3.13396450166353)).astype(np.float32)
+    y = (y + e.astype(np.float32)).astype(np.float32)
+    return (y * F32(0.3010299956639812)).astype(np.float32)
+
+
+def amplitude_coeff(n: int) -> np.float32:
+    """scalingCoeff, src/domains/dsp/amplitude/module_impl.cc:49-51."""
+    return F32(20.0) * np.log10(F32(1.0) / F32(n), dtype=np.float32)
+
+
+def amplitude(x: np.ndarray, n: int) -> np.ndarray:
+    """src/domains/dsp/amplitude/module_impl_native_cpu.cc:73-99 — n = length of the sample axis."""
+    coeff = amplitude_coeff(n)
+    if np.iscomplexobj(x):
+        re = x.real.astype(np.float32)
+        im = x.imag.astype(np.float32)
+        mag = np.sqrt(((re * re).astype(np.float32) + (im * im).astype(np.float32)).astype(np.float32))
+    else:
+        mag = np.abs(x.astype(np.float32))
+    with np.errstate(divide="ignore"):
+        body = (F32(20.0) * approx_log10(np.where(mag == 0, F32(1), mag))).astype(np.float32) + coeff
+    return np.where(mag == 0, F32(-np.inf), body).astype(np.float32)
+
+
+def range_coefficients(lo: float, hi: float):
+    """RangeImpl::updateCoefficients, src/domains/core/range/module_impl.cc:51-63."""
+    lower, upper = F32(min(lo, hi)), F32(max(lo, hi))
+    if lower == upper:
+        return F32(0.0), F32(0.5)
+    scale = F32(1.0) / (upper - lower)
+    return scale, (-lower * scale).astype(np.float32)
+
+
+def range_(x: np.ndarray, lo: float, hi: float) -> np.ndarray:
+    """src/domains/core/range/module_impl_native_cpu.cc:67-82 — tanh soft knee."""
+    scale, offset = range_coefficients(lo, hi)
+    x = x.astype(np.float32)
+    if scale == 0:
+        return np.full_like(x, F32(0.5))
+    normalized = ((x * scale).astype(np.float32) + offset).astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        t = np.tanh((F32(4.0) * (normalized - F32(0.5)).astype(np.float32)).astype(np.float32)).astype(np.float32)
+    return (F32(0.5) + (F32(0.5) * t).astype(np.float32)).astype(np.float32)
+
+
+def spectrum_engine(x: np.ndarray, enable_scale: bool = False, range_min: float = -120.0,
+                    range_max: float = 0.0) -> np.ndarray:
+    """src/domains/dsp/spectrum_engine/block_impl.cc:120-217 with the sample axis innermost:
+    cast(bypass) -> window -> invert -> reshape -> multiply -> fft -> amplitude -> [range]."""
+    x = np.asarray(x, dtype=np.complex64)
+    n = x.shape[-1]
+    w = invert(window(n))
+    spectrum = fft(multiply(x, w.reshape((1,) * (x.ndim - 1) + (n,))))
+    out = amplitude(spectrum, n)
+    if enable_scale:
+        out = range_(out, range_min, range_max)
+    return out

@@ -1,0 +1,145 @@
+"""GPU parity of the standalone modules (one C-ABI call each, through the host mirror's TestContext) against
+the reference CPU modules (oracle/_ref), plus the reference's own known-answer cases restated
+(src/domains/**/module_tests.cc)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(module_type, inputs, config=None, out="signal", axes=None):
+    import cyberether_b200 as cb
+    ctx = cb.TestContext(module_type)
+    for name, arr in inputs.items():
+        ax = (axes or {}).get(name)
+        if ax is None:
+            ax = dict(sampleAxis=arr.ndim - 1, batchAxis=0 if arr.ndim > 1 else None)
+        ctx.set_input(name, arr, **ax)
+    ctx.set_config(**(config or {}))
+    assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
+    return ctx.output(out)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 1000, 1024, 4096, 65536])
+def test_window_matches_reference(ref, n):
+    got = _run("window", {}, {"size": n}, out="window")
+    want = ref.window(n)
+    assert got.dtype == np.complex64 and got.shape == (n,)
+    # F64 cos on the device vs glibc: identical after rounding to F32 except for rare double-rounding ties.
+    ulp = np.spacing(np.abs(want.real).astype(np.float32)).max()
+    assert np.abs(got.real - want.real).max() <= ulp
+    assert np.all(got.imag == 0)
+    assert float((got.real != want.real).mean()) < 1e-3
+
+
+def test_window_formula_known_answer():
+    """src/domains/dsp/window/module_tests.cc:45 — taps match the Blackman formula within 1e-5."""
+    n = 64
+    got = _run("window", {}, {"size": n}, out="window")
+    i = np.arange(n)
+    want = 0.42 - 0.5 * np.cos(2 * np.pi * i / (n - 1)) + 0.08 * np.cos(4 * np.pi * i / (n - 1))
+    assert np.abs(got.real - want).max() < 1e-5
+
+
+@pytest.mark.parametrize("shape,axis", [((4096,), 0), ((8, 64), 1), ((5, 7), 1), ((3, 4, 6), 2)])
+def test_invert_bit_exact(ref, shape, axis):
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32(shape, 11)
+    got = _run("invert", {"signal": x})
+    want = ref.run_block("invert", {"signal": x}, None, "signal")
+    if shape[axis] % 2 == 0:
+        assert np.array_equal(got, want)          # sign flips are exact
+    else:
+        assert np.abs(got - want).max() <= 2 * np.spacing(np.float32(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("sa,sb", [((64, 4096), (1, 4096)), ((64, 4096), (64, 4096)), ((4, 3, 8), (3, 1)),
+                                   ((16,), (16,)), ((2, 5), (5,)), ((6, 1, 4), (1, 7, 1))])
+def test_multiply_cf32_bit_exact(ref, sa, sb):
+    from cyberether_b200.synthetic import gaussian_cf32
+    a, b = gaussian_cf32(sa, 1), gaussian_cf32(sb, 2)
+    got = _run("multiply", {"a": a, "b": b}, out="product")
+    want = ref.multiply(a, b)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_multiply_f32_bit_exact(ref):
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((128, 512)).astype(np.float32)
+    b = rng.standard_normal((512,)).astype(np.float32)
+    assert np.array_equal(_run("multiply", {"a": a, "b": b}, out="product"), ref.multiply(a, b))
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("forward", [True, False])
+def test_fft_c2c_matches_reference(ref, n, forward):
+    """North-star tolerance for the spectrum: max|a-b| <= 1e-5 * max|b| per transform (we assert 2e-6)."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    rows = 7 if n <= 4096 else 3
+    x = gaussian_cf32((rows, n), 100 + n)
+    got = _run("fft", {"signal": x}, {"forward": forward})
+    want = ref.fft(x, forward=forward)
+    rel = np.abs(got - want).max(axis=-1) / np.abs(want).max(axis=-1)
+    assert rel.max() <= 2e-6, rel.max()
+    exact = np.fft.fft(x.astype(np.complex128), axis=-1) if forward else np.fft.ifft(x.astype(np.complex128), axis=-1) * n
+    ours = np.abs(got - exact).max() / np.abs(exact).max()
+    theirs = np.abs(want - exact).max() / np.abs(exact).max()
+    assert ours <= 3 * theirs + 1e-7, (ours, theirs)    # no less accurate than pocketfft
+
+
+def test_fft_4096_large_batch_roundtrip():
+    """Size-independent property at scale: ifft(fft(x)) == N x (reference fft/module_tests.cc:136-143)."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((2048, 4096), 5)
+    y = _run("fft", {"signal": x}, {"forward": True})
+    z = _run("fft", {"signal": y}, {"forward": False})
+    assert np.abs(z / 4096 - x).max() <= 1e-5 * np.abs(x).max()
+
+
+def test_fft_known_answers():
+    """fft/module_tests.cc: DC -> spike at bin 0 (1e-3), single tone -> spike at its bin."""
+    n = 64
+    got = _run("fft", {"signal": np.ones(n, np.complex64)}, {"forward": True})
+    assert abs(got[0].real - n) < 1e-3 and np.abs(got[1:]).max() < 1e-3
+    n = 1024
+    x = np.exp(2j * np.pi * 5 * np.arange(n) / n).astype(np.complex64)
+    got = _run("fft", {"signal": x}, {"forward": True})
+    assert abs(abs(got[5]) - 1024.0) < 1e-2 and int(np.abs(got).argmax()) == 5
+
+
+def test_amplitude_cf32_bit_exact(ref):
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((32, 4096), 9, scale=30.0)
+    x[0, :8] = 0
+    x[1, :4] = [1e-30, 1e30, 1 + 0j, 2 + 0j]
+    got = _run("amplitude", {"signal": x})
+    want = ref.amplitude(x)
+    assert np.array_equal(got, want)              # same operation order, no FMA: bit-identical
+    assert np.all(np.isneginf(got[0, :8]))
+
+
+def test_amplitude_f32_bit_exact(ref):
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal((16, 1000)) * 10).astype(np.float32)
+    x[0, 0] = 0.0
+    assert np.array_equal(_run("amplitude", {"signal": x}), ref.amplitude(x))
+
+
+@pytest.mark.parametrize("lo,hi", [(-1.0, 1.0), (-120.0, 0.0), (0.0, -120.0), (5.0, 5.0)])
+def test_range_matches_reference(ref, lo, hi):
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((64, 1024)) * max(1.0, abs(hi - lo))).astype(np.float32)
+    x[0, :3] = [-np.inf, np.inf, 0.0]
+    got = _run("range", {"signal": x}, {"min": lo, "max": hi})
+    want = ref.range_(x, lo, hi)
+    # CUDA tanhf vs glibc tanhf: <= 2 ulp of tanh -> <= 1.2e-7 absolute on [0, 1] (reference test: 1e-6).
+    assert np.abs(got - want).max() <= 2.5e-7
+    assert got[0, 0] == want[0, 0] and got[0, 1] == want[0, 1]
+
+
+def test_cast_bypass_and_f32():
+    import cyberether_b200 as cb
+    x = np.arange(8, dtype=np.float32)
+    got = _run("cast", {"buffer": x}, {"outputType": "CF32"}, out="buffer")
+    assert np.array_equal(got, x.astype(np.complex64))
