@@ -60,6 +60,19 @@ def _ref_worker(args):
     return rows * N_FFT * cycles, dt
 
 
+def usable_cores() -> int:
+    """Host threads this process may actually use: the affinity mask capped by the cgroup CPU quota
+    (the GPU box exposes 128 logical CPUs but cpu.max grants 16)."""
+    cores = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            cores = max(1, min(cores, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return cores
+
+
 def run_reference_cpu(cycles: int, warm: int, rows_per_proc: int = 512):
     """Times the reference's spectrum_engine block (reference Flowgraph + scheduler_synchronous +
     NativeCpuRuntime) on every host core: one independent single-threaded reference process per core,
@@ -68,7 +81,7 @@ def run_reference_cpu(cycles: int, warm: int, rows_per_proc: int = 512):
     from oracle import ref
     if not ref.available():
         return None
-    cores = len(os.sched_getaffinity(0))
+    cores = usable_cores()
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()

@@ -3,6 +3,8 @@
 // (device allocation) and the stream ownership of src/runtime/native/cuda/impl.cc:35-118 in the
 // reference. One b200_ctx per device; any number may coexist in a process (the reference has a
 // single-device singleton, include/jetstream/backend/base.hh:125-136).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -31,6 +33,26 @@ extern "C" {
 const char* b200_version(void) { return "b200dsp 0.1.0 (sm_100a)"; }
 
 const char* b200_last_error(void) { return last_error().c_str(); }
+
+int b200_amplitude_scaling_coeff(uint64_t n, float* coeff) {
+    B200_REQUIRE(coeff != nullptr && n > 0, "b200_amplitude_scaling_coeff: bad argument");
+    *coeff = 20.0f * std::log10(1.0f / static_cast<float>(n));
+    return B200_SUCCESS;
+}
+
+int b200_range_coefficients(float min, float max, float* scale, float* offset) {
+    B200_REQUIRE(scale && offset, "b200_range_coefficients: null output");
+    const float lower = min < max ? min : max;
+    const float upper = min < max ? max : min;
+    if (lower == upper) {
+        *scale = 0.0f;
+        *offset = 0.5f;
+        return B200_SUCCESS;
+    }
+    *scale = 1.0f / (upper - lower);
+    *offset = -lower * *scale;
+    return B200_SUCCESS;
+}
 
 int b200_device_count(int* count) {
     B200_REQUIRE(count != nullptr, "b200_device_count: null output");

@@ -6,7 +6,12 @@
 // (src/domains/dsp/fft/module_impl_native_cuda.cc:321-333,433) and, for the chain, the module
 // sequence of src/domains/dsp/spectrum_engine/block_impl.cc:120-217.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
+
+#ifndef B200_FFT4096_DEFAULT_CTAS
+#define B200_FFT4096_DEFAULT_CTAS 2
+#endif
 
 #include "fft4096.cuh"
 
@@ -142,15 +147,39 @@ constexpr uint64_t kMaxGenericN = 16384;
 
 static bool fft_size_supported(const uint64_t n) { return is_pow2(n) && n >= 2 && n <= kMaxGenericN; }
 
-template <int MODE, int WIN>
-static int launch_4096(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
-    auto kernel = fft4096_kernel<MODE, WIN>;
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft4096SmemBytes));
-    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
+// CTAs per SM for the 4096 kernel (2: 3-deep TMA ring, <=128 regs; 3: 2-deep ring, <=80 regs).
+// Overridable for A/B measurements: B200_FFT4096_CTAS=2|3.
+static int fft4096_ctas() {
+    static const int value = [] {
+        const char* env = getenv("B200_FFT4096_CTAS");
+        const int v = env ? atoi(env) : 0;
+        return (v == 2 || v == 3) ? v : B200_FFT4096_DEFAULT_CTAS;
+    }();
+    return value;
+}
+
+template <int MODE, int WIN, int CTAS>
+static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    auto kernel = fft4096_kernel<MODE, WIN, CTAS>;
+    constexpr int smem = fft4096_smem_bytes(CTAS);
+    static bool configured[64] = {};
+    if (!configured[ctx->device & 63]) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[ctx->device & 63] = true;
+    }
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * CTAS;
     const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
-    kernel<<<grid, kFft4096Threads, kFft4096SmemBytes, stream>>>(p);
+    kernel<<<grid, kFft4096Threads, smem, stream>>>(p);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
+}
+
+template <int MODE, int WIN>
+static int launch_4096(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    if (fft4096_ctas() == 3) {
+        return launch_4096_ctas<MODE, WIN, 3>(ctx, p, stream);
+    }
+    return launch_4096_ctas<MODE, WIN, 2>(ctx, p, stream);
 }
 
 template <int MODE, int WIN, int BPT>

@@ -26,11 +26,17 @@ namespace b200 {
 
 constexpr int kFft4096N = 4096;
 constexpr int kFft4096Threads = 256;
-constexpr int kFft4096Stages = 3;
 constexpr int kFft4096RowBytes = kFft4096N * 8;
-// A stage holds the 32 KiB row; the second exchange uses a padded [16][16][17] layout (34816 B).
-constexpr int kFft4096StageBytes = 16 * 272 * 8;
-constexpr int kFft4096SmemBytes = kFft4096Stages * kFft4096StageBytes + 64;
+// A stage holds the 32 KiB row; the second exchange uses a padded [k1=16][k0=16][c=16 (+2 pad)] layout:
+// row pitch 18 elements (16-byte aligned rows -> LDS.128 in pass 3, conflict-free), plane pitch 288.
+constexpr int kFft4096X2Row = 18;
+constexpr int kFft4096X2Plane = 16 * kFft4096X2Row;
+constexpr int kFft4096StageBytes = 16 * kFft4096X2Plane * 8;   // 36864
+// CTAs per SM -> TMA ring depth (shared memory: 227 KB per SM)
+__host__ __device__ constexpr int fft4096_stages(const int ctas) { return ctas >= 3 ? 2 : 3; }
+__host__ __device__ constexpr int fft4096_smem_bytes(const int ctas) {
+    return fft4096_stages(ctas) * kFft4096StageBytes + 64;
+}
 
 // ---- mbarrier / TMA (bulk async copy) PTX wrappers ------------------------------------------
 
@@ -69,6 +75,9 @@ __device__ __forceinline__ void tma_load_row(void* smem_dst, const void* gmem_sr
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -105,10 +114,12 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const TwiddleSet
     }
 }
 
-template <int MODE, int WIN>
-__global__ void __launch_bounds__(kFft4096Threads, 2) fft4096_kernel(const FftParams p) {
+template <int MODE, int WIN, int CTAS>
+__global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const FftParams p) {
+    constexpr int kFft4096Stages = fft4096_stages(CTAS);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kFft4096Stages * kFft4096StageBytes);
+    uint64_t* const reads_done = full + kFft4096Stages;   // split barrier (B): 8 warp arrivals per row
 
     const uint32_t t = threadIdx.x;
     const uint64_t first = blockIdx.x;
@@ -121,6 +132,7 @@ __global__ void __launch_bounds__(kFft4096Threads, 2) fft4096_kernel(const FftPa
         for (int s = 0; s < kFft4096Stages; ++s) {
             mbar_init(&full[s], 1);
         }
+        mbar_init(reads_done, kFft4096Threads / 32);
         fence_mbar_init();
     }
     __syncthreads();
@@ -156,14 +168,14 @@ __global__ void __launch_bounds__(kFft4096Threads, 2) fft4096_kernel(const FftPa
     // Per-thread byte offsets inside a stage buffer (element = 8 bytes).
     //   pass 1 load / exchange-1 store : t + 256 a                       (a, k0 = register index)
     //   exchange-1 load  (t = 16 k0 + c): 256 k0 + c + 16 b
-    //   exchange-2 store (t = 16 k0 + c): 17 k0 + c + 272 k1            (row pitch 17 / plane pitch 272:
-    //   exchange-2 load  (t = k0 + 16 k1): 17 k0 + 272 k1 + c             conflict-free, immediate offsets)
+    //   exchange-2 store (t = 16 k0 + c): 18 k0 + c + 288 k1            (row pitch 18 / plane pitch 288:
+    //   exchange-2 load  (t = k0 + 16 k1): 18 k0 + 288 k1 + c             conflict-free, immediate offsets)
     const uint32_t off_p1 = t * 8;
     const uint32_t off_x1 = (256 * hi4 + lo4) * 8;
-    const uint32_t off_x2s = (17 * hi4 + lo4) * 8;
-    const uint32_t off_x2l = (17 * lo4 + 272 * hi4) * 8;
+    const uint32_t off_x2s = (kFft4096X2Row * hi4 + lo4) * 8;
+    const uint32_t off_x2l = (kFft4096X2Row * lo4 + kFft4096X2Plane * hi4) * 8;
 
-    uint32_t stage = 0, parity = 0;
+    uint32_t stage = 0, parity = 0, row_parity = 0;
     uint32_t refill_stage = 0;  // stage of the previous row (refilled after barrier (A))
     unsigned char* out_ptr = static_cast<unsigned char*>(p.out) +
                              (first * kFft4096N + t) * (MODE == MODE_C2C ? 8 : 4);
@@ -215,19 +227,28 @@ __global__ void __launch_bounds__(kFft4096Threads, 2) fft4096_kernel(const FftPa
         for (int b = 0; b < 16; ++b) {
             v[b] = *reinterpret_cast<const float2*>(buf + off_x1 + 128 * b);
         }
-        dft16(v);
+        dft16_first_layer(v);   // consumes every loaded value: this warp's exchange-1 reads have completed
+        // Split barrier (B) "all exchange-1 reads done before any exchange-2 write": arrive now (one lane
+        // per warp), wait only right before the stores, so the butterfly math overlaps the other warps.
+        __syncwarp();
+        if ((t & 31) == 0) {
+            mbar_arrive(reads_done);
+        }
+        dft16_rest(v);
         apply_twiddles(v, tw2);
-        __syncthreads();  // (B) all exchange-1 reads done before exchange-2 writes
+        mbar_wait(reads_done, row_parity);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            *reinterpret_cast<float2*>(buf + off_x2s + 2176 * k) = v[dft16_pos(k)];
+            *reinterpret_cast<float2*>(buf + off_x2s + kFft4096X2Plane * 8 * k) = v[dft16_pos(k)];
         }
         __syncthreads();  // (C)
 
         // ---- pass 3 -------------------------------------------------------------------------
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            v[c] = *reinterpret_cast<const float2*>(buf + off_x2l + 8 * c);
+        for (int c = 0; c < 16; c += 2) {
+            const float4 pair = *reinterpret_cast<const float4*>(buf + off_x2l + 8 * c);
+            v[c] = make_float2(pair.x, pair.y);
+            v[c + 1] = make_float2(pair.z, pair.w);
         }
         dft16(v);
 
@@ -254,6 +275,7 @@ __global__ void __launch_bounds__(kFft4096Threads, 2) fft4096_kernel(const FftPa
         out_ptr += out_step;
 
         refill_stage = stage;
+        row_parity ^= 1;
         if (++stage == kFft4096Stages) {
             stage = 0;
             parity ^= 1;

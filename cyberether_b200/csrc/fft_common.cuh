@@ -46,14 +46,17 @@ __device__ __forceinline__ void bfly4(float2& a, float2& b, float2& c, float2& d
 // 16-point DFT in place as 4x4. Result X[k] lands in v[dft16_pos(k)].
 __host__ __device__ constexpr int dft16_pos(const int k) { return 4 * (k & 3) + (k >> 2); }
 
-__device__ __forceinline__ void dft16(float2 (&v)[16]) {
-    constexpr float kC = 0.92387953251128674f;  // cos(pi/8)
-    constexpr float kS = 0.38268343236508977f;  // sin(pi/8)
-    constexpr float kH = 0.70710678118654752f;  // sqrt(1/2)
+__device__ __forceinline__ void dft16_first_layer(float2 (&v)[16]) {
 #pragma unroll
     for (int a0 = 0; a0 < 4; ++a0) {
         bfly4(v[a0], v[a0 + 4], v[a0 + 8], v[a0 + 12]);
     }
+}
+
+__device__ __forceinline__ void dft16_rest(float2 (&v)[16]) {
+    constexpr float kC = 0.92387953251128674f;  // cos(pi/8)
+    constexpr float kS = 0.38268343236508977f;  // sin(pi/8)
+    constexpr float kH = 0.70710678118654752f;  // sqrt(1/2)
     // Internal twiddles W16^(a0*q) on v[a0 + 4q], a0,q in 1..3.
     // a0=1: q=1 -> W^1, q=2 -> W^2, q=3 -> W^3
     v[5] = cmul(v[5], make_float2(kC, -kS));
@@ -71,6 +74,11 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
     for (int q = 0; q < 4; ++q) {
         bfly4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
+}
+
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    dft16_first_layer(v);
+    dft16_rest(v);
 }
 
 // ---- prologue ------------------------------------------------------------------------------

@@ -553,14 +553,22 @@ class Cast(Module):
         return _call("b200_cast_f32_cf32", ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size, stream)
 
 
-def merge_broadcast_signal_axes(a: Tensor, b: Tensor, rank: int) -> Dict[str, int]:
-    """Signal axes of a broadcast result: right-aligned union, `a` wins on conflicts."""
+def merge_broadcast_signal_axes(a: Tensor, b: Tensor, rank: int) -> Optional[Dict[str, int]]:
+    """MergeBroadcastSignalAxes (src/memory/axis.cc:332-359): each tensor's roles are right-aligned into the
+    output rank; a role present on both inputs must land on the same output axis, otherwise ERROR
+    ("Signal roles map to conflicting output axes"). Returns None on conflict."""
     merged: Dict[str, int] = {}
-    for t in (b, a):
-        shift = rank - t.rank
-        for key in ("sampleAxis", "batchAxis", "channelAxis"):
+    for key in ("sampleAxis", "batchAxis", "channelAxis"):
+        mapped = []
+        for t in (a, b):
             if t.has_attribute(key):
-                merged[key] = int(t.attribute(key)) + shift
+                mapped.append(int(t.attribute(key)) + (rank - t.rank))
+        if len(mapped) == 2 and mapped[0] != mapped[1]:
+            return None
+        if mapped:
+            merged[key] = mapped[0]
+    if len(set(merged.values())) != len(merged):
+        return None
     return merged
 
 
@@ -587,6 +595,9 @@ class Multiply(Module):
             if da != db and da != 1 and db != 1:
                 return _error(f"[MODULE_MULTIPLY] Input shapes {list(a.shape)} and {list(b.shape)} are not broadcastable.")
             shape[rank - 1 - i] = max(da, db)
+        self._axes = merge_broadcast_signal_axes(a, b, rank)
+        if self._axes is None:
+            return _error("[MEMORY:AXIS] Signal roles map to conflicting output axes.")
         self._plan = tuple(shape)
         return Result.SUCCESS
 
@@ -606,7 +617,9 @@ class Multiply(Module):
         self.view_b = self.b.data.broadcast_to(shape)
         self.c = Tensor.create(self.a.device, self.a.dtype, shape)
         self.c.propagate_attributes(self.a)
-        self.c.attributes.update(merge_broadcast_signal_axes(self.a, self.b, len(shape)))
+        for key in ("sampleAxis", "batchAxis", "channelAxis"):
+            self.c.remove_attribute(key)
+        self.c.attributes.update(self._axes)
         self.outputs["product"] = TensorLink()
         self.outputs["product"].produced(self.name, "product", self.c)
         self._shape = _u64_array(shape)
@@ -732,8 +745,12 @@ class Fft(Module):
 
 
 def amplitude_scaling_coeff(n: int) -> float:
-    """scalingCoeff = 20 * log10f(1 / (F32)N) (src/domains/dsp/amplitude/module_impl.cc:49-51), in F32."""
-    return float(np.float32(20.0) * np.log10(np.float32(1.0) / np.float32(n), dtype=np.float32))
+    """scalingCoeff = 20 * log10f(1 / (F32)N) (src/domains/dsp/amplitude/module_impl.cc:49-51). Evaluated by
+    the library with the host libm's log10f — the same function the reference calls — because other F32
+    log10 implementations (e.g. numpy's) differ in the last bit for non-power-of-two N."""
+    out = ctypes.c_float()
+    _native.check(_native.load().b200_amplitude_scaling_coeff(int(n), ctypes.byref(out)))
+    return float(out.value)
 
 
 @register_module
@@ -789,13 +806,10 @@ class Amplitude(Module):
 
 def range_coefficients(lo: float, hi: float) -> Tuple[float, float]:
     """RangeImpl::updateCoefficients (src/domains/core/range/module_impl.cc:51-63), F32 arithmetic."""
-    lower = np.float32(min(lo, hi))
-    upper = np.float32(max(lo, hi))
-    if lower == upper:
-        return 0.0, 0.5
-    scale = np.float32(1.0) / (upper - lower)
-    offset = -lower * scale
-    return float(scale), float(offset)
+    scale, offset = ctypes.c_float(), ctypes.c_float()
+    _native.check(_native.load().b200_range_coefficients(ctypes.c_float(lo), ctypes.c_float(hi),
+                                                         ctypes.byref(scale), ctypes.byref(offset)))
+    return float(scale.value), float(offset.value)
 
 
 @register_module

@@ -107,6 +107,12 @@ int b200_amplitude_cf32(b200_ctx* ctx, const b200_cf32* in, float* out, uint64_t
 int b200_amplitude_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, float coeff,
                        b200_stream stream);
 
+/* Host-side coefficient helpers (pure functions, no device work):
+ * amplitude scalingCoeff = 20 * log10f(1.0f / (float)n)      src/domains/dsp/amplitude/module_impl.cc:49-51
+ * range scale/offset     = RangeImpl::updateCoefficients     src/domains/core/range/module_impl.cc:51-63 */
+int b200_amplitude_scaling_coeff(uint64_t n, float* coeff);
+int b200_range_coefficients(float min, float max, float* scale, float* offset);
+
 /* range ("Scale") — src/domains/core/range/module_impl_native_cpu.cc:67-82:
  * out = scale == 0 ? 0.5 : 0.5 + 0.5*tanhf(4*((in*scale + offset) - 0.5)); scale/offset from
  * RangeImpl::updateCoefficients (src/domains/core/range/module_impl.cc:51-63). */

@@ -17,6 +17,8 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 
 F32 = np.float32
@@ -88,9 +90,15 @@ def approx_log10(x: np.ndarray) -> np.ndarray:
     return (y * F32(0.3010299956639812)).astype(np.float32)
 
 
+_libm = ctypes.CDLL("libm.so.6")
+_libm.log10f.restype = ctypes.c_float
+_libm.log10f.argtypes = [ctypes.c_float]
+
+
 def amplitude_coeff(n: int) -> np.float32:
-    """scalingCoeff, src/domains/dsp/amplitude/module_impl.cc:49-51."""
-    return F32(20.0) * np.log10(F32(1.0) / F32(n), dtype=np.float32)
+    """scalingCoeff, src/domains/dsp/amplitude/module_impl.cc:49-51: 20.0f * std::log10(1.0f / (F32)N) —
+    glibc's log10f (numpy's F32 log10 differs in the last bit for some N)."""
+    return F32(F32(20.0) * F32(_libm.log10f(float(F32(1.0) / F32(n)))))
 
 
 def amplitude(x: np.ndarray, n: int) -> np.ndarray:

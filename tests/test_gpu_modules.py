@@ -58,10 +58,29 @@ def test_invert_bit_exact(ref, shape, axis):
 def test_multiply_cf32_bit_exact(ref, sa, sb):
     from cyberether_b200.synthetic import gaussian_cf32
     a, b = gaussian_cf32(sa, 1), gaussian_cf32(sb, 2)
-    got = _run("multiply", {"a": a, "b": b}, out="product")
-    want = ref.multiply(a, b)
+    # only the sample axis is declared (right-aligned roles must agree, src/memory/axis.cc:332-359)
+    axes = {"a": dict(sampleAxis=len(sa) - 1), "b": dict(sampleAxis=len(sb) - 1)}
+    got = _run("multiply", {"a": a, "b": b}, out="product", axes=axes)
+    want = ref.run_block("multiply", {"a": a, "b": b}, None, "product",
+                         axes={"a": (len(sa) - 1, -1, -1), "b": (len(sb) - 1, -1, -1)})
     assert got.shape == want.shape
     assert np.array_equal(got, want)
+
+
+def test_multiply_conflicting_axes_rejected_like_reference(ref):
+    """Batch roles that right-align to different output axes are an ERROR in the reference
+    ("Signal roles map to conflicting output axes"); the mirror rejects the same graph."""
+    import cyberether_b200 as cb
+    from oracle.ref import RefError
+    from cyberether_b200.synthetic import gaussian_cf32
+    a, b = gaussian_cf32((4, 3, 8), 1), gaussian_cf32((3, 1), 2)
+    with pytest.raises(RefError):
+        ref.run_block("multiply", {"a": a, "b": b}, None, "product", axes={"a": (2, 0, -1), "b": (1, 0, -1)})
+    ctx = cb.TestContext("multiply")
+    ctx.set_input("a", a, sampleAxis=2, batchAxis=0)
+    ctx.set_input("b", b, sampleAxis=1, batchAxis=0)
+    assert ctx.run() == cb.Result.ERROR
+    assert "conflicting output axes" in cb.last_error()
 
 
 def test_multiply_f32_bit_exact(ref):
