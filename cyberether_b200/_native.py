@@ -55,6 +55,15 @@ SIGNATURES = {
     "b200_chain_exec_host": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_u64]),
     "b200_chain_plan_destroy": (c_int, [c_vp]),
     "b200_chain_plan_variant": (ctypes.c_char_p, [c_vp]),
+    "b200_filter_taps_host": (c_int, [ctypes.c_double, ctypes.c_double, P(ctypes.c_double), c_u64, c_u64, c_vp]),
+    "b200_fir_plan_create": (c_int, [c_vp, c_vp, c_u64, c_u64, c_u64, P(c_vp)]),
+    "b200_fir_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_vp]),
+    "b200_fir_reset": (c_int, [c_vp, c_vp]),
+    "b200_fir_plan_destroy": (c_int, [c_vp]),
+    "b200_fm_plan_create": (c_int, [c_vp, c_u64, c_f32, c_int, c_int, P(c_vp)]),
+    "b200_fm_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_vp]),
+    "b200_fm_reset": (c_int, [c_vp, c_vp]),
+    "b200_fm_plan_destroy": (c_int, [c_vp]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ from __future__ import annotations
 from typing import Dict, List, Optional
 
 from .jetstream import (Module, Result, SynchronousScheduler, Tensor, TensorLink, build_module, _error,
-                        resolve_signal_axes)
+                        resolve_signal_axes, filter_resample_plan)
 
 
 class Block:
@@ -156,3 +156,69 @@ class SpectrumEngine(Block):
                 return r
             return self.module_expose_output("buffer", "range", "signal")
         return self.module_expose_output("buffer", "amplitude", "signal")
+
+
+class Filter(Block):
+    """`filter` — include/jetstream/domains/dsp/filter/block.hh:10-19, src/domains/dsp/filter/block_impl.cc.
+    cast(bypass) -> filter_taps (static) -> fir_filter (fused time-domain replacement of the reference's
+    pad/fft/multiply/fold/ifft/normalize/unpad/overlap_add chain). Resampling engages under exactly the
+    reference's conditions (block_impl.cc:64-90); otherwise the block silently runs at full rate."""
+    TYPE = "filter"
+    DEFAULTS = {"sampleRate": 2e6, "bandwidth": 1e6, "center": (0.0,), "taps": 101, "heads": 1}
+
+    def create_impl(self) -> Result:
+        port = self.inputs.get("signal")
+        if port is None or not port.resolved():
+            return Result.INCOMPLETE
+        cfg = self.config
+        heads = int(cfg["heads"])
+        if heads == 0:
+            return _error("[BLOCK_FILTER] Heads must be greater than 0.")
+        tensor = port.tensor
+        if tensor.dtype not in ("F32", "CF32"):
+            return _error("[BLOCK_FILTER] Signal input must have data type F32 or CF32.")
+        axes = resolve_signal_axes(tensor)
+        if axes is None:
+            return _error("[BLOCK_FILTER] Signal axis metadata is invalid.")
+        if axes.channel is not None:
+            return _error("[BLOCK_FILTER] Signal already has channelAxis. Generated filter channels cannot be nested.")
+        signal_size = tensor.shape[axes.sample]
+        centers = list(cfg["center"])[:heads] + [0.0] * max(0, heads - len(cfg["center"]))
+        r = filter_resample_plan(float(cfg["sampleRate"]), float(cfg["bandwidth"]), int(cfg["taps"]), signal_size)
+        if r > 1 and any(float(c) != 0.0 for c in centers):
+            return _error("[BLOCK_FILTER_B200] Resampling heads with a non-zero center (fold offsets + "
+                          "phase_correction) are not implemented by this provider yet.")
+        self.resample = r > 1
+        result = self.module_create("cast_signal", "cast", {"outputType": "CF32"}, {"buffer": port})
+        if result != Result.SUCCESS:
+            return result
+        result = self.module_create("filter_taps", "filter_taps",
+                                    {"sampleRate": float(cfg["sampleRate"]), "bandwidth": float(cfg["bandwidth"]),
+                                     "center": tuple(float(c) for c in centers), "taps": int(cfg["taps"])}, {})
+        if result != Result.SUCCESS:
+            return result
+        result = self.module_create("fir", "fir_filter", {"decimation": r},
+                                    {"signal": self.module_get_output("cast_signal", "buffer"),
+                                     "coeffs": self.module_get_output("filter_taps", "coeffs")})
+        if result != Result.SUCCESS:
+            return result
+        self.module_expose_output("buffer", "fir", "buffer")
+        if self.resample:
+            import numpy as np
+            self.outputs["buffer"].tensor.set_attribute("sampleRate", float(np.float32(float(cfg["sampleRate"]) / r)))
+        return Result.SUCCESS
+
+
+class FmBlock(Block):
+    """`fm` block — include/jetstream/domains/dsp/fm/block.hh:8-15: one `fm` module."""
+    TYPE = "fm"
+    DEFAULTS = {"mode": "narrow", "deemphasis": "none", "sampleRate": 240e3}
+
+    def create_impl(self) -> Result:
+        port = self.inputs.get("signal")
+        if port is None or not port.resolved():
+            return Result.INCOMPLETE
+        result = self.module_create("fm", "fm", dict(self.config), {"signal": port})
+        if result != Result.SUCCESS:
+            return result
+        return self.module_expose_output("signal", "fm", "signal")

@@ -1,0 +1,398 @@
+// Streaming decimating FIR — the B200 replacement for the `filter` block's per-cycle module chain
+// (src/domains/dsp/filter/block_impl.cc:350-582): pad -> fft -> multiply(filter spectrum) -> fold ->
+// ifft -> multiply_constant(1/M) -> unpad -> overlap_add.
+//
+// That chain computes, frame by frame with a carried tail, exactly the causal linear convolution of the
+// time-continuous stream (the batch axis holds consecutive frames, overlap_add/module_impl_native_cpu.cc:155-198)
+// with the taps, kept at every R-th sample when the block resamples (fold + ifft + 1/M == time-domain
+// decimation):
+//        y[q] = sum_{k=0}^{L-1} h[k] * xs[q R - k],      xs = ... previous cycles ..., frame 0, frame 1, ...
+// so it is evaluated directly in the time domain: one pass over the input (8 B/sample), 8/R B/sample out,
+// state = the last L-1 input samples (instead of the reference's (L-1)/R output-tail samples).
+//
+// Kernel: a CTA stages the input span of a tile of QT = threads*OB outputs into shared memory, split into
+// R polyphase planes (plane p holds xs[.. + p], unit stride in q, odd plane pitch: conflict-free); each
+// thread owns OB consecutive outputs and walks the taps of one plane at a time with a register sliding
+// window (1 shared load + OB packed FMAs per tap), so the FP32x2 pipe, not shared memory, is the inner
+// bound. Taps are re-ordered per plane on the host and live in shared memory (broadcast loads).
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+struct FirParams {
+    const float2* x;        // [n_in] stream (frames concatenated)
+    const float2* hist;     // [L-1] last inputs of the previous call (zeros initially)
+    float2* y;              // [frames, heads, frame_out]
+    const float* taps;      // device: [heads][R][lp_pad] real, or complex as float2
+    uint64_t n_in, n_out;   // n_out = n_in / R
+    uint32_t L, R, heads;
+    uint32_t lp_pad;        // taps per plane, padded to a multiple of OB
+    uint32_t hpad;          // history rows (in units of R samples) staged below the tile, incl. OB slack
+    uint32_t qt;            // outputs per tile = blockDim.x * OB
+    uint32_t plane_pitch;   // odd
+    uint64_t frame_out;     // outputs per frame (T / R)
+};
+
+template <int OB, bool REAL_TAPS>
+__global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* const planes = reinterpret_cast<float2*>(smem_raw);
+    const uint32_t tap_words = p.heads * p.R * p.lp_pad * (REAL_TAPS ? 1 : 2);
+    float* const taps_s = reinterpret_cast<float*>(planes + static_cast<size_t>(p.R) * p.plane_pitch);
+    float2* const out_s = reinterpret_cast<float2*>(taps_s + ((tap_words + 1) & ~1u));
+
+    const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
+    for (uint32_t i = tid; i < tap_words; i += nthreads) {
+        taps_s[i] = p.taps[i];
+    }
+
+    const uint64_t tiles = (p.n_out + p.qt - 1) / p.qt;
+    const uint32_t span = (p.qt - 1) * p.R + p.hpad * p.R + 1;     // staged samples per tile
+    const int64_t hist_len = static_cast<int64_t>(p.L) - 1;
+
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t q0 = tile * p.qt;
+        const int64_t j0 = static_cast<int64_t>(q0 * p.R) - static_cast<int64_t>(p.hpad) * p.R;
+        __syncthreads();   // previous tile's out_s/planes consumers are done
+        // ---- stage: sample i (stream index j0 + i) -> plane[i mod R][i div R]
+        {
+            uint32_t plane = tid % p.R, pos = tid / p.R;
+            const uint32_t step_plane = nthreads % p.R, step_pos = nthreads / p.R;
+            for (uint32_t i = tid; i < span; i += nthreads) {
+                const int64_t j = j0 + i;
+                float2 v = make_float2(0.f, 0.f);
+                if (j >= 0) {
+                    if (static_cast<uint64_t>(j) < p.n_in) {
+                        v = ldg_stream_f2(p.x + j);
+                    }
+                } else if (j >= -hist_len) {
+                    v = p.hist[hist_len + j];
+                }
+                planes[static_cast<size_t>(plane) * p.plane_pitch + pos] = v;
+                plane += step_plane;
+                pos += step_pos;
+                if (plane >= p.R) {
+                    plane -= p.R;
+                    ++pos;
+                }
+            }
+        }
+        __syncthreads();
+
+        const uint32_t o0 = tid * OB;
+        for (uint32_t head = 0; head < p.heads; ++head) {
+            float2 acc[OB];
+#pragma unroll
+            for (int i = 0; i < OB; ++i) {
+                acc[i] = make_float2(0.f, 0.f);
+            }
+            for (uint32_t plane = 0; plane < p.R; ++plane) {
+                // taps of this plane: k = kp0 + m R with kp0 = (R - plane) % R; input row offset D - m
+                const uint32_t d = plane == 0 ? p.hpad : p.hpad - 1;
+                const float2* const xp = planes + static_cast<size_t>(plane) * p.plane_pitch + o0 + d;
+                const float* const hp = taps_s + (static_cast<size_t>(head) * p.R + plane) * p.lp_pad *
+                                                     (REAL_TAPS ? 1 : 2);
+                float2 w[OB];
+#pragma unroll
+                for (int i = 0; i < OB; ++i) {
+                    w[i] = xp[i];
+                }
+                for (uint32_t m0 = 0; m0 < p.lp_pad; m0 += OB) {
+#pragma unroll
+                    for (int s = 0; s < OB; ++s) {
+                        // logical window element i lives in w[(i - s) mod OB]
+                        if constexpr (REAL_TAPS) {
+                            const float h = hp[m0 + s];
+                            const float2 hh = make_float2(h, h);
+#pragma unroll
+                            for (int i = 0; i < OB; ++i) {
+                                acc[i] = __ffma2_rn(w[(i - s + OB) % OB], hh, acc[i]);
+                            }
+                        } else {
+                            const float2 h = reinterpret_cast<const float2*>(hp)[m0 + s];
+                            const float2 hr = make_float2(h.x, h.x), hi = make_float2(-h.y, h.y);
+#pragma unroll
+                            for (int i = 0; i < OB; ++i) {
+                                const float2 v = w[(i - s + OB) % OB];
+                                acc[i] = __ffma2_rn(v, hr, acc[i]);
+                                acc[i] = __ffma2_rn(make_float2(v.y, v.x), hi, acc[i]);
+                            }
+                        }
+                        // slide: next tap (m+1) needs row offset one lower
+                        w[(OB - 1 - s) % OB] = xp[-static_cast<int>(m0 + s) - 1];
+                    }
+                }
+            }
+            // ---- stage the tile's outputs, then store coalesced
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < OB; ++i) {
+                out_s[o0 + i] = acc[i];
+            }
+            __syncthreads();
+            for (uint32_t o = tid; o < p.qt; o += nthreads) {
+                const uint64_t q = q0 + o;
+                if (q < p.n_out) {
+                    const uint64_t frame = q / p.frame_out;
+                    const uint64_t m = q - frame * p.frame_out;
+                    stg_stream_f2(p.y + (frame * p.heads + head) * p.frame_out + m, out_s[o]);
+                }
+            }
+        }
+    }
+}
+
+// New history = last L-1 samples of concat(old history, x).
+__global__ void fir_history_kernel(const float2* __restrict__ x, const float2* __restrict__ old_hist,
+                                   float2* __restrict__ new_hist, const uint64_t n_in, const uint32_t hist_len) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < hist_len; i += gridDim.x * blockDim.x) {
+        // element i of the new history is stream index n_in - hist_len + i
+        const int64_t j = static_cast<int64_t>(n_in) - hist_len + i;
+        new_hist[i] = j >= 0 ? x[j] : old_hist[hist_len + j];
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_fir_plan {
+    b200_ctx* ctx;
+    uint32_t L, R, heads;
+    bool real_taps;
+    int ob;
+    uint32_t lp_pad, hpad, threads, qt, plane_pitch;
+    size_t smem;
+    float* taps_dev;
+    float2* hist[2];
+    int cur;
+};
+
+template <int OB>
+static int fir_launch(b200_fir_plan* pl, const FirParams& p, unsigned grid, cudaStream_t s) {
+    if (pl->real_taps) {
+        auto k = fir_decim_kernel<OB, true>;
+        B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl->smem)));
+        k<<<grid, pl->threads, pl->smem, s>>>(p);
+    } else {
+        auto k = fir_decim_kernel<OB, false>;
+        B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl->smem)));
+        k<<<grid, pl->threads, pl->smem, s>>>(p);
+    }
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+extern "C" {
+
+// filter_taps — FilterTapsImplNativeCpu::generateCoeffs (src/domains/dsp/filter_taps/module_impl_native_cpu.cc:46-80):
+// windowed-sinc x Blackman x upconversion, all in F64 with the same libm the reference uses, rounded to CF32.
+// STATIC_OUTPUT module: evaluated once on the host (the reference has no CUDA implementation of it either).
+int b200_filter_taps_host(double sample_rate, double bandwidth, const double* center, uint64_t heads, uint64_t taps,
+                          b200_cf32* out_host) {
+    B200_REQUIRE(center && out_host, "b200_filter_taps_host: null argument");
+    B200_REQUIRE(std::isfinite(sample_rate) && sample_rate > 0.0, "[MODULE_FILTER_TAPS] Sample rate must be positive.");
+    B200_REQUIRE(std::isfinite(bandwidth) && bandwidth > 0.0 && bandwidth <= sample_rate,
+                 "[MODULE_FILTER_TAPS] Bandwidth must be between 0 and sample rate.");
+    B200_REQUIRE(taps != 0, "[MODULE_FILTER_TAPS] Number of taps cannot be zero.");
+    B200_REQUIRE(taps % 2 == 1, "[MODULE_FILTER_TAPS] Number of taps must be odd (%llu).",
+                 static_cast<unsigned long long>(taps));
+    B200_REQUIRE(heads >= 1, "[MODULE_FILTER_TAPS] At least one center frequency is required.");
+    const double kPi = 3.14159265358979323846;
+    const double filterWidth = (bandwidth / sample_rate) / 2.0;
+    const std::complex<double> j(0.0, 1.0);
+    for (uint64_t c = 0; c < heads; ++c) {
+        B200_REQUIRE(std::isfinite(center[c]) && center[c] <= sample_rate / 2.0 && center[c] >= -sample_rate / 2.0,
+                     "[MODULE_FILTER_TAPS] Center frequency #%llu is outside +-sampleRate/2.",
+                     static_cast<unsigned long long>(c));
+        const double filterOffset = center[c] / sample_rate;
+        for (uint64_t i = 0; i < taps; ++i) {
+            const double fi = static_cast<double>(i);
+            const double halfLen = static_cast<double>(taps - 1) / 2.0;
+            const double n = fi - halfLen;
+            const double sincVal = (n == 0.0) ? (2.0 * filterWidth) : std::sin(2.0 * kPi * filterWidth * n) / (kPi * n);
+            const double windowVal = (taps == 1) ? 1.0
+                                                 : 0.42 - 0.50 * std::cos(2.0 * kPi * fi / (taps - 1)) +
+                                                       0.08 * std::cos(4.0 * kPi * fi / (taps - 1));
+            const auto upconvert = std::exp(j * 2.0 * kPi * n * filterOffset);
+            const auto result = sincVal * windowVal * upconvert;
+            out_host[c * taps + i].re = static_cast<float>(result.real());
+            out_host[c * taps + i].im = static_cast<float>(result.imag());
+        }
+    }
+    return B200_SUCCESS;
+}
+
+int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t ntaps, uint64_t heads,
+                         uint64_t decimation, b200_fir_plan** plan) {
+    B200_REQUIRE(ctx && taps_host && plan, "b200_fir_plan_create: null argument");
+    *plan = nullptr;
+    B200_REQUIRE(ntaps >= 1 && ntaps <= 65536, "b200_fir_plan_create: tap count %llu out of range (1..65536)",
+                 static_cast<unsigned long long>(ntaps));
+    B200_REQUIRE(heads >= 1 && heads <= 1024, "b200_fir_plan_create: heads must be in 1..1024");
+    B200_REQUIRE(decimation >= 1 && decimation <= 4096, "b200_fir_plan_create: decimation must be in 1..4096");
+    DeviceGuard guard(ctx);
+    auto* pl = new b200_fir_plan();
+    pl->ctx = ctx;
+    pl->L = static_cast<uint32_t>(ntaps);
+    pl->R = static_cast<uint32_t>(decimation);
+    pl->heads = static_cast<uint32_t>(heads);
+    pl->real_taps = true;
+    for (uint64_t i = 0; i < ntaps * heads; ++i) {
+        pl->real_taps = pl->real_taps && taps_host[i].im == 0.0f;
+    }
+    // Tile geometry: the largest odd OB (register sliding window) whose staged planes fit ~96 KB.
+    const uint32_t lp = (pl->L + pl->R - 1) / pl->R;
+    const int ob_options[4] = {7, 5, 3, 1};
+    const uint32_t thread_options[3] = {128, 64, 32};
+    bool found = false;
+    for (int oi = 0; oi < 4 && !found; ++oi) {
+        for (int ti = 0; ti < 3 && !found; ++ti) {
+            const int ob = ob_options[oi];
+            const uint32_t threads = thread_options[ti];
+            const uint32_t lp_pad = (lp + ob - 1) / ob * ob;
+            const uint32_t hpad = lp_pad + 1;                       // rows of history incl. slack for padded taps
+            const uint32_t qt = threads * ob;
+            uint32_t pitch = qt + hpad + 1;
+            pitch |= 1u;
+            const size_t tap_words = static_cast<size_t>(pl->heads) * pl->R * lp_pad * (pl->real_taps ? 1 : 2);
+            const size_t smem = static_cast<size_t>(pl->R) * pitch * 8 + ((tap_words + 1) & ~size_t(1)) * 4 +
+                                static_cast<size_t>(qt) * 8;
+            if (smem <= 100 * 1024) {
+                pl->ob = ob;
+                pl->threads = threads;
+                pl->lp_pad = lp_pad;
+                pl->hpad = hpad;
+                pl->qt = qt;
+                pl->plane_pitch = pitch;
+                pl->smem = smem;
+                found = true;
+            }
+        }
+    }
+    if (!found) {
+        delete pl;
+        return fail("b200_fir_plan_create: taps=%llu heads=%llu decimation=%llu does not fit the shared-memory tile",
+                    static_cast<unsigned long long>(ntaps), static_cast<unsigned long long>(heads),
+                    static_cast<unsigned long long>(decimation));
+    }
+    // Re-order taps per plane: plane p, slot m <- h[kp0 + m R], kp0 = (R - p) % R; zero beyond L.
+    const uint32_t per = pl->real_taps ? 1 : 2;
+    std::vector<float> host(static_cast<size_t>(pl->heads) * pl->R * pl->lp_pad * per, 0.0f);
+    for (uint32_t h = 0; h < pl->heads; ++h) {
+        for (uint32_t pidx = 0; pidx < pl->R; ++pidx) {
+            const uint32_t kp0 = (pl->R - pidx) % pl->R;
+            for (uint32_t m = 0; m < pl->lp_pad; ++m) {
+                const uint64_t k = kp0 + static_cast<uint64_t>(m) * pl->R;
+                if (k < pl->L) {
+                    const b200_cf32 t = taps_host[static_cast<size_t>(h) * pl->L + k];
+                    const size_t idx = ((static_cast<size_t>(h) * pl->R + pidx) * pl->lp_pad + m) * per;
+                    host[idx] = t.re;
+                    if (!pl->real_taps) {
+                        host[idx + 1] = t.im;
+                    }
+                }
+            }
+        }
+    }
+    void* dev = nullptr;
+    if (b200_malloc(ctx, host.size() * sizeof(float), &dev) != B200_SUCCESS) {
+        delete pl;
+        return B200_ERROR;
+    }
+    pl->taps_dev = static_cast<float*>(dev);
+    cudaError_t e = cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    const size_t hist_bytes = std::max<size_t>(1, pl->L - 1) * sizeof(float2);
+    void* h0 = nullptr;
+    void* h1 = nullptr;
+    if (e != cudaSuccess || b200_malloc(ctx, hist_bytes, &h0) != B200_SUCCESS ||
+        b200_malloc(ctx, hist_bytes, &h1) != B200_SUCCESS) {
+        cudaFree(dev);
+        cudaFree(h0);
+        delete pl;
+        return fail("b200_fir_plan_create: device setup failed");
+    }
+    pl->hist[0] = static_cast<float2*>(h0);
+    pl->hist[1] = static_cast<float2*>(h1);
+    pl->cur = 0;
+    *plan = pl;
+    return B200_SUCCESS;
+}
+
+int b200_fir_reset(b200_fir_plan* plan, b200_stream stream) {
+    B200_REQUIRE(plan, "b200_fir_reset: null plan");
+    DeviceGuard guard(plan->ctx);
+    const size_t hist_bytes = std::max<size_t>(1, plan->L - 1) * sizeof(float2);
+    B200_CUDA_CHECK(cudaMemsetAsync(plan->hist[plan->cur], 0, hist_bytes, as_stream(stream)));
+    return B200_SUCCESS;
+}
+
+int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_t frames, uint64_t frame_len,
+                  b200_stream stream) {
+    B200_REQUIRE(plan, "b200_fir_exec: null plan");
+    const uint64_t n_in = frames * frame_len;
+    if (n_in == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(x && y, "b200_fir_exec: null buffer");
+    B200_REQUIRE(frame_len % plan->R == 0, "b200_fir_exec: frame length %llu is not a multiple of the decimation %u",
+                 static_cast<unsigned long long>(frame_len), plan->R);
+    DeviceGuard guard(plan->ctx);
+    FirParams p{};
+    p.x = reinterpret_cast<const float2*>(x);
+    p.hist = plan->hist[plan->cur];
+    p.y = reinterpret_cast<float2*>(y);
+    p.taps = plan->taps_dev;
+    p.n_in = n_in;
+    p.n_out = n_in / plan->R;
+    p.L = plan->L;
+    p.R = plan->R;
+    p.heads = plan->heads;
+    p.lp_pad = plan->lp_pad;
+    p.hpad = plan->hpad;
+    p.qt = plan->qt;
+    p.plane_pitch = plan->plane_pitch;
+    p.frame_out = frame_len / plan->R;
+    const uint64_t tiles = (p.n_out + p.qt - 1) / p.qt;
+    const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(8, (220 * 1024) / (plan->smem + 1024)));
+    const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * per_sm;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, cap));
+    const cudaStream_t s = as_stream(stream);
+    int rc = B200_SUCCESS;
+    switch (plan->ob) {
+        case 7: rc = fir_launch<7>(plan, p, grid, s); break;
+        case 5: rc = fir_launch<5>(plan, p, grid, s); break;
+        case 3: rc = fir_launch<3>(plan, p, grid, s); break;
+        default: rc = fir_launch<1>(plan, p, grid, s); break;
+    }
+    if (rc != B200_SUCCESS) {
+        return rc;
+    }
+    if (plan->L > 1) {
+        const uint32_t hist_len = plan->L - 1;
+        fir_history_kernel<<<(hist_len + 255) / 256, 256, 0, s>>>(p.x, plan->hist[plan->cur], plan->hist[plan->cur ^ 1],
+                                                                 n_in, hist_len);
+        B200_LAUNCH_CHECK();
+        plan->cur ^= 1;
+    }
+    return B200_SUCCESS;
+}
+
+int b200_fir_plan_destroy(b200_fir_plan* plan) {
+    if (!plan) {
+        return B200_SUCCESS;
+    }
+    DeviceGuard guard(plan->ctx);
+    cudaFree(plan->taps_dev);
+    cudaFree(plan->hist[0]);
+    cudaFree(plan->hist[1]);
+    delete plan;
+    return B200_SUCCESS;
+}
+
+}  // extern "C"

@@ -943,6 +943,270 @@ class SpectralChain(Module):
         return self.compute_deinitialize()
 
 
+@register_module
+class FilterTaps(Module):
+    """`filter_taps` — src/domains/dsp/filter_taps/module_impl.cc:12-140 (+ native_cpu.cc:46-80). STATIC_OUTPUT:
+    evaluated once, on the host in F64 (b200_filter_taps_host), uploaded on the first compute cycle."""
+    TYPE = "filter_taps"
+    DEFAULTS = {"sampleRate": 2e6, "bandwidth": 1e6, "center": (0.0,), "taps": 101}
+
+    def validate(self):
+        c = self.config
+        centers = [float(v) for v in c["center"]]
+        taps = int(c["taps"])
+        sr, bw = float(c["sampleRate"]), float(c["bandwidth"])
+        if not math.isfinite(sr) or sr <= 0.0:
+            return _error(f"[MODULE_FILTER_TAPS] Sample rate must be positive ({sr}).")
+        if not math.isfinite(bw) or bw <= 0.0 or bw > sr:
+            return _error("[MODULE_FILTER_TAPS] Bandwidth must be between 0 and sample rate.")
+        if taps == 0:
+            return _error("[MODULE_FILTER_TAPS] Number of taps cannot be zero.")
+        if taps % 2 == 0:
+            return _error(f"[MODULE_FILTER_TAPS] Number of taps must be odd ({taps}).")
+        if not centers:
+            return _error("[MODULE_FILTER_TAPS] At least one center frequency is required.")
+        for i, ct in enumerate(centers):
+            if not math.isfinite(ct) or abs(ct) > sr / 2.0:
+                return _error(f"[MODULE_FILTER_TAPS] Center frequency #{i} must be within +-sampleRate/2.")
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.STATIC_OUTPUT)
+        return self.define_interface_output("coeffs")
+
+    def create_impl(self):
+        c = self.config
+        centers = [float(v) for v in c["center"]]
+        heads, taps = len(centers), int(c["taps"])
+        host = np.zeros((heads, taps), dtype=np.complex64)
+        arr = (ctypes.c_double * heads)(*centers)
+        result = _call("b200_filter_taps_host", ctypes.c_double(float(c["sampleRate"])),
+                       ctypes.c_double(float(c["bandwidth"])), arr, heads, taps,
+                       host.ctypes.data_as(ctypes.c_void_p))
+        if result != Result.SUCCESS:
+            return result
+        self.host_coeffs = host
+        self.output = Tensor.create(self.alloc_device, "CF32", (heads, taps))
+        self.output.set_attribute("sampleAxis", 1)
+        self.output.set_attribute("channelAxis", 0)
+        self.output.set_attribute("sampleRate", float(np.float32(c["sampleRate"])))
+        self.output.set_attribute("bandwidth", float(np.float32(c["bandwidth"])))
+        self.outputs["coeffs"] = TensorLink()
+        self.outputs["coeffs"].produced(self.name, "coeffs", self.output)
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.output)
+        if err:
+            return err
+        self.output.data.copy_(torch.from_numpy(self.host_coeffs), non_blocking=False)
+        return Result.SUCCESS
+
+
+def filter_resample_plan(sample_rate: float, bandwidth: float, taps: int, signal_size: int):
+    """CalculateCandidatePlan (src/domains/dsp/filter/block_impl.cc:40-168) for zero-centred heads: returns the
+    integer resampler ratio R (1 = the block silently runs at full rate)."""
+    if taps == 0:
+        return 1
+    ratio = float(sample_rate) / float(bandwidth)
+    if not math.isfinite(ratio) or ratio <= 0.0 or ratio >= 2.0 ** 64:
+        return 1
+    if ratio != math.floor(ratio):
+        return 1
+    r = int(ratio)
+    if (taps - 1) % r != 0:
+        return 1
+    if (taps + signal_size - 1) % r != 0:
+        return 1
+    return r
+
+
+@register_module
+class FirFilter(Module):
+    """`fir_filter` — B200-only fused module: the per-cycle module chain of the `filter` block
+    (src/domains/dsp/filter/block_impl.cc:350-582) as one streaming time-domain (decimating) FIR kernel.
+    Inputs: `signal` CF32 [T] or [B, T] (batch = consecutive frames), `coeffs` CF32 [heads, taps] (settled).
+    Output `buffer`: [B, heads, T / R] with channelAxis = old sample axis, sampleAxis = +1."""
+    TYPE = "fir_filter"
+    DEFAULTS = {"decimation": 1}
+
+    def __init__(self):
+        super().__init__()
+        self._plan_handle = None
+
+    def validate(self):
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        if t.dtype != "CF32":
+            return _error("[MODULE_FIR_FILTER_B200] Signal input must be CF32.")
+        axes = resolve_signal_axes(t)
+        if axes is None:
+            return _error("[BLOCK_FILTER] Signal axis metadata is invalid.")
+        if axes.channel is not None:
+            return _error("[BLOCK_FILTER] Signal already has channelAxis. Generated filter channels cannot be nested.")
+        if not (t.rank == 1 or (t.rank == 2 and axes.sample == 1 and axes.batch in (0, None))):
+            return _error("[MODULE_FIR_FILTER_B200] Supported layouts: [T] or [batch, T] with the sample axis innermost.")
+        r = int(self.config["decimation"])
+        if r < 1 or t.shape[-1] % r != 0:
+            return _error("[MODULE_FIR_FILTER_B200] Frame length must be a multiple of the decimation.")
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_interface_input("signal")
+        self.define_interface_input("coeffs")
+        return self.define_interface_output("buffer")
+
+    def create_impl(self):
+        self.input = self.inputs["signal"].tensor
+        self.coeffs = self.inputs["coeffs"].tensor
+        if self.coeffs.dtype != "CF32" or self.coeffs.rank != 2:
+            return _error("[MODULE_FIR_FILTER_B200] Coefficients must be CF32 [heads, taps].")
+        self._heads, self._taps = self.coeffs.shape
+        self._r = int(self.config["decimation"])
+        t = self.input
+        self._frame_len = t.shape[-1]
+        self._frames = t.size // self._frame_len
+        out_shape = tuple(t.shape[:-1]) + (self._heads, self._frame_len // self._r)
+        self.output = Tensor.create(t.device, "CF32", out_shape)
+        self.output.propagate_attributes(t)
+        sample_axis = t.rank - 1
+        self.output.set_attribute("sampleAxis", sample_axis + 1)
+        self.output.set_attribute("channelAxis", sample_axis)
+        if t.has_attribute("batchAxis"):
+            b = int(t.attribute("batchAxis"))
+            self.output.set_attribute("batchAxis", b + 1 if b >= sample_axis else b)
+        self.outputs["buffer"] = TensorLink()
+        self.outputs["buffer"].produced(self.name, "buffer", self.output)
+        return Result.SUCCESS
+
+    def _create_plan(self):
+        err = _require_cuda(self, self.input, self.coeffs)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        torch.cuda.current_stream(self.input.device).synchronize()   # coefficients are settled static output
+        host = np.ascontiguousarray(self.coeffs.numpy())
+        handle = ctypes.c_void_p()
+        result = _call("b200_fir_plan_create", ctx.handle, host.ctypes.data_as(ctypes.c_void_p), self._taps,
+                       self._heads, self._r, ctypes.byref(handle))
+        if result == Result.SUCCESS:
+            self._plan_handle = handle
+        return result
+
+    def compute_submit(self, stream):
+        if self._plan_handle is None:
+            result = self._create_plan()
+            if result != Result.SUCCESS:
+                return result
+        return _call("b200_fir_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), self._frames,
+                     self._frame_len, stream)
+
+    def compute_deinitialize(self):
+        if self._plan_handle is not None:
+            _call("b200_fir_plan_destroy", self._plan_handle)
+            self._plan_handle = None
+        return Result.SUCCESS
+
+    def destroy(self):
+        return self.compute_deinitialize()
+
+
+@register_module
+class Fm(Module):
+    """`fm` — src/domains/dsp/fm/module_impl.cc:8-155 (+ native_cpu.cc:43-175). Narrow mode (optionally with
+    50/75 us de-emphasis); the wideband stereo decoder is not implemented by this provider yet."""
+    TYPE = "fm"
+    DEFAULTS = {"mode": "narrow", "deemphasis": "none", "sampleRate": 240e3}
+
+    def __init__(self):
+        super().__init__()
+        self._plan_handle = None
+
+    def validate(self):
+        c = self.config
+        if c["mode"] not in ("narrow", "wide"):
+            return _error("[MODULE_FM] Mode must be 'narrow' or 'wide'.")
+        if c["deemphasis"] not in ("none", "50us", "75us"):
+            return _error("[MODULE_FM] De-emphasis must be 'none', '50us', or '75us'.")
+        sr = float(c["sampleRate"])
+        if not math.isfinite(sr) or sr <= 0.0:
+            return _error("[MODULE_FM] Sample rate must be finite and positive.")
+        if sr > 20e6:
+            return _error("[MODULE_FM] Sample rate must not exceed 20 MHz.")
+        if c["mode"] == "wide" and sr < 200e3:
+            return _error("[MODULE_FM] Wideband mode requires a sample rate of at least 200 kHz.")
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        if t.dtype != "CF32":
+            return _error("[MODULE_FM_B200] Input must be complex (CF32).")
+        axes = resolve_signal_axes(t)
+        if axes is None:
+            return _error("[MODULE_FM] Input must contain valid signal axis metadata.")
+        if c["mode"] == "wide":
+            if axes.channel is not None:
+                return _error("[MODULE_FM] Wideband mode does not support channelized input.")
+            return _error("[MODULE_FM_B200] Wideband (stereo) mode is not implemented by this provider yet.")
+        if axes.sample != t.rank - 1 or (axes.batch not in (None, 0)):
+            return _error("[MODULE_FM_B200] Supported layouts: sample axis innermost, batch axis outermost.")
+        self._axes = axes
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_interface_input("signal")
+        return self.define_interface_output("signal")
+
+    def create_impl(self):
+        self.input = self.inputs["signal"].tensor
+        if not self.input.contiguous():
+            return _error("[MODULE_FM_B200] Strided inputs are not supported by this provider yet.")
+        t = self.input
+        self._frame_len = t.shape[-1]
+        self._frames = t.shape[0] if (self._axes.batch == 0 and t.rank >= 2) else 1
+        self._lanes = t.size // (self._frame_len * self._frames)
+        self.output = Tensor.create(t.device, "F32", t.shape)
+        self.output.propagate_attributes(t)
+        self.output.set_attribute("frequency", 0.0)
+        self.outputs["signal"] = TensorLink()
+        self.outputs["signal"].produced(self.name, "signal", self.output)
+        return Result.SUCCESS
+
+    def compute_initialize(self):
+        if self.input.device.type != "cuda":
+            return Result.SUCCESS
+        ctx = Context.get(self.input.device)
+        handle = ctypes.c_void_p()
+        deemph = {"none": 0, "50us": 50, "75us": 75}[self.config["deemphasis"]]
+        result = _call("b200_fm_plan_create", ctx.handle, self._lanes, ctypes.c_float(float(self.config["sampleRate"])),
+                       1 if self.config["mode"] == "wide" else 0, deemph, ctypes.byref(handle))
+        if result == Result.SUCCESS:
+            self._plan_handle = handle
+        return result
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.output)
+        if err:
+            return err
+        if self._plan_handle is None:
+            result = self.compute_initialize()
+            if result != Result.SUCCESS:
+                return result
+        return _call("b200_fm_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), self._frames,
+                     self._frame_len, stream)
+
+    def compute_deinitialize(self):
+        if self._plan_handle is not None:
+            _call("b200_fm_plan_destroy", self._plan_handle)
+            self._plan_handle = None
+        return Result.SUCCESS
+
+    def destroy(self):
+        return self.compute_deinitialize()
+
+
 # ---------------------------------------------------------------------------------------------
 # Runtime (per device x runtime segment) — src/runtime/native/cuda/impl.cc
 # ---------------------------------------------------------------------------------------------

@@ -148,6 +148,43 @@ int b200_chain_plan_destroy(b200_chain_plan* plan);
 /* Name of the kernel variant exec() launches for this plan (for logs / profiles). */
 const char* b200_chain_plan_variant(const b200_chain_plan* plan);
 
+/* ---- filter block ---------------------------------------------------------------------------- */
+
+/* filter_taps — FilterTapsImplNativeCpu::generateCoeffs, src/domains/dsp/filter_taps/module_impl_native_cpu.cc:46-80
+ * (validation of src/domains/dsp/filter_taps/module_impl.cc:12-105). STATIC_OUTPUT, evaluated once, on the
+ * host, in F64 with the reference's own formula; out_host: [heads, taps] CF32. */
+int b200_filter_taps_host(double sample_rate, double bandwidth, const double* center, uint64_t heads,
+                          uint64_t taps, b200_cf32* out_host);
+
+/* Streaming (decimating) FIR = the per-cycle module chain of the `filter` block
+ * (src/domains/dsp/filter/block_impl.cc:350-582: pad -> fft -> multiply -> fold -> ifft -> multiply_constant ->
+ * unpad -> overlap_add) evaluated in the time domain: y[q] = sum_k h[k] xs[q R - k] over the time-continuous
+ * stream of frames; `decimation` = R (1 when the block does not resample, block_impl.cc:64-90).
+ *   taps_host : [heads, ntaps] CF32 on the HOST (captured by the plan)
+ *   x         : [frames, frame_len] CF32 device, frames consecutive in time
+ *   y         : [frames, heads, frame_len / R] CF32 device
+ * The plan carries the last ntaps-1 input samples across calls (the reference carries the (ntaps-1)/R
+ * output tail in overlap_add, module_impl_native_cpu.cc:155-198); b200_fir_reset zeroes it. */
+int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t ntaps, uint64_t heads,
+                         uint64_t decimation, b200_fir_plan** plan);
+int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_t frames, uint64_t frame_len,
+                  b200_stream stream);
+int b200_fir_reset(b200_fir_plan* plan, b200_stream stream);
+int b200_fir_plan_destroy(b200_fir_plan* plan);
+
+/* ---- fm ---------------------------------------------------------------------------------------- */
+
+/* fm — FmImplNativeCpu::computeSubmit, src/domains/dsp/fm/module_impl_native_cpu.cc:43-175, coefficients of
+ * src/domains/dsp/fm/module_impl.cc:108-155. x: [frames, lanes, frame_len] CF32 (frames consecutive in time,
+ * lanes independent), out: same shape F32. wide != 0 (stereo) is not implemented yet -> ERROR.
+ * deemphasis_us: 0 (none), 50 or 75. Per-lane state (previous sample, de-emphasis) lives in the plan. */
+int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wide, int deemphasis_us,
+                        b200_fm_plan** plan);
+int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t frames, uint64_t frame_len,
+                 b200_stream stream);
+int b200_fm_reset(b200_fm_plan* plan, b200_stream stream);
+int b200_fm_plan_destroy(b200_fm_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif
