@@ -272,10 +272,8 @@ def main_ours(args):
     t_end = time.perf_counter()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    tm = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total_max = float(tm.item())
+    from cyberether_b200.sharding import max_over_ranks
+    ms_total_max = max_over_ranks(ms_total, dev)
     ms_per_step = ms_total_max / args.steps
     samples_per_step_all = rows * n * world
     value = samples_per_step_all / (ms_per_step * 1e-3) / 1e6
@@ -296,10 +294,7 @@ def main_ours(args):
     for _ in range(e2e_steps):
         e2e_step()  # synchronous: returns when out_host is complete
     t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = samples_per_step_all * e2e_steps / float(te.item()) / 1e6
+    e2e_value = samples_per_step_all * e2e_steps / max_over_ranks(t_e2e, dev) / 1e6
     checksum = float(out_host[:: max(1, rows // 64)].double().sum())   # the step's result is read on the host
 
     sampler.stop_flag.set()

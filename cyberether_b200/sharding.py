@@ -1,0 +1,54 @@
+"""Batch sharding of the spectral chain across the GPUs of one box.
+
+Every FFT row is independent (the fft transforms along the sample axis only, the window broadcasts over all
+other axes, amplitude/range are elementwise), so the outermost non-sample axis is cut into contiguous slabs,
+one per rank, with NO data-path collective. torch.distributed is used for the plumbing only: the barrier that
+brackets a timed region, the MAX-over-ranks reduction of device times, and an optional gather of results at
+the graph boundary for a consumer that wants the whole spectrum on one rank."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slab [begin, end) of `total_rows` owned by `rank`; slabs differ by at most one row."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, extra = divmod(total_rows, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def all_shards(total_rows: int, world: int) -> List[Tuple[int, int]]:
+    return [shard_bounds(total_rows, world, r) for r in range(world)]
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """MAX reduction of a per-rank scalar (device time in ms); identity when not distributed."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_rows(local: torch.Tensor, total_rows: int, dst: int = 0):
+    """Graph-boundary gather: concatenates every rank's [rows_r, n] slab on `dst` in rank order (None elsewhere).
+    Slabs may differ by one row, so they are padded to the largest slab for the collective."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bounds = all_shards(total_rows, world)
+    largest = max(e - b for b, e in bounds)
+    padded = local
+    if local.shape[0] < largest:
+        padded = torch.zeros((largest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, parts, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([p[: e - b] for p, (b, e) in zip(parts, bounds)], dim=0)

@@ -148,3 +148,128 @@ def spectrum_engine(x: np.ndarray, enable_scale: bool = False, range_min: float 
     if enable_scale:
         out = range_(out, range_min, range_max)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# filter block
+# ---------------------------------------------------------------------------------------------
+
+def filter_taps(sample_rate: float, bandwidth: float, center, taps: int) -> np.ndarray:
+    """FilterTapsImplNativeCpu::generateCoeffs, src/domains/dsp/filter_taps/module_impl_native_cpu.cc:46-80
+    (windowed sinc x Blackman x upconversion in F64, stored CF32 [heads, taps])."""
+    center = np.atleast_1d(np.asarray(center, dtype=np.float64))
+    width = (bandwidth / sample_rate) / 2.0
+    i = np.arange(taps, dtype=np.float64)
+    n = i - (taps - 1) / 2.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sinc = np.where(n == 0.0, 2.0 * width, np.sin(2.0 * JST_PI * width * n) / (JST_PI * n))
+    win = np.ones(taps) if taps == 1 else (0.42 - 0.50 * np.cos(2.0 * JST_PI * i / (taps - 1)) +
+                                           0.08 * np.cos(4.0 * JST_PI * i / (taps - 1)))
+    out = np.empty((len(center), taps), dtype=np.complex64)
+    for c, ct in enumerate(center):
+        up = np.exp(1j * 2.0 * JST_PI * n * (ct / sample_rate))
+        res = sinc * win * up
+        out[c].real = res.real.astype(np.float32)
+        out[c].imag = res.imag.astype(np.float32)
+    return out
+
+
+def filter_resample_ratio(sample_rate: float, bandwidth: float, taps: int, signal_size: int) -> int:
+    """CalculateCandidatePlan, src/domains/dsp/filter/block_impl.cc:40-168 (zero-centred heads)."""
+    ratio = sample_rate / bandwidth
+    if not np.isfinite(ratio) or ratio <= 0 or ratio != np.floor(ratio):
+        return 1
+    r = int(ratio)
+    if (taps - 1) % r != 0 or (taps + signal_size - 1) % r != 0:
+        return 1
+    return r
+
+
+class FilterBlock:
+    """The `filter` block as the reference wires it (src/domains/dsp/filter/block_impl.cc:350-582), stage by
+    stage in the frequency domain: pad -> fft -> multiply -> fold -> ifft -> multiply_constant -> unpad ->
+    overlap_add, with the overlap tail carried across frames and across calls
+    (overlap_add/module_impl_native_cpu.cc:121-203). Input [B, T] (frames consecutive in time) or [T]."""
+
+    def __init__(self, sample_rate: float, bandwidth: float, taps: int, frame_len: int, center=(0.0,)):
+        self.taps = filter_taps(sample_rate, bandwidth, center, taps)        # [heads, L]
+        self.heads, self.L = self.taps.shape
+        self.T = frame_len
+        self.M = frame_len + taps - 1
+        self.R = filter_resample_ratio(sample_rate, bandwidth, taps, frame_len)
+        if self.R > 1 and np.any(np.asarray(center) != 0):
+            raise NotImplementedError("fold offsets / phase_correction are outside this port")
+        padded = np.zeros((self.heads, self.M), np.complex64)
+        padded[:, : self.L] = self.taps                                      # pad (core/pad): zeros at the tail
+        self.filter_spectrum = fft(padded)                                   # fftFilter (static)
+        self.tail = np.zeros((self.heads, (self.L - 1) // self.R), np.complex64)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, np.complex64)
+        frames = x.reshape(-1, self.T)
+        out = np.empty((frames.shape[0], self.heads, self.T // self.R), np.complex64)
+        for b, frame in enumerate(frames):
+            padded = np.zeros(self.M, np.complex64)
+            padded[: self.T] = frame
+            product = multiply(fft(padded)[None, :], self.filter_spectrum)   # [heads, M]
+            if self.R > 1:                                                   # fold: F64 mean of R aliased bins
+                size = self.M // self.R
+                folded = product.astype(np.complex128).reshape(self.heads, self.R, size).sum(axis=1) / float(self.R)
+                product = folded.astype(np.complex64)
+            time = fft(product, forward=False)
+            norm = F32(1.0) / F32(time.shape[-1])
+            time = (time * norm).astype(np.complex64)                        # multiply_constant
+            pad = (self.L - 1) // self.R
+            body, tail = time[:, : time.shape[-1] - pad].copy(), time[:, time.shape[-1] - pad:]
+            body[:, :pad] += self.tail                                       # overlap_add
+            self.tail = tail.copy()
+            out[b] = body
+        return out.reshape(x.shape[:-1] + (self.heads, self.T // self.R))
+
+
+# ---------------------------------------------------------------------------------------------
+# fm (narrow)
+# ---------------------------------------------------------------------------------------------
+
+class FmNarrow:
+    """FmImplNativeCpu::computeSubmit narrow path, src/domains/dsp/fm/module_impl_native_cpu.cc:43-129 with the
+    coefficients of module_impl.cc:108-124. Input [frames, lanes, frame_len] (or fewer dims); state per lane."""
+
+    def __init__(self, sample_rate: float, deemphasis: str = "none", lanes: int = 1):
+        sr = F32(sample_rate)
+        kf = F32(100e3) / sr
+        self.ref = F32(1.0 / (2.0 * JST_PI * float(kf)))
+        self.deemph = deemphasis != "none"
+        tau = 50e-6 if deemphasis == "50us" else 75e-6
+        self.alpha = F32(1.0 - np.exp(-1.0 / (float(sr) * tau))) if self.deemph else F32(1.0)
+        self.prev = np.zeros(lanes, np.complex64)
+        self.has_prev = np.zeros(lanes, bool)
+        self.state = np.zeros(lanes, np.float32)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        frames, lanes, n = x.shape
+        out = np.empty(x.shape, np.float32)
+        for lane in range(lanes):
+            stream = x[:, lane, :].reshape(-1)
+            prev = np.concatenate([[self.prev[lane]], stream[:-1]])
+            pr, pi = prev.real.astype(np.float32), prev.imag.astype(np.float32)
+            cr, ci = stream.real.astype(np.float32), stream.imag.astype(np.float32)
+            with np.errstate(invalid="ignore", over="ignore"):
+                re = (pr * cr).astype(np.float32) + (pi * ci).astype(np.float32)   # conj(prev) * cur, no FMA
+                im = (pr * ci).astype(np.float32) - (pi * cr).astype(np.float32)
+                d = (np.arctan2(im, re).astype(np.float32) * self.ref).astype(np.float32)
+            bad = ~(np.isfinite(cr) & np.isfinite(ci) & np.isfinite(pr) & np.isfinite(pi))
+            d[bad] = np.nan
+            if not self.has_prev[lane]:
+                d[0] = F32(0.0)
+            if self.deemph:
+                y = self.state[lane]
+                for i in range(d.size):
+                    if np.isfinite(d[i]):
+                        y = F32(y + F32(self.alpha * F32(d[i] - y)))
+                        d[i] = y
+                self.state[lane] = y
+            out[:, lane, :] = d.reshape(frames, n)
+            self.prev[lane] = stream[-1]
+            self.has_prev[lane] = True
+        return out

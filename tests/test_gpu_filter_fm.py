@@ -68,7 +68,7 @@ def test_filter_taps_bit_exact(ref):
     assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
     got = ctx.output("coeffs")
     with ref.Session() as s:
-        s.add_block("t", "filter_taps", {"sampleRate": 8e6, "bandwidth": 1e6, "center": [0.0, 1.5e6, -2e6], "taps": 129})
+        s.add_block("t", "filter_taps", {"sampleRate": 8e6, "bandwidth": 1e6, "center": [0.0, 1.5e6, -2e6], "taps": 129, "heads": 3})
         s.compute()
         want = s.output("t", "coeffs")
     assert np.array_equal(got, want)

@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference Module/Block/Scheduler interface: lifecycle, validation, error behaviour,
+topological order and static settlement. Runs on CPU tensors (compute itself refuses without CUDA)."""
+import numpy as np
+import pytest
+
+import cyberether_b200 as cb
+from cyberether_b200.blocks import Filter, FmBlock, SpectrumEngine
+from cyberether_b200.jetstream import Taint, TensorLink, build_module, filter_resample_plan
+
+
+def tensor(shape, dtype=np.complex64, **axes):
+    return cb.Tensor.from_numpy(np.zeros(shape, dtype), device="cpu", **axes)
+
+
+def link(t):
+    return TensorLink(tensor=t)
+
+
+def test_registry_exact_four_key_lookup():
+    assert cb.list_available_modules("fft") == [("fft", "cuda", "native", "b200")]
+    with pytest.raises(KeyError):
+        build_module("fft", "cuda", "native", "generic")
+    with pytest.raises(KeyError):
+        build_module("nonexistent")
+
+
+def test_fft_lifecycle_and_attributes():
+    m = build_module("fft")
+    x = tensor((8, 1024), sampleAxis=1, batchAxis=0)
+    assert m.create("fft", {"forward": True}, {"signal": link(x)}) == cb.Result.SUCCESS
+    out = m.outputs["signal"].tensor
+    assert out.shape == (8, 1024) and out.dtype == "CF32"
+    assert out.attribute("sampleAxis") == 1 and out.attribute("batchAxis") == 0
+    assert m.taint == Taint.DISCONTIGUOUS | Taint.STATELESS
+    assert m.reconfigure({"forward": False}) == cb.Result.RECREATE       # fft/module_impl.cc: reconfigure -> RECREATE
+
+
+def test_fft_rejects_missing_axes_and_unknown_config():
+    m = build_module("fft")
+    assert m.create("fft", None, {"signal": link(tensor((4, 64)))}) == cb.Result.ERROR
+    assert "signal axis metadata" in cb.last_error()
+    m = build_module("fft")
+    assert m.create("fft", {"bogus": 1}, {"signal": link(tensor((64,)))}) == cb.Result.ERROR
+    m = build_module("fft")
+    assert m.create("fft", None, {}) == cb.Result.INCOMPLETE           # unconnected declared input
+
+
+def test_window_is_static_and_validates_size():
+    m = build_module("window")
+    assert m.create("w", {"size": 0}, {}) == cb.Result.ERROR
+    m = build_module("window")
+    assert m.create("w", {"size": 4096}, {}) == cb.Result.SUCCESS
+    assert m.taint & Taint.STATIC_OUTPUT
+    assert m.outputs["window"].tensor.attribute("sampleAxis") == 0
+
+
+def test_multiply_broadcast_shapes_and_errors():
+    m = build_module("multiply")
+    a, b = tensor((6, 1, 4), sampleAxis=2), tensor((1, 7, 1), sampleAxis=2)
+    assert m.create("m", None, {"a": link(a), "b": link(b)}) == cb.Result.SUCCESS
+    assert m.outputs["product"].tensor.shape == (6, 7, 4)
+    m = build_module("multiply")
+    assert m.create("m", None, {"a": link(tensor((4, 5), sampleAxis=1)), "b": link(tensor((4, 6), sampleAxis=1))}) \
+        == cb.Result.ERROR
+    assert "not broadcastable" in cb.last_error()
+
+
+def test_amplitude_and_range_coefficients():
+    m = build_module("amplitude")
+    assert m.create("a", None, {"signal": link(tensor((4, 4096), sampleAxis=1, batchAxis=0))}) == cb.Result.SUCCESS
+    assert abs(m.scaling_coeff + 72.2472) < 1e-4 and m.outputs["signal"].tensor.dtype == "F32"
+    m = build_module("amplitude")
+    assert m.create("a", None, {"signal": link(tensor((4, 8)))}) == cb.Result.ERROR   # no sample/channel axis
+    r = build_module("range")
+    x = tensor((16,), np.float32)
+    assert r.create("r", {"min": -120.0, "max": 0.0}, {"signal": link(x)}) == cb.Result.SUCCESS
+    assert abs(r.scale - 1 / 120) < 1e-9 and r.offset == 1.0
+    assert r.reconfigure({"min": 0.0, "max": 0.0}) == cb.Result.SUCCESS and r.scale == 0.0 and r.offset == 0.5
+    r = build_module("range")
+    assert r.create("r", None, {"signal": link(tensor((16,)))}) == cb.Result.ERROR      # CF32 rejected
+
+
+def test_cast_bypass_aliases_input():
+    m = build_module("cast")
+    x = tensor((32,))
+    assert m.create("c", {"outputType": "CF32"}, {"buffer": link(x)}) == cb.Result.SUCCESS
+    assert m.bypass and m.outputs["buffer"].tensor.data.data_ptr() == x.data.data_ptr()
+
+
+def test_spectrum_engine_wiring_fused_and_unfused():
+    x = tensor((64, 4096), sampleAxis=1, batchAxis=0)
+    fused = SpectrumEngine(enableScale=True)
+    assert fused.create("spec", {"buffer": x}) == cb.Result.SUCCESS
+    assert list(fused.modules) == ["cast_input", "window", "invert", "spectral_chain"]
+    out = fused.output("buffer")
+    assert out.shape == (64, 4096) and out.dtype == "F32" and out.attribute("sampleAxis") == 1
+    unfused = SpectrumEngine(enableScale=True, fused=False)
+    assert unfused.create("spec", {"buffer": x}) == cb.Result.SUCCESS
+    assert list(unfused.modules) == ["cast_input", "window", "invert", "reshape_window", "multiply", "fft",
+                                     "amplitude", "range"]       # the reference's own sequence (block_impl.cc:120-217)
+    order = [m.name.split(":")[1] for m in unfused.scheduler.order]
+    assert order.index("window") < order.index("invert") < order.index("multiply") < order.index("fft") \
+        < order.index("amplitude") < order.index("range")
+    sched = unfused.scheduler
+    static = {m.name.split(":")[1] for m in sched.order if sched.is_static(m)}
+    assert static == {"window", "invert", "reshape_window"}     # settle after cycle 1 (block_tests.cc:103-122)
+    assert SpectrumEngine(enableAgc=True).create("s", {"buffer": x}) == cb.Result.ERROR
+    assert SpectrumEngine().create("s", {"buffer": tensor((4, 8))}) == cb.Result.ERROR
+
+
+def test_compute_without_cuda_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    block = SpectrumEngine()
+    assert block.create("spec", {"buffer": tensor((2, 4096), sampleAxis=1, batchAxis=0)}) == cb.Result.SUCCESS
+    assert block.compute() == cb.Result.ERROR
+    assert "no CPU path" in cb.last_error()
+
+
+def test_filter_resampling_conditions_match_reference():
+    """src/domains/dsp/filter/block_impl.cc:64-90 — integer ratio, (taps-1) % R == 0, (T+taps-1) % R == 0."""
+    assert filter_resample_plan(8e6, 1e6, 129, 4096) == 8
+    assert filter_resample_plan(8e6, 1e6, 127, 4096) == 1      # BASELINE config 3 as worded: silently full rate
+    assert filter_resample_plan(8e6, 3e6, 129, 4096) == 1      # non-integer ratio
+    assert filter_resample_plan(8e6, 1e6, 129, 4100) == 1      # (T + taps - 1) % R != 0
+    f = Filter(sampleRate=8e6, bandwidth=1e6, taps=129)
+    assert f.create("f", {"signal": tensor((8, 4096), sampleAxis=1, batchAxis=0)}) == cb.Result.SUCCESS
+    out = f.output("buffer")
+    assert out.shape == (8, 1, 512)
+    assert (out.attribute("sampleAxis"), out.attribute("channelAxis"), out.attribute("batchAxis")) == (2, 1, 0)
+    assert out.attribute("sampleRate") == 1e6
+    assert Filter(taps=128).create("f", {"signal": tensor((8, 4096), sampleAxis=1, batchAxis=0)}) == cb.Result.ERROR
+    assert "must be odd" in cb.last_error()
+    assert Filter(heads=0).create("f", {"signal": tensor((8, 4096), sampleAxis=1, batchAxis=0)}) == cb.Result.ERROR
+
+
+def test_fm_validation_matches_reference_messages():
+    x = tensor((4, 1024), sampleAxis=1, batchAxis=0)
+    assert FmBlock(mode="medium").create("fm", {"signal": x}) == cb.Result.ERROR
+    assert "Mode must be 'narrow' or 'wide'" in cb.last_error()
+    assert FmBlock(deemphasis="10us").create("fm", {"signal": x}) == cb.Result.ERROR
+    assert FmBlock(sampleRate=30e6).create("fm", {"signal": x}) == cb.Result.ERROR
+    assert FmBlock(mode="wide", sampleRate=100e3).create("fm", {"signal": x}) == cb.Result.ERROR
+    ok = FmBlock(sampleRate=250e3)
+    assert ok.create("fm", {"signal": x}) == cb.Result.SUCCESS
+    out = ok.output("signal")
+    assert out.dtype == "F32" and out.shape == (4, 1024) and out.attribute("frequency") == 0.0
+
+
+def test_scheduler_detects_cycles_and_duplicates():
+    from cyberether_b200.jetstream import SynchronousScheduler
+    s = SynchronousScheduler("cpu")
+    m = build_module("window")
+    assert m.create("w", {"size": 8}, {}) == cb.Result.SUCCESS
+    assert s.add(m) == cb.Result.SUCCESS
+    assert s.add(m) == cb.Result.ERROR

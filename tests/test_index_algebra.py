@@ -1,0 +1,142 @@
+"""The index algebra of the two FFT kernels, emulated in numpy (F64) against np.fft: the 16x16x16 three-pass
+scheme of fft4096_kernel (including both shared-memory exchange layouts) and the generic Stockham passes."""
+import numpy as np
+
+
+def W(n, e):
+    return np.exp(-2j * np.pi * (e % n) / n)
+
+
+def dft16(v):
+    v = v.copy()
+
+    def b4(a, b, c, d):
+        s0, s1, s2, s3 = a + c, a - c, b + d, b - d
+        return s0 + s2, s1 - 1j * s3, s0 - s2, s1 + 1j * s3
+    for a0 in range(4):
+        v[a0], v[a0 + 4], v[a0 + 8], v[a0 + 12] = b4(v[a0], v[a0 + 4], v[a0 + 8], v[a0 + 12])
+    for a0 in range(4):
+        for q in range(4):
+            v[a0 + 4 * q] *= W(16, a0 * q)
+    for q in range(4):
+        v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3] = b4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3])
+    return np.array([v[4 * (k & 3) + (k >> 2)] for k in range(16)])      # dft16_pos
+
+
+def test_dft16_4x4_decomposition():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(16) + 1j * rng.standard_normal(16)
+    assert np.abs(dft16(x) - np.fft.fft(x)).max() < 1e-12
+
+
+def test_fft4096_three_pass_scheme_with_padded_exchange():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(4096) + 1j * rng.standard_normal(4096)
+    stage = np.zeros(16 * 288, complex)                 # kFft4096X2Plane = 288, row pitch 18
+    for t in range(256):                                # pass 1: thread t, registers a
+        y = dft16(np.array([x[t + 256 * a] for a in range(16)]))
+        for k0 in range(16):
+            stage[256 * k0 + t] = y[k0] * W(4096, t * k0)
+    regs = {}
+    for t in range(256):                                # pass 2: t = 16 k0 + c, reads 256 k0 + 16 b + c
+        k0, c = t >> 4, t & 15
+        y = dft16(np.array([stage[256 * k0 + 16 * b + c] for b in range(16)]))
+        regs[t] = [y[k1] * W(256, c * k1) for k1 in range(16)]
+    for t in range(256):                                # exchange-2 stores (after the split barrier)
+        k0, c = t >> 4, t & 15
+        for k1 in range(16):
+            stage[288 * k1 + 18 * k0 + c] = regs[t][k1]
+    out = np.zeros(4096, complex)
+    for t in range(256):                                # pass 3: t = k0 + 16 k1
+        k0, k1 = t & 15, t >> 4
+        y = dft16(np.array([stage[288 * k1 + 18 * k0 + c] for c in range(16)]))
+        for k2 in range(16):
+            out[t + 256 * k2] = y[k2]
+    assert np.abs(out - np.fft.fft(x)).max() < 1e-9
+
+
+def test_exchange_layouts_are_bank_conflict_free():
+    """8-byte elements: a half-warp (16 lanes) must touch 16 distinct (address / 8) mod 16 classes."""
+    for w in range(8):
+        for half in range(2):
+            lanes = [32 * w + 16 * half + i for i in range(16)]
+            for k in range(16):
+                assert len({(256 * k + t) % 16 for t in lanes}) == 16                        # pass-1 load/store
+                assert len({(256 * (t >> 4) + 16 * k + (t & 15)) % 16 for t in lanes}) == 16     # exchange-1 load
+                assert len({(288 * k + 18 * (t >> 4) + (t & 15)) % 16 for t in lanes}) == 16     # exchange-2 store
+    # exchange-2 load is LDS.128 (2 elements): a quarter-warp (8 lanes) must cover all 32 banks
+    for w in range(8):
+        for quarter in range(4):
+            lanes = [32 * w + 8 * quarter + i for i in range(8)]
+            for c in range(0, 16, 2):
+                banks = set()
+                for t in lanes:
+                    base = (288 * (t >> 4) + 18 * (t & 15) + c) * 2          # 4-byte words
+                    banks.update((base + j) % 32 for j in range(4))
+                assert len(banks) == 32
+
+
+def stockham(x):
+    n = len(x)
+    log2n = int(np.log2(n))
+    buf = x.astype(complex).copy()
+    ns = 1
+    if log2n % 2 == 1:
+        new = np.zeros(n, complex)
+        for j in range(n // 2):
+            new[2 * j], new[2 * j + 1] = buf[j] + buf[j + n // 2], buf[j] - buf[j + n // 2]
+        buf, ns = new, 2
+    while ns < n:
+        new = np.zeros(n, complex)
+        shift = n // (4 * ns)
+        for j in range(n // 4):
+            k = j % ns
+            u = [buf[j + t * (n // 4)] * W(n, k * t * shift) for t in range(4)]
+            s0, s1, s2, s3 = u[0] + u[2], u[0] - u[2], u[1] + u[3], u[1] - u[3]
+            y = [s0 + s2, s1 - 1j * s3, s0 - s2, s1 + 1j * s3]
+            j0 = ((j - k) << 2) + k
+            for t in range(4):
+                new[j0 + t * ns] = y[t]
+        buf, ns = new, ns * 4
+    return buf
+
+
+def test_generic_stockham_passes():
+    rng = np.random.default_rng(2)
+    for n in (2, 4, 8, 16, 32, 64, 512, 2048):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        assert np.abs(stockham(x) - np.fft.fft(x)).max() < 1e-10 * n
+
+
+def test_inverse_by_swapping_parts():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(64) + 1j * rng.standard_normal(64)
+    sw = lambda z: z.imag + 1j * z.real
+    assert np.abs(sw(np.fft.fft(sw(x))) - np.fft.ifft(x) * 64).max() < 1e-12
+
+
+def test_fir_polyphase_plane_indexing():
+    """fir_decim_kernel: sample i of the staged span -> plane i mod R, row i div R; tap k of output o reads plane
+    (-k) mod R at row o + hpad - m - (plane != 0), k = kp0 + m R."""
+    rng = np.random.default_rng(4)
+    for (L, R, qt, ob) in [(129, 8, 21, 7), (33, 4, 10, 5), (17, 1, 9, 3), (41, 40, 6, 1), (7, 3, 14, 7)]:
+        lp = -(-L // R)
+        lp_pad = -(-lp // ob) * ob
+        hpad = lp_pad + 1
+        h = rng.standard_normal(L)
+        xs = rng.standard_normal(qt * R + hpad * R)          # stream; tile starts at q0 R = hpad R
+        span = (qt - 1) * R + hpad * R + 1
+        planes = np.zeros((R, qt + hpad + 1))
+        for i in range(span):
+            planes[i % R, i // R] = xs[i]
+        for o in range(qt):
+            acc = 0.0
+            for plane in range(R):
+                kp0 = (R - plane) % R
+                d = hpad if plane == 0 else hpad - 1
+                for m in range(lp_pad):
+                    k = kp0 + m * R
+                    tap = h[k] if k < L else 0.0
+                    acc += tap * planes[plane, o + d - m]
+            want = sum(h[k] * xs[(o + hpad) * R - k] for k in range(L))
+            assert abs(acc - want) < 1e-9

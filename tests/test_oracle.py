@@ -1,0 +1,124 @@
+"""Pins the oracle: the numpy port (oracle/port.py) against (i) the UNMODIFIED reference compiled from
+/root/reference (oracle/_ref, when present), (ii) the committed golden vectors that library produced
+(tests/golden/reference_vectors.npz) and (iii) the reference's own known-answer module tests. CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLDEN)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+# ---- (ii) golden vectors -------------------------------------------------------------------------
+
+def test_golden_window_bit_exact(gold):
+    for n in (8, 4096):
+        assert np.array_equal(port.window(n), gold[f"window{n}"])
+
+
+def test_golden_fft(gold):
+    assert rel(port.fft(gold["fft1024_in"]), gold["fft1024_out"]) < 1e-6
+    assert abs(abs(gold["fft1024_out"][5]) - 1024.0) < 1e-2          # BASELINE.md §2 sanity value
+    assert rel(port.fft(gold["fft256_in"]), gold["fft256_fwd"]) < 1e-6
+    assert rel(port.fft(gold["fft256_in"], forward=False), gold["fft256_inv"]) < 1e-6
+
+
+def test_golden_amplitude_bit_exact_and_range(gold):
+    assert np.array_equal(port.amplitude(gold["amp_in"], 512), gold["amp_out"])
+    assert np.abs(port.range_(gold["amp_out"], -80.0, -20.0) - gold["range_out"]).max() <= 2.4e-7   # tanhf ulp
+
+
+def test_golden_chain(gold):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from parity import assert_db_close, true_spectrum
+    x = gold["chain_in"]
+    spec = true_spectrum(x, port.invert(port.window(4096)))
+    assert_db_close(port.spectrum_engine(x, False), gold["chain_db"], spec)
+    assert_db_close(port.spectrum_engine(x, True), gold["chain_scaled"], spec, scale=2.0 / 120.0, floor=3e-7)
+    assert int(gold["chain_db"][0].argmax()) == 2048          # row 0: tones at bins 0, 511, 2048 shifted by N/2
+
+
+def test_golden_filter_taps_bit_exact(gold):
+    assert np.array_equal(port.filter_taps(8e6, 1e6, [0.0, 1.5e6], 33), gold["taps33"])
+
+
+@pytest.mark.parametrize("taps,decim", [(129, 8), (127, 1)])
+def test_golden_filter_block(gold, taps, decim):
+    block = port.FilterBlock(8e6, 1e6, taps, 1024)
+    assert block.R == decim
+    for i in range(2):
+        got = block(gold[f"filter{taps}_in{i}"])
+        want = gold[f"filter{taps}_out{i}"]
+        assert got.shape == want.shape
+        assert rel(got, want) < 2e-6
+
+
+def test_filter_chain_equals_time_domain_decimated_convolution(gold):
+    """The identity the CUDA kernel relies on: fold + ifft + 1/M + unpad + overlap-add
+    == causal streaming convolution kept at every R-th sample."""
+    taps, r = 129, 8
+    x = np.concatenate([gold["filter129_in0"].reshape(-1), gold["filter129_in1"].reshape(-1)]).astype(np.complex128)
+    h = port.filter_taps(8e6, 1e6, [0.0], taps)[0].astype(np.complex128)
+    y = np.convolve(x, h)[: x.size][::r]
+    want = np.concatenate([gold["filter129_out0"].reshape(-1), gold["filter129_out1"].reshape(-1)])
+    assert rel(y, want) < 2e-6
+
+
+@pytest.mark.parametrize("de", ["none", "75us"])
+def test_golden_fm(gold, de):
+    fm = port.FmNarrow(250e3, de, lanes=1)
+    for i in range(2):
+        x = gold[f"fm_{de}_in{i}"]
+        got = fm(x[:, None, :])[:, 0, :]
+        want = gold[f"fm_{de}_out{i}"]
+        assert np.abs(got - want).max() <= 1e-6                 # atan2f: numpy vs glibc, <= 1-2 ulp
+
+
+# ---- (i) the compiled reference, when present ------------------------------------------------------
+
+def test_port_matches_compiled_reference(ref):
+    from cyberether_b200.synthetic import gaussian_cf32, spectral_rows
+    x = gaussian_cf32((5, 1024), 3)
+    assert np.array_equal(port.window(1024), ref.window(1024))
+    w = port.invert(port.window(1024)).reshape(1, 1024)
+    assert np.array_equal(port.multiply(x, w), ref.multiply(x, w))
+    assert rel(port.fft(x), ref.fft(x)) < 1e-6
+    spectrum = ref.fft(x)
+    assert np.array_equal(port.amplitude(spectrum, 1024), ref.amplitude(spectrum))
+    xs = spectral_rows(11, 3)
+    assert np.abs(port.spectrum_engine(xs, True) - ref.spectrum_engine(xs, True)).max() < 2e-4
+
+
+# ---- (iii) the reference's own known-answer tests --------------------------------------
+
+def test_known_answer_fft_dc_and_roundtrip():
+    """src/domains/dsp/fft/module_tests.cc:52-143."""
+    out = port.fft(np.ones(64, np.complex64))
+    assert abs(out[0].real - 64) < 1e-3 and np.abs(out[1:]).max() < 1e-3
+    t = np.arange(64) / 64.0
+    x = (np.cos(2 * np.pi * 4 * t) + 1j * np.sin(2 * np.pi * 4 * t)).astype(np.complex64)
+    back = port.fft(port.fft(x), forward=False)
+    assert np.abs(back / 64 - x).max() < 1e-2
+
+
+def test_known_answer_amplitude_and_range():
+    """amplitude/module_tests.cc (0.1-0.5 dB vs exact log10, -inf at 0); range/module_tests.cc:62-65 (1e-6)."""
+    x = np.array([1 + 0j, 0.5 + 0j, 0j, 3 + 4j], np.complex64)
+    out = port.amplitude(x, 4)
+    exact = 20 * np.log10(np.array([1, 0.5, 1, 5.0])) + 20 * np.log10(1 / 4)
+    assert np.isneginf(out[2])
+    assert np.abs(out[[0, 1, 3]] - exact[[0, 1, 3]]).max() < 0.1
+    r = port.range_(np.array([-1.0, 0.0, 1.0], np.float32), -1.0, 1.0)
+    assert np.abs(r - (0.5 + 0.5 * np.tanh(4 * (np.array([0, 0.5, 1.0]) - 0.5)))).max() < 1e-6
