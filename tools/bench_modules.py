@@ -1,0 +1,88 @@
+"""Secondary measurements (not the bench.py contract): per-module kernels and the FIR / FM configs of
+BASELINE.json, device-resident inputs, CUDA events, achieved GB/s against the measured HBM peak."""
+import ctypes, json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cyberether_b200 as cb
+from cyberether_b200 import _native
+from cyberether_b200.jetstream import Context
+
+lib = _native.load()
+dev = torch.device("cuda:0")
+ctx = Context.get(dev)
+sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+
+def timeit(fn, iters=20, warm=5):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+results = []
+def report(name, ms, samples, bytes_per_sample):
+    gbs = samples * bytes_per_sample / ms * 1e-6
+    results.append(dict(kernel=name, ms=ms, msamples_s=samples / ms * 1e-3, gbs=gbs, frac_of_measured_peak=gbs / PEAK,
+                        algorithmic_bytes_per_sample=bytes_per_sample))
+    print(f"{name:46s} {ms:8.4f} ms {samples/ms*1e-6:9.1f} GS/s {gbs:8.0f} GB/s {100*gbs/PEAK:5.1f}% of measured HBM")
+
+rows, n = 16384, 4096
+g = torch.Generator(device=dev); g.manual_seed(0)
+x = torch.view_as_complex(torch.randn(rows, n, 2, device=dev, generator=g))
+w = torch.view_as_complex(torch.randn(n, 2, device=dev, generator=g))
+y = torch.empty_like(x); f = torch.empty(rows, n, device=dev); f2 = torch.empty_like(f)
+shape = (ctypes.c_uint64 * 2)(rows, n); sa = (ctypes.c_uint64 * 2)(n, 1); sb = (ctypes.c_uint64 * 2)(0, 1)
+report("multiply cf32 [16384,4096] x [1,4096]", timeit(lambda: _native.check(lib.b200_multiply_cf32(ctx.handle, x.data_ptr(), w.data_ptr(), y.data_ptr(), 2, shape, sa, sb, sp))), rows * n, 16)
+plan = ctypes.c_void_p(); _native.check(lib.b200_fft_plan_c2c(ctx.handle, n, rows, ctypes.byref(plan)))
+report("fft c2c 4096 x 16384", timeit(lambda: _native.check(lib.b200_fft_exec(plan, x.data_ptr(), y.data_ptr(), 1, sp))), rows * n, 16)
+report("cuFFT (torch.fft.fft) 4096 x 16384 [baseline]", timeit(lambda: torch.fft.fft(x)), rows * n, 16)
+for nn in (256, 1024, 2048, 8192, 16384):
+    rr = rows * n // nn
+    xx = x.reshape(rr, nn); yy = y.reshape(rr, nn)
+    pl = ctypes.c_void_p(); _native.check(lib.b200_fft_plan_c2c(ctx.handle, nn, rr, ctypes.byref(pl)))
+    report(f"fft c2c {nn} x {rr} (generic stockham)", timeit(lambda: _native.check(lib.b200_fft_exec(pl, xx.data_ptr(), yy.data_ptr(), 1, sp))), rr * nn, 16)
+    report(f"cuFFT {nn} x {rr} [baseline]", timeit(lambda: torch.fft.fft(xx)), rr * nn, 16)
+coeff = cb.amplitude_scaling_coeff(n)
+report("amplitude cf32", timeit(lambda: _native.check(lib.b200_amplitude_cf32(ctx.handle, y.data_ptr(), f.data_ptr(), rows * n, coeff, sp))), rows * n, 12)
+sc, off = cb.range_coefficients(-120.0, 0.0)
+report("range f32", timeit(lambda: _native.check(lib.b200_range_f32(ctx.handle, f.data_ptr(), f2.data_ptr(), rows * n, sc, off, sp))), rows * n, 8)
+# unfused chain = the reference CUDA path's structure (multiply -> fft -> amplitude -> range), our kernels
+def unfused():
+    _native.check(lib.b200_multiply_cf32(ctx.handle, x.data_ptr(), w.data_ptr(), y.data_ptr(), 2, shape, sa, sb, sp))
+    _native.check(lib.b200_fft_exec(plan, y.data_ptr(), y.data_ptr(), 1, sp))
+    _native.check(lib.b200_amplitude_cf32(ctx.handle, y.data_ptr(), f.data_ptr(), rows * n, coeff, sp))
+    _native.check(lib.b200_range_f32(ctx.handle, f.data_ptr(), f2.data_ptr(), rows * n, sc, off, sp))
+report("unfused chain, 4 kernels (our modules)", timeit(unfused), rows * n, 12)
+def unfused_cufft():
+    t = torch.fft.fft(x * w)
+    _native.check(lib.b200_amplitude_cf32(ctx.handle, t.data_ptr(), f.data_ptr(), rows * n, coeff, sp))
+    _native.check(lib.b200_range_f32(ctx.handle, f.data_ptr(), f2.data_ptr(), rows * n, sc, off, sp))
+report("unfused chain with cuFFT (reference CUDA structure)", timeit(unfused_cufft), rows * n, 12)
+win = torch.zeros(n, dtype=torch.complex64, device=dev); win.real = torch.rand(n, device=dev)
+cp = ctypes.c_void_p(); torch.cuda.synchronize(); _native.check(lib.b200_chain_plan_create(ctx.handle, n, rows, win.data_ptr(), ctypes.byref(cp)))
+report("fused chain 4096 x 16384", timeit(lambda: _native.check(lib.b200_chain_exec(cp, x.data_ptr(), f.data_ptr(), rows, coeff, 1, sc, off, sp))), rows * n, 12)
+
+# ---- FIR (BASELINE config 3: 2^26 CF32 samples as [8192, 8192] frames)
+frames, T = 8192, 8192
+xs = torch.view_as_complex(torch.randn(frames, T, 2, device=dev, generator=g))
+for taps, R in ((129, 8), (127, 1), (129, 1)):
+    centers = (ctypes.c_double * 1)(0.0)
+    host = np.zeros((1, taps), np.complex64)
+    _native.check(lib.b200_filter_taps_host(8e6, 1e6, centers, 1, taps, host.ctypes.data_as(ctypes.c_void_p)))
+    fp = ctypes.c_void_p(); _native.check(lib.b200_fir_plan_create(ctx.handle, host.ctypes.data_as(ctypes.c_void_p), taps, 1, R, ctypes.byref(fp)))
+    yo = torch.empty(frames, 1, T // R, dtype=torch.complex64, device=dev)
+    report(f"fir {taps} taps decimate {R}, 2^26 samples", timeit(lambda: _native.check(lib.b200_fir_exec(fp, xs.data_ptr(), yo.data_ptr(), frames, T, sp)), iters=10, warm=3), frames * T, 8 + 8 / R)
+# ---- FM narrow (2^24 samples)
+fr, fl = 2048, 8192
+xf = torch.view_as_complex(torch.randn(fr, fl, 2, device=dev, generator=g)); of = torch.empty(fr, fl, device=dev)
+for de in (0, 75):
+    mp_ = ctypes.c_void_p(); _native.check(lib.b200_fm_plan_create(ctx.handle, 1, 250e3, 0, de, ctypes.byref(mp_)))
+    report(f"fm narrow deemphasis={de}us, 2^24 samples", timeit(lambda: _native.check(lib.b200_fm_exec(mp_, xf.data_ptr(), of.data_ptr(), fr, fl, sp)), iters=10, warm=3), fr * fl, 12)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(dict(peak_gbs=PEAK, results=results), open("gpurun_out/bench_modules.json", "w"), indent=1)
