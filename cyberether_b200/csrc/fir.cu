@@ -59,28 +59,55 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
         const uint64_t q0 = tile * p.qt;
         const int64_t j0 = static_cast<int64_t>(q0 * p.R) - static_cast<int64_t>(p.hpad) * p.R;
         __syncthreads();   // previous tile's out_s/planes consumers are done
-        // ---- stage: sample i (stream index j0 + i) -> plane[i mod R][i div R]
+        // ---- stage: sample i (stream index j0 + i) -> plane[i mod R][i div R] with cp.async (LDGSTS, 8 bytes):
+        // every request of the tile is in flight at once and no register is held for it. Out-of-range samples
+        // are zero-filled by the src-size operand. (Versions that waited per load / per batch of 8 were
+        // long-scoreboard bound: profiles/r01_fir_ncu.json.)
         {
             uint32_t plane = tid % p.R, pos = tid / p.R;
             const uint32_t step_plane = nthreads % p.R, step_pos = nthreads / p.R;
-            for (uint32_t i = tid; i < span; i += nthreads) {
-                const int64_t j = j0 + i;
-                float2 v = make_float2(0.f, 0.f);
-                if (j >= 0) {
-                    if (static_cast<uint64_t>(j) < p.n_in) {
-                        v = ldg_stream_f2(p.x + j);
+            const uint32_t plane_base = static_cast<uint32_t>(__cvta_generic_to_shared(planes));
+            const bool interior = j0 >= 0 && static_cast<uint64_t>(j0) + span <= p.n_in;   // CTA-uniform
+            if (interior) {
+                const float2* src = p.x + j0 + tid;
+                for (uint32_t i = tid; i < span; i += nthreads) {
+                    const uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * 8u;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                    src += nthreads;
+                    plane += step_plane;
+                    pos += step_pos;
+                    if (plane >= p.R) {
+                        plane -= p.R;
+                        ++pos;
                     }
-                } else if (j >= -hist_len) {
-                    v = p.hist[hist_len + j];
                 }
-                planes[static_cast<size_t>(plane) * p.plane_pitch + pos] = v;
-                plane += step_plane;
-                pos += step_pos;
-                if (plane >= p.R) {
-                    plane -= p.R;
-                    ++pos;
+            } else {
+                for (uint32_t i = tid; i < span; i += nthreads) {
+                    const int64_t j = j0 + i;
+                    const float2* src = p.x;
+                    uint32_t bytes = 0;
+                    if (j >= 0) {
+                        if (static_cast<uint64_t>(j) < p.n_in) {
+                            src = p.x + j;
+                            bytes = 8;
+                        }
+                    } else if (j >= -hist_len) {
+                        src = p.hist + (hist_len + j);
+                        bytes = 8;
+                    }
+                    const uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * 8u;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes)
+                                 : "memory");
+                    plane += step_plane;
+                    pos += step_pos;
+                    if (plane >= p.R) {
+                        plane -= p.R;
+                        ++pos;
+                    }
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
 
@@ -102,19 +129,21 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 for (int i = 0; i < OB; ++i) {
                     w[i] = xp[i];
                 }
+                const float2* xq = xp;      // xq[-(s+1)] is the element tap (m0 + s + 1) slides in
+                const float* hq = hp;
                 for (uint32_t m0 = 0; m0 < p.lp_pad; m0 += OB) {
 #pragma unroll
                     for (int s = 0; s < OB; ++s) {
                         // logical window element i lives in w[(i - s) mod OB]
                         if constexpr (REAL_TAPS) {
-                            const float h = hp[m0 + s];
+                            const float h = hq[s];
                             const float2 hh = make_float2(h, h);
 #pragma unroll
                             for (int i = 0; i < OB; ++i) {
                                 acc[i] = __ffma2_rn(w[(i - s + OB) % OB], hh, acc[i]);
                             }
                         } else {
-                            const float2 h = reinterpret_cast<const float2*>(hp)[m0 + s];
+                            const float2 h = reinterpret_cast<const float2*>(hq)[s];
                             const float2 hr = make_float2(h.x, h.x), hi = make_float2(-h.y, h.y);
 #pragma unroll
                             for (int i = 0; i < OB; ++i) {
@@ -124,8 +153,10 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                             }
                         }
                         // slide: next tap (m+1) needs row offset one lower
-                        w[(OB - 1 - s) % OB] = xp[-static_cast<int>(m0 + s) - 1];
+                        w[(OB - 1 - s) % OB] = xq[-s - 1];
                     }
+                    xq -= OB;
+                    hq += OB * (REAL_TAPS ? 1 : 2);
                 }
             }
             // ---- stage the tile's outputs, then store coalesced
@@ -135,12 +166,24 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 out_s[o0 + i] = acc[i];
             }
             __syncthreads();
-            for (uint32_t o = tid; o < p.qt; o += nthreads) {
-                const uint64_t q = q0 + o;
-                if (q < p.n_out) {
-                    const uint64_t frame = q / p.frame_out;
-                    const uint64_t m = q - frame * p.frame_out;
-                    stg_stream_f2(p.y + (frame * p.heads + head) * p.frame_out + m, out_s[o]);
+            if (p.heads == 1) {
+                for (uint32_t o = tid; o < p.qt; o += nthreads) {
+                    if (q0 + o < p.n_out) {
+                        stg_stream_f2(p.y + q0 + o, out_s[o]);      // [frames, 1, frame_out] is the stream itself
+                    }
+                }
+            } else {
+                uint64_t frame = (q0 + tid) / p.frame_out;
+                uint64_t m = (q0 + tid) - frame * p.frame_out;
+                for (uint32_t o = tid; o < p.qt; o += nthreads) {
+                    if (q0 + o < p.n_out) {
+                        stg_stream_f2(p.y + (frame * p.heads + head) * p.frame_out + m, out_s[o]);
+                    }
+                    m += nthreads;
+                    while (m >= p.frame_out) {
+                        m -= p.frame_out;
+                        ++frame;
+                    }
                 }
             }
         }
