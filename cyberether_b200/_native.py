@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200_amplitude_scaling_coeff": (c_int, [c_u64, P(c_f32)]),
     "b200_range_coefficients": (c_int, [c_f32, c_f32, P(c_f32), P(c_f32)]),
     "b200_cast_f32_cf32": (c_int, [c_vp, c_vp, c_vp, c_u64, c_vp]),
+    "b200_copy_strided": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, P(c_u64), P(c_u64), P(c_u64), c_vp]),
     "b200_chain_plan_create": (c_int, [c_vp, c_u64, c_u64, c_vp, P(c_vp)]),
     "b200_chain_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_vp]),
     "b200_chain_exec_host": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_u64]),

@@ -224,6 +224,34 @@ __global__ void cast_f32_cf32_kernel(const float* __restrict__ in, float2* __res
     }
 }
 
+// ---- strided copy (layout gather / scatter) ----------------------------------------------------------
+// The role of the reference's fft_layout kernel (src/domains/dsp/fft/module_impl_native_cuda.cc:31-141): bring a
+// strided / permuted view into the contiguous [batch, n] layout the fast kernels use, and scatter results back.
+struct CopyPlan {
+    int rank;
+    uint64_t shape[8];
+    uint64_t src_stride[8];
+    uint64_t dst_stride[8];
+};
+
+template <typename T>
+__global__ void copy_strided_kernel(const T* __restrict__ src, T* __restrict__ dst, const uint64_t total,
+                                    const CopyPlan plan) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        uint64_t rem = i, os = 0, od = 0;
+#pragma unroll 1
+        for (int d = plan.rank - 1; d >= 0; --d) {
+            const uint64_t q = rem / plan.shape[d];
+            const uint64_t coord = rem - q * plan.shape[d];
+            rem = q;
+            os += coord * plan.src_stride[d];
+            od += coord * plan.dst_stride[d];
+        }
+        dst[od] = src[os];
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
@@ -397,6 +425,36 @@ int b200_range_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, f
     DeviceGuard guard(ctx);
     range_f32_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(in, out, count, scale,
                                                                                             offset);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+int b200_copy_strided(b200_ctx* ctx, const void* src, void* dst, int elem_bytes, int rank, const uint64_t* shape,
+                      const uint64_t* src_stride, const uint64_t* dst_stride, b200_stream stream) {
+    B200_REQUIRE(ctx && src && dst && shape && src_stride && dst_stride, "b200_copy_strided: null argument");
+    B200_REQUIRE(rank >= 1 && rank <= 8, "b200_copy_strided: rank %d unsupported (1..8)", rank);
+    B200_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "b200_copy_strided: element size must be 4 (F32) or 8 (CF32)");
+    CopyPlan plan{};
+    plan.rank = rank;
+    uint64_t total = 1;
+    for (int d = 0; d < rank; ++d) {
+        plan.shape[d] = shape[d];
+        plan.src_stride[d] = src_stride[d];
+        plan.dst_stride[d] = dst_stride[d];
+        total *= shape[d];
+    }
+    if (total == 0) {
+        return B200_SUCCESS;
+    }
+    DeviceGuard guard(ctx);
+    const int grid = stream_grid(ctx, total, 256, 8);
+    if (elem_bytes == 8) {
+        copy_strided_kernel<float2><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float2*>(src),
+                                                                          static_cast<float2*>(dst), total, plan);
+    } else {
+        copy_strided_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(src),
+                                                                         static_cast<float*>(dst), total, plan);
+    }
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

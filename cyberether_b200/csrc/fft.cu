@@ -13,7 +13,7 @@
 #define B200_FFT4096_DEFAULT_CTAS 2
 #endif
 
-#include "fft4096.cuh"
+#include "fft_radix.cuh"
 
 namespace b200 {
 
@@ -211,13 +211,72 @@ static int launch_generic_bpt(const b200_ctx* ctx, const FftParams& p, cudaStrea
     return B200_SUCCESS;
 }
 
+template <int LOG2N, int MODE, int WIN>
+static int launch_radix(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    auto kernel = fft_radix_kernel<LOG2N, MODE, WIN>;
+    constexpr int smem = radix_smem_bytes(LOG2N);
+    constexpr int threads = radix_threads(LOG2N);
+    constexpr int per_sm = threads > 256 ? 1 : 2;
+    static bool configured[64] = {};
+    if (!configured[ctx->device & 63]) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[ctx->device & 63] = true;
+    }
+    const uint64_t rows_per_block = static_cast<uint64_t>(threads) * 16 >> LOG2N;
+    const uint64_t blocks = (p.rows + rows_per_block - 1) / rows_per_block;
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * per_sm;
+    kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), threads, smem, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+// Register-radix kernel for the (mode, window) combinations the modules actually use; 0 = not handled here.
+template <int MODE, int WIN>
+static int try_launch_radix(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    constexpr bool kInstantiated = (MODE == MODE_C2C && WIN == WIN_NONE) || (MODE != MODE_C2C && WIN == WIN_REAL);
+    if constexpr (kInstantiated) {
+        if ((reinterpret_cast<uintptr_t>(p.in) & 15u) != 0) {
+            return B200_SUCCESS;
+        }
+        *handled = true;
+        switch (p.n) {
+            case 16: return launch_radix<4, MODE, WIN>(ctx, p, stream);
+            case 32: return launch_radix<5, MODE, WIN>(ctx, p, stream);
+            case 64: return launch_radix<6, MODE, WIN>(ctx, p, stream);
+            case 128: return launch_radix<7, MODE, WIN>(ctx, p, stream);
+            case 256: return launch_radix<8, MODE, WIN>(ctx, p, stream);
+            case 512: return launch_radix<9, MODE, WIN>(ctx, p, stream);
+            case 1024: return launch_radix<10, MODE, WIN>(ctx, p, stream);
+            case 2048: return launch_radix<11, MODE, WIN>(ctx, p, stream);
+            case 4096: return launch_radix<12, MODE, WIN>(ctx, p, stream);
+            case 8192: return launch_radix<13, MODE, WIN>(ctx, p, stream);
+            default: *handled = false; return B200_SUCCESS;
+        }
+    }
+    return B200_SUCCESS;
+}
+
+static bool fft4096_use_generic() {
+    static const bool value = [] {
+        const char* env = getenv("B200_FFT4096_GENERIC");
+        return env && atoi(env) != 0;
+    }();
+    return value;
+}
+
 template <int MODE, int WIN>
 static int launch_fft(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
     if (p.rows == 0) {
         return B200_SUCCESS;
     }
-    if (p.n == kFft4096N && (reinterpret_cast<uintptr_t>(p.in) & 15u) == 0) {
+    if (p.n == kFft4096N && (reinterpret_cast<uintptr_t>(p.in) & 15u) == 0 && !fft4096_use_generic()) {
         return launch_4096<MODE, WIN>(ctx, p, stream);
+    }
+    bool handled = false;
+    const int rc = try_launch_radix<MODE, WIN>(ctx, p, stream, &handled);
+    if (handled || rc != B200_SUCCESS) {
+        return rc;
     }
     if (p.n <= 1024) {
         return launch_generic_bpt<MODE, WIN, 1>(ctx, p, stream);

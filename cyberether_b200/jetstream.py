@@ -393,6 +393,44 @@ def _u64_array(values: Sequence[int]):
     return (ctypes.c_uint64 * len(values))(*[int(v) for v in values])
 
 
+def _contiguous_strides(shape: Sequence[int]) -> List[int]:
+    strides, acc = [], 1
+    for dim in reversed(list(shape)):
+        strides.append(acc)
+        acc *= int(dim)
+    return list(reversed(strides))
+
+
+class _Layout:
+    """DISCONTIGUOUS support: brings a strided and/or permuted view into a contiguous staging tensor whose last
+    axis is the chosen one (gather) and writes a contiguous staging result back through the inverse mapping
+    (scatter), with b200_copy_strided — the role of the reference's fft_layout kernel
+    (src/domains/dsp/fft/module_impl_native_cuda.cc:31-141). `direct` = already contiguous with the axis last."""
+
+    def __init__(self, tensor: torch.Tensor, axis: Optional[int]):
+        rank = tensor.dim()
+        self.axis = rank - 1 if axis is None else axis
+        self.perm = [d for d in range(rank) if d != self.axis] + [self.axis]
+        self.direct = tensor.is_contiguous() and self.axis == rank - 1
+        self.shape_p = [tensor.shape[d] for d in self.perm]
+
+    def gather(self, ctx, src: torch.Tensor, staging: torch.Tensor, stream) -> "Result":
+        shape = _u64_array(self.shape_p)
+        src_stride = _u64_array([src.stride(d) for d in self.perm])
+        dst_stride = _u64_array(_contiguous_strides(self.shape_p))
+        return _call("b200_copy_strided", ctx.handle, ctypes.c_void_p(src.data_ptr()),
+                     ctypes.c_void_p(staging.data_ptr()), src.element_size(), len(self.shape_p), shape, src_stride,
+                     dst_stride, stream)
+
+    def scatter(self, ctx, staging: torch.Tensor, dst: torch.Tensor, shape_p: Sequence[int], stream) -> "Result":
+        shape = _u64_array(shape_p)
+        src_stride = _u64_array(_contiguous_strides(shape_p))
+        dst_stride = _u64_array([dst.stride(d) for d in self.perm])
+        return _call("b200_copy_strided", ctx.handle, ctypes.c_void_p(staging.data_ptr()),
+                     ctypes.c_void_p(dst.data_ptr()), dst.element_size(), len(shape_p), shape, src_stride, dst_stride,
+                     stream)
+
+
 # ---------------------------------------------------------------------------------------------
 # Modules on the hot path (type strings / config fields / ports: SURVEY.md Appendix C)
 # ---------------------------------------------------------------------------------------------
@@ -452,8 +490,12 @@ class Invert(Module):
 
     def create_impl(self):
         self.input = self.inputs["signal"].tensor
-        if not self.input.contiguous():
-            return _error("[MODULE_INVERT_B200] Strided inputs are not supported by this provider yet.")
+        self._layout = _Layout(self.input.data, None)
+        self._layout.perm = list(range(self.input.rank))
+        self._layout.shape_p = list(self.input.shape)
+        self._layout.direct = self.input.contiguous()
+        self._staging = None if self._layout.direct else torch.empty(self.input.shape, dtype=torch.complex64,
+                                                                      device=self.input.device)
         self.output = Tensor.create(self.input.device, "CF32", self.input.shape)
         self.output.propagate_attributes(self.input)
         self.outputs["signal"] = TensorLink()
@@ -469,7 +511,13 @@ class Invert(Module):
         if err:
             return err
         ctx = Context.get(self.input.device)
-        return _call("b200_invert_cf32", ctx.handle, self.input.ptr(), self.output.ptr(), self._outer, self._n,
+        src = self.input.ptr()
+        if not self._layout.direct:
+            result = self._layout.gather(ctx, self.input.data, self._staging, stream)
+            if result != Result.SUCCESS:
+                return result
+            src = ctypes.c_void_p(self._staging.data_ptr())
+        return _call("b200_invert_cf32", ctx.handle, src, self.output.ptr(), self._outer, self._n,
                      self._inner, stream)
 
 
@@ -670,7 +718,9 @@ class MultiplyConstant(Module):
 
 @register_module
 class Fft(Module):
-    """`fft` — src/domains/dsp/fft/module_impl.cc:8-96; C2C along the sample axis, unnormalised."""
+    """`fft` — src/domains/dsp/fft/module_impl.cc:8-96; unnormalised C2C along the sample axis. Any sample axis and
+    strided inputs are accepted (Taint::DISCONTIGUOUS): they are gathered into the contiguous [batch, n] layout of
+    the kernels and scattered back. Real-input transforms (R2C / FFTPACK) are not implemented yet."""
     TYPE = "fft"
     DEFAULTS = {"forward": True, "complexOutput": False}
 
@@ -692,9 +742,6 @@ class Fft(Module):
         if t.dtype != "CF32":
             return _error("[MODULE_FFT_B200] Real-input transforms (R2C / FFTPACK R2R) are not implemented by "
                           "this provider yet; cast to CF32 first.")
-        if axes.sample != t.rank - 1:
-            return _error("[MODULE_FFT_B200] Transforms along a non-innermost axis are not implemented by this "
-                          "provider yet.")
         self._axis = axes.sample
         return Result.SUCCESS
 
@@ -705,14 +752,16 @@ class Fft(Module):
 
     def create_impl(self):
         self.input = self.inputs["signal"].tensor
-        if not self.input.contiguous():
-            return _error("[MODULE_FFT_B200] Strided inputs are not supported by this provider yet.")
         self.output = Tensor.create(self.input.device, "CF32", self.input.shape)
         self.output.propagate_attributes(self.input)
         self.outputs["signal"] = TensorLink()
         self.outputs["signal"].produced(self.name, "signal", self.output)
         self._n = self.input.shape[self._axis]
         self._batch = self.input.size // self._n
+        self._layout = _Layout(self.input.data, self._axis)
+        self._staging = None
+        if not self._layout.direct:
+            self._staging = torch.empty(self._layout.shape_p, dtype=torch.complex64, device=self.input.device)
         return Result.SUCCESS
 
     def compute_initialize(self):
@@ -731,8 +780,18 @@ class Fft(Module):
             result = self.compute_initialize()
             if result != Result.SUCCESS:
                 return result
-        return _call("b200_fft_exec", self._plan_handle, self.input.ptr(), self.output.ptr(),
-                     1 if self.config["forward"] else 0, stream)
+        forward = 1 if self.config["forward"] else 0
+        if self._layout.direct:
+            return _call("b200_fft_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), forward, stream)
+        ctx = Context.get(self.input.device)
+        result = self._layout.gather(ctx, self.input.data, self._staging, stream)
+        if result != Result.SUCCESS:
+            return result
+        ptr = ctypes.c_void_p(self._staging.data_ptr())
+        result = _call("b200_fft_exec", self._plan_handle, ptr, ptr, forward, stream)      # in place
+        if result != Result.SUCCESS:
+            return result
+        return self._layout.scatter(ctx, self._staging, self.output.data, self._layout.shape_p, stream)
 
     def compute_deinitialize(self):
         if self._plan_handle is not None:
@@ -785,8 +844,12 @@ class Amplitude(Module):
 
     def create_impl(self):
         self.input = self.inputs["signal"].tensor
-        if not self.input.contiguous():
-            return _error("[MODULE_AMPLITUDE_B200] Strided inputs are not supported by this provider yet.")
+        self._layout = _Layout(self.input.data, None)
+        self._layout.perm = list(range(self.input.rank))       # keep the axis order, only densify
+        self._layout.shape_p = list(self.input.shape)
+        self._layout.direct = self.input.contiguous()
+        self._staging = None if self._layout.direct else torch.empty(self.input.shape, dtype=self.input.data.dtype,
+                                                                      device=self.input.device)
         self.scaling_coeff = amplitude_scaling_coeff(self._norm)
         self.output = Tensor.create(self.input.device, "F32", self.input.shape)
         self.output.propagate_attributes(self.input)
@@ -800,7 +863,13 @@ class Amplitude(Module):
             return err
         ctx = Context.get(self.input.device)
         fn = "b200_amplitude_cf32" if self.input.dtype == "CF32" else "b200_amplitude_f32"
-        return _call(fn, ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size,
+        src = self.input.ptr()
+        if not self._layout.direct:
+            result = self._layout.gather(ctx, self.input.data, self._staging, stream)
+            if result != Result.SUCCESS:
+                return result
+            src = ctypes.c_void_p(self._staging.data_ptr())
+        return _call(fn, ctx.handle, src, self.output.ptr(), self.input.size,
                      ctypes.c_float(self.scaling_coeff), stream)
 
 
@@ -833,8 +902,12 @@ class Range(Module):
 
     def create_impl(self):
         self.input = self.inputs["signal"].tensor
-        if not self.input.contiguous():
-            return _error("[MODULE_RANGE_B200] Strided inputs are not supported by this provider yet.")
+        self._layout = _Layout(self.input.data, None)
+        self._layout.perm = list(range(self.input.rank))
+        self._layout.shape_p = list(self.input.shape)
+        self._layout.direct = self.input.contiguous()
+        self._staging = None if self._layout.direct else torch.empty(self.input.shape, dtype=torch.float32,
+                                                                      device=self.input.device)
         self.scale, self.offset = range_coefficients(float(self.config["min"]), float(self.config["max"]))
         self.output = Tensor.create(self.input.device, "F32", self.input.shape)
         self.output.propagate_attributes(self.input)
@@ -851,7 +924,13 @@ class Range(Module):
         if err:
             return err
         ctx = Context.get(self.input.device)
-        return _call("b200_range_f32", ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size,
+        src = self.input.ptr()
+        if not self._layout.direct:
+            result = self._layout.gather(ctx, self.input.data, self._staging, stream)
+            if result != Result.SUCCESS:
+                return result
+            src = ctypes.c_void_p(self._staging.data_ptr())
+        return _call("b200_range_f32", ctx.handle, src, self.output.ptr(), self.input.size,
                      ctypes.c_float(self.scale), ctypes.c_float(self.offset), stream)
 
 

@@ -119,6 +119,13 @@ int b200_range_coefficients(float min, float max, float* scale, float* offset);
 int b200_range_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, float scale,
                    float offset, b200_stream stream);
 
+/* Layout gather / scatter: strided element copy over `shape` (rank <= 8, strides in ELEMENTS, elem_bytes 4 or 8).
+ * The role of the reference's `fft_layout` kernel, src/domains/dsp/fft/module_impl_native_cuda.cc:31-141: modules that
+ * declare Module::Taint::DISCONTIGUOUS bring strided / non-innermost-axis views into the contiguous [batch, n]
+ * layout of the fast kernels with it and scatter the result back. */
+int b200_copy_strided(b200_ctx* ctx, const void* src, void* dst, int elem_bytes, int rank, const uint64_t* shape,
+                      const uint64_t* src_stride, const uint64_t* dst_stride, b200_stream stream);
+
 /* cast F32 -> CF32 (imag 0) — src/domains/core/cast/module_impl_native_cpu.cc (CF32 input bypasses). */
 int b200_cast_f32_cf32(b200_ctx* ctx, const float* in, b200_cf32* out, uint64_t count, b200_stream stream);
 

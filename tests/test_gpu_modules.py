@@ -162,3 +162,64 @@ def test_cast_bypass_and_f32():
     x = np.arange(8, dtype=np.float32)
     got = _run("cast", {"buffer": x}, {"outputType": "CF32"}, out="buffer")
     assert np.array_equal(got, x.astype(np.complex64))
+
+
+# ---- DISCONTIGUOUS layouts (reference: "Trailing Batch Strided", "Rank 3 Batched Heads", "Rank 4 Non-Contiguous") ----
+
+def _run_view(module_type, base, view_fn, axes, config=None, out="signal"):
+    """Feeds a strided/permuted torch VIEW of `base` (so the module really sees a non-contiguous tensor)."""
+    import torch
+    import cyberether_b200 as cb
+    from cyberether_b200.jetstream import TensorLink, NativeCudaRuntime
+    dev = torch.from_numpy(base).cuda()
+    tensor = cb.Tensor(view_fn(dev), dict(axes))
+    module = cb.build_module(module_type)
+    assert module.create("dut", config, {"signal": TensorLink(tensor=tensor)}) == cb.Result.SUCCESS, cb.last_error()
+    rt = NativeCudaRuntime("t")
+    assert rt.create([module]) == cb.Result.SUCCESS
+    assert rt.compute([], set(), set()) == cb.Result.SUCCESS, cb.last_error()
+    result = module.outputs[out].tensor.numpy()
+    rt.destroy()
+    module.destroy()
+    return result
+
+
+def test_fft_trailing_batch_axis(ref):
+    """Sample axis 0, batch axis 1 ("FFT - Trailing Batch Roundtrip CF32", fft/module_tests.cc:802-852)."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((256, 6), 21)
+    want = ref.run_block("fft", {"signal": x}, {"forward": True}, "signal", axes={"signal": (0, 1, -1)})
+    got = _run_view("fft", x, lambda t: t, {"sampleAxis": 0, "batchAxis": 1}, {"forward": True})
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_fft_rank3_heads_middle_sample_axis(ref):
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((3, 128, 5), 22)
+    want = ref.run_block("fft", {"signal": x}, {"forward": False}, "signal", axes={"signal": (1, 0, 2)})
+    got = _run_view("fft", x, lambda t: t, {"sampleAxis": 1, "batchAxis": 0, "channelAxis": 2}, {"forward": False})
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_fft_strided_slice_view():
+    """A strided view (every other row of a larger buffer, offset start) transforms like its dense copy."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    base = gaussian_cf32((10, 512), 23)
+    got = _run_view("fft", base, lambda t: t[1::2, :], {"sampleAxis": 1, "batchAxis": 0}, {"forward": True})
+    want = np.fft.fft(base[1::2, :].astype(np.complex128), axis=1)
+    assert got.shape == (5, 512)
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_amplitude_and_range_non_contiguous_bit_exact(ref):
+    from cyberether_b200.synthetic import gaussian_cf32
+    base = gaussian_cf32((4, 6, 64), 24, 5.0)
+    view = np.ascontiguousarray(base.transpose(1, 0, 2)[:, ::2, :])          # dense copy of what the view holds
+    got = _run_view("amplitude", base, lambda t: t.permute(1, 0, 2)[:, ::2, :], {"sampleAxis": 2})
+    want = ref.run_block("amplitude", {"signal": view}, None, "signal", axes={"signal": (2, -1, -1)})
+    assert np.array_equal(got, want)
+    fbase = np.random.default_rng(1).standard_normal((6, 40)).astype(np.float32)
+    got = _run_view("range", fbase, lambda t: t[:, ::4], {}, {"min": -2.0, "max": 2.0})
+    want = ref.range_(np.ascontiguousarray(fbase[:, ::4]), -2.0, 2.0)
+    assert np.abs(got - want).max() <= 2.5e-7

@@ -140,3 +140,58 @@ def test_fir_polyphase_plane_indexing():
                     acc += tap * planes[plane, o + d - m]
             want = sum(h[k] * xs[(o + hpad) * R - k] for k in range(L))
             assert abs(acc - want) < 1e-9
+
+
+def _radices(log2n):
+    rem, out = 1 << log2n, []
+    while rem > 1:
+        r = min(16, rem)
+        out.append(r)
+        rem //= r
+    return out
+
+
+def test_fft_radix_kernel_padded_stockham_scheme():
+    """fft_radix_kernel (16 <= N <= 8192): block of THREADS*16 samples, passes ping-pong between the exchange
+    buffer and the stage buffer through pad(a) = a + a/16; checks the result and that every exchange store of a
+    half-warp hits 16 distinct 8-byte bank pairs."""
+    from collections import defaultdict
+    pad = lambda a: a + (a >> 4)
+    for log2n in range(4, 14):
+        n, rad = 1 << log2n, _radices(log2n)
+        threads = max(256, n // 16)
+        block, t_per_row = threads * 16, n // 16
+        rows = block // n
+        rng = np.random.default_rng(log2n)
+        x = rng.standard_normal(block) + 1j * rng.standard_normal(block)
+        bufs = [np.zeros(block + block // 16 + 16, complex) for _ in range(2)]
+        bufs[0][:block] = x                                   # the TMA lands the block linearly
+        out = np.zeros(block, complex)
+        ns = 1
+        for p, r in enumerate(rad):
+            last = p == len(rad) - 1
+            src, dst = bufs[p % 2], bufs[(p + 1) % 2]
+            writes = []
+            for tid in range(threads):
+                g, lt = tid // t_per_row, tid % t_per_row
+                for b in range(16 // r):
+                    j = lt + b * t_per_row
+                    k = j & (ns - 1)
+                    u = [src[(g * n + j + t * (n // r)) if p == 0 else pad(g * n + j + t * (n // r))] for t in range(r)]
+                    w = np.exp(-2j * np.pi * k / (r * ns))
+                    y = np.fft.fft(np.array([u[t] * w ** t for t in range(r)]))
+                    j0 = (j - k) * r + k
+                    for t in range(r):
+                        a = g * n + j0 + t * ns
+                        if last:
+                            out[a] = y[t]
+                        else:
+                            writes.append((pad(a), y[t], tid, b, t))
+            banks = defaultdict(list)
+            for a, val, tid, b, t in writes:
+                dst[a] = val
+                banks[(tid // 16, b, t)].append(a % 16)
+            assert all(len(set(v)) == len(v) for v in banks.values()), (log2n, p)
+            ns *= r
+        want = np.fft.fft(x.reshape(rows, n), axis=1).reshape(-1)
+        assert np.abs(out - want).max() < 1e-9 * n, log2n
