@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -292,7 +293,13 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
     // Tile geometry: the largest odd OB (register sliding window) whose staged planes fit ~96 KB.
     const uint32_t lp = (pl->L + pl->R - 1) / pl->R;
     const int ob_options[4] = {7, 5, 3, 1};
-    const uint32_t thread_options[3] = {128, 64, 32};
+    uint32_t thread_options[3] = {128, 64, 32};
+    if (const char* env = getenv("B200_FIR_THREADS")) {          // A/B aid: preferred CTA size
+        const int v = atoi(env);
+        if (v == 32 || v == 64 || v == 128) {
+            thread_options[0] = static_cast<uint32_t>(v);
+        }
+    }
     bool found = false;
     for (int oi = 0; oi < 4 && !found; ++oi) {
         for (int ti = 0; ti < 3 && !found; ++ti) {

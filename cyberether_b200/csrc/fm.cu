@@ -8,6 +8,7 @@
 // the de-emphasis recurrence is evaluated as a blocked linear-recurrence scan: per-chunk (gain, offset)
 // pairs -> serial carry propagation over chunks -> each chunk replayed sequentially from its carry in the
 // reference's own operation order.
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -132,6 +133,296 @@ __global__ void fm_deemph_apply_kernel(float* __restrict__ d, const float2* __re
     }
 }
 
+// =====================================================================================================
+// Wideband (stereo) FM — src/domains/dsp/fm/module_impl_native_cpu.cc:130-170.
+// Per sample the reference runs, sequentially per lane:
+//   NCO pilot phase (F32 running sum with wrap, input independent)
+//   4 one-pole filters (pilot I/Q, two cascaded)            -> pilotCos, pilotSin
+//   sum  = LP3(notch(d))                                     4 biquads
+//   diff = LP3(notch(2 d sin(2 (phase + atan2(pilotCos, pilotSin)))))
+//   left/right = sum +- diff, optional one-pole de-emphasis each
+// Every stage is a small LINEAR recurrence driven by a pointwise function of earlier stages, so each is
+// evaluated as a blocked scan: (1) per chunk, zero-state response at the chunk end; (2) serial carry
+// propagation over chunks, state <- A^m state + response (A^C pre-evaluated on the host in F64, A^m by stepping
+// for the rare chunk that contains non-finite samples); (3) replay of each chunk from its carry with the
+// reference's own operation order (no FMA contraction). Non-finite discriminator samples emit NaN and leave
+// every filter state untouched, exactly as the reference's `continue` path.
+// =====================================================================================================
+
+struct Biquad {
+    float b0, b1, b2, a1, a2;
+};
+
+struct FmWideCoeffs {
+    float pilot_alpha;
+    float pilot_phase_increment;
+    float deemphasis_alpha;
+    int deemphasis;
+    Biquad notch;
+    Biquad lowpass[3];
+};
+
+constexpr int kWideChunk = 256;
+constexpr float kTwoPiF = 6.28318530717958647692f;   // (float)(2.0f * JST_PI): the reference compares/subtracts in double
+                                                     // of a float, see advance_phase
+
+// FmImpl::applyBiquad (src/domains/dsp/fm/module_impl.cc:157-164), transposed direct form II, no FMA.
+__device__ __forceinline__ float biquad_step(const float x, const Biquad& c, float& z1, float& z2) {
+    const float y = __fadd_rn(__fmul_rn(c.b0, x), z1);
+    z1 = __fadd_rn(__fsub_rn(__fmul_rn(c.b1, x), __fmul_rn(c.a1, y)), z2);
+    z2 = __fsub_rn(__fmul_rn(c.b2, x), __fmul_rn(c.a2, y));
+    return y;
+}
+
+// state.pilotPhase += inc; if (state.pilotPhase >= 2.0f * JST_PI) state.pilotPhase -= 2.0f * JST_PI;
+// JST_PI is a double literal, so the comparison and the subtraction happen in F64 and round back to F32.
+__device__ __forceinline__ float advance_phase(float phase, const float inc) {
+    phase = __fadd_rn(phase, inc);
+    const double two_pi = 2.0 * 3.14159265358979323846;
+    if (static_cast<double>(phase) >= two_pi) {
+        phase = static_cast<float>(static_cast<double>(phase) - two_pi);
+    }
+    return phase;
+}
+
+// The NCO phase is input independent and identical for every lane: one thread evaluates the F32 recurrence.
+__global__ void fm_wide_phase_kernel(float* __restrict__ phase, float* __restrict__ phase_state, const uint64_t lane_len,
+                                     const float inc) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) {
+        return;
+    }
+    float ph = *phase_state;
+    for (uint64_t n = 0; n < lane_len; ++n) {
+        phase[n] = ph;
+        ph = advance_phase(ph, inc);
+    }
+    *phase_state = ph;
+}
+
+// Generic blocked scan over S-state systems. System must provide:
+//   static constexpr int S;  __device__ void step(float* state, uint64_t n, lane, bool replay)  — one sample, reference op order;
+//   returns false when the sample is skipped (non-finite discriminator).
+template <class System>
+__global__ void scan_reduce_kernel(const System sys, float* __restrict__ chunk_resp, int* __restrict__ chunk_count,
+                                   const uint64_t lanes, const uint64_t lane_len, const uint64_t chunks_per_lane) {
+    const uint64_t total = lanes * chunks_per_lane;
+    for (uint64_t c = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; c < total;
+         c += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t lane = c / chunks_per_lane, n0 = (c % chunks_per_lane) * kWideChunk;
+        float st[System::S];
+#pragma unroll
+        for (int i = 0; i < System::S; ++i) {
+            st[i] = 0.0f;
+        }
+        int count = 0;
+        for (uint64_t n = n0; n < n0 + kWideChunk && n < lane_len; ++n) {
+            count += sys.step(st, n, lane, false) ? 1 : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < System::S; ++i) {
+            chunk_resp[c * System::S + i] = st[i];
+        }
+        chunk_count[c] = count;
+    }
+}
+
+// carry-in of chunk c overwrites its response slot; `power` is A^kWideChunk (row-major S x S, F32).
+template <class System>
+__global__ void scan_carry_kernel(const System sys, float* __restrict__ chunk_resp, const int* __restrict__ chunk_count,
+                                  const float* __restrict__ power, float* __restrict__ lane_state,
+                                  const uint64_t lanes, const uint64_t chunks_per_lane) {
+    const uint64_t lane = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (lane >= lanes) {
+        return;
+    }
+    float st[System::S];
+#pragma unroll
+    for (int i = 0; i < System::S; ++i) {
+        st[i] = lane_state[lane * System::S + i];
+    }
+    for (uint64_t c = 0; c < chunks_per_lane; ++c) {
+        float* const slot = chunk_resp + (lane * chunks_per_lane + c) * System::S;
+        float resp[System::S], next[System::S];
+#pragma unroll
+        for (int i = 0; i < System::S; ++i) {
+            resp[i] = slot[i];
+            slot[i] = st[i];
+        }
+        const int count = chunk_count[lane * chunks_per_lane + c];
+        if (count == kWideChunk) {
+#pragma unroll
+            for (int i = 0; i < System::S; ++i) {
+                float acc = resp[i];
+#pragma unroll
+                for (int j = 0; j < System::S; ++j) {
+                    acc = fmaf(power[i * System::S + j], st[j], acc);
+                }
+                next[i] = acc;
+            }
+        } else {
+            // homogeneous response by stepping `count` zero-input samples, then add the zero-state response
+#pragma unroll
+            for (int i = 0; i < System::S; ++i) {
+                next[i] = st[i];
+            }
+            for (int k = 0; k < count; ++k) {
+                sys.step_homogeneous(next);
+            }
+#pragma unroll
+            for (int i = 0; i < System::S; ++i) {
+                next[i] += resp[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < System::S; ++i) {
+            st[i] = next[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < System::S; ++i) {
+        lane_state[lane * System::S + i] = st[i];
+    }
+}
+
+template <class System>
+__global__ void scan_replay_kernel(const System sys, const float* __restrict__ chunk_carry, const uint64_t lanes,
+                                   const uint64_t lane_len, const uint64_t chunks_per_lane) {
+    const uint64_t total = lanes * chunks_per_lane;
+    for (uint64_t c = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; c < total;
+         c += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t lane = c / chunks_per_lane, n0 = (c % chunks_per_lane) * kWideChunk;
+        float st[System::S];
+#pragma unroll
+        for (int i = 0; i < System::S; ++i) {
+            st[i] = chunk_carry[c * System::S + i];
+        }
+        for (uint64_t n = n0; n < n0 + kWideChunk && n < lane_len; ++n) {
+            sys.step(st, n, lane, true);
+        }
+    }
+}
+
+// Addressing of sample n of `lane` inside [frames, lanes, frame_len].
+struct LaneIndex {
+    uint64_t lanes, frame_len;
+    __device__ __forceinline__ uint64_t operator()(const uint64_t lane, const uint64_t n) const {
+        const uint64_t frame = n / frame_len, s = n - frame * frame_len;
+        return (frame * lanes + lane) * frame_len + s;
+    }
+};
+
+// (P) pilot recovery: state [cosStage, sinStage, pilotCos, pilotSin]; replay writes the difference-channel input
+//     2 d sin(2 (phase + atan2(pilotCos, pilotSin))) computed from the state BEFORE... no: AFTER this sample's update,
+//     as the reference does (module_impl_native_cpu.cc:133-147).
+struct PilotSystem {
+    static constexpr int S = 4;
+    const float* d;         // discriminator output [frames, lanes, frame_len]
+    const float* phase;     // [lane_len]
+    float* diff_in;         // [frames, lanes, frame_len]
+    LaneIndex at;
+    float alpha;
+    __device__ __forceinline__ bool step(float* st, const uint64_t n, const uint64_t lane, const bool replay) const {
+        const uint64_t e = at(lane, n);
+        const float v = d[e];
+        if (!isfinite(v)) {
+            if (replay) {
+                diff_in[e] = v;
+            }
+            return false;
+        }
+        const float ph = phase[n];
+        const float pc = cosf(ph), ps = sinf(ph);
+        st[0] = __fadd_rn(st[0], __fmul_rn(alpha, __fsub_rn(__fmul_rn(v, pc), st[0])));
+        st[1] = __fadd_rn(st[1], __fmul_rn(alpha, __fsub_rn(__fmul_rn(v, ps), st[1])));
+        st[2] = __fadd_rn(st[2], __fmul_rn(alpha, __fsub_rn(st[0], st[2])));
+        st[3] = __fadd_rn(st[3], __fmul_rn(alpha, __fsub_rn(st[1], st[3])));
+        if (replay) {
+            const float offset = atan2f(st[2], st[3]);
+            const float carrier = sinf(__fmul_rn(2.0f, __fadd_rn(ph, offset)));
+            diff_in[e] = __fmul_rn(__fmul_rn(2.0f, v), carrier);
+        }
+        return true;
+    }
+    __device__ __forceinline__ void step_homogeneous(float* st) const {
+        st[0] = __fadd_rn(st[0], __fmul_rn(alpha, __fsub_rn(0.0f, st[0])));
+        st[1] = __fadd_rn(st[1], __fmul_rn(alpha, __fsub_rn(0.0f, st[1])));
+        st[2] = __fadd_rn(st[2], __fmul_rn(alpha, __fsub_rn(st[0], st[2])));
+        st[3] = __fadd_rn(st[3], __fmul_rn(alpha, __fsub_rn(st[1], st[3])));
+    }
+};
+
+// (A) audio path: notch + 3 low-pass biquads; "lanes" here are 2 * lanes: even = sum path (input d), odd =
+//     difference path (input diff_in). State [notch z1,z2, lp0 z1,z2, lp1 z1,z2, lp2 z1,z2]. Replay writes in place.
+struct AudioSystem {
+    static constexpr int S = 8;
+    float* sum;             // in: d, out: sum          [frames, lanes, frame_len]
+    float* diff;            // in: diff_in, out: difference
+    LaneIndex at;
+    Biquad notch;
+    Biquad lp[3];
+    __device__ __forceinline__ float filter(float x, float* st) const {
+        x = biquad_step(x, notch, st[0], st[1]);
+        x = biquad_step(x, lp[0], st[2], st[3]);
+        x = biquad_step(x, lp[1], st[4], st[5]);
+        return biquad_step(x, lp[2], st[6], st[7]);
+    }
+    __device__ __forceinline__ bool step(float* st, const uint64_t n, const uint64_t vlane, const bool replay) const {
+        float* const buf = (vlane & 1) ? diff : sum;
+        const uint64_t e = at(vlane >> 1, n);
+        const float v = buf[e];
+        if (!isfinite(v)) {
+            return false;
+        }
+        const float y = filter(v, st);
+        if (replay) {
+            buf[e] = y;
+        }
+        return true;
+    }
+    __device__ __forceinline__ void step_homogeneous(float* st) const { (void)filter(0.0f, st); }
+};
+
+// (E) left/right + de-emphasis: state [leftDeemphasis, rightDeemphasis]; writes the interleaved [.., 2] output.
+struct StereoSystem {
+    static constexpr int S = 2;
+    const float* sum;
+    const float* diff;
+    float* out;             // [frames, lanes, frame_len, 2]
+    LaneIndex at;
+    float alpha;
+    int deemphasis;
+    __device__ __forceinline__ bool step(float* st, const uint64_t n, const uint64_t lane, const bool replay) const {
+        const uint64_t e = at(lane, n);
+        const float s = sum[e], df = diff[e];
+        if (!isfinite(s) || !isfinite(df)) {
+            if (replay) {
+                const float q = __int_as_float(0x7fc00000);
+                out[2 * e] = q;
+                out[2 * e + 1] = q;
+            }
+            return false;
+        }
+        float left = __fadd_rn(s, df), right = __fsub_rn(s, df);
+        if (deemphasis) {
+            st[0] = __fadd_rn(st[0], __fmul_rn(alpha, __fsub_rn(left, st[0])));
+            st[1] = __fadd_rn(st[1], __fmul_rn(alpha, __fsub_rn(right, st[1])));
+            left = st[0];
+            right = st[1];
+        }
+        if (replay) {
+            out[2 * e] = left;
+            out[2 * e + 1] = right;
+        }
+        return true;
+    }
+    __device__ __forceinline__ void step_homogeneous(float* st) const {
+        if (deemphasis) {
+            st[0] = __fadd_rn(st[0], __fmul_rn(alpha, __fsub_rn(0.0f, st[0])));
+            st[1] = __fadd_rn(st[1], __fmul_rn(alpha, __fsub_rn(0.0f, st[1])));
+        }
+    }
+};
+
 __global__ void fm_state_update_kernel(const float2* __restrict__ x, FmState* __restrict__ state,
                                        const uint64_t frames, const uint64_t lanes, const uint64_t frame_len) {
     const uint64_t lane = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -151,10 +442,58 @@ struct b200_fm_plan {
     float ref;
     float alpha;          // 1.0 = de-emphasis disabled
     bool deemphasis;
+    bool wide;
     FmState* state;
     float2* chunk_coeff;
     uint64_t chunk_capacity;
+    // wide mode
+    FmWideCoeffs wc;
+    float* wide_state;        // [phase(1) | pilot lanes*4 | audio 2*lanes*8 | stereo lanes*2]
+    float* power;             // [pilot 16 | audio 64 | stereo 4]  A^kWideChunk, row-major
+    float* scratch;           // [sum total | diff total | phase lane_len | chunk_resp | chunk_count]
+    uint64_t scratch_total, scratch_lane_len;
 };
+
+namespace {
+
+// A^kWideChunk of a linear update, evaluated in F64 by stepping unit vectors through `homogeneous`.
+template <int S, class Fn>
+void transition_power(Fn homogeneous, float* out) {
+    for (int j = 0; j < S; ++j) {
+        double st[S] = {};
+        st[j] = 1.0;
+        for (int k = 0; k < kWideChunk; ++k) {
+            homogeneous(st);
+        }
+        for (int i = 0; i < S; ++i) {
+            out[i * S + j] = static_cast<float>(st[i]);
+        }
+    }
+}
+
+void biquad_h(const Biquad& c, double& z1, double& z2, double& x) {
+    const double y = c.b0 * x + z1;
+    z1 = c.b1 * x - c.a1 * y + z2;
+    z2 = c.b2 * x - c.a2 * y;
+    x = y;
+}
+
+}  // namespace
+
+template <class System>
+static int run_scan(const System& sys, float* chunk_resp, int* chunk_count, const float* power, float* lane_state,
+                    uint64_t lanes, uint64_t lane_len, uint64_t chunks_per_lane, unsigned cap, cudaStream_t s) {
+    const uint64_t total = lanes * chunks_per_lane;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((total + 63) / 64, cap));
+    scan_reduce_kernel<System><<<grid, 64, 0, s>>>(sys, chunk_resp, chunk_count, lanes, lane_len, chunks_per_lane);
+    B200_LAUNCH_CHECK();
+    scan_carry_kernel<System><<<static_cast<unsigned>((lanes + 31) / 32), 32, 0, s>>>(sys, chunk_resp, chunk_count, power,
+                                                                                      lane_state, lanes, chunks_per_lane);
+    B200_LAUNCH_CHECK();
+    scan_replay_kernel<System><<<grid, 64, 0, s>>>(sys, chunk_resp, lanes, lane_len, chunks_per_lane);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
 
 extern "C" {
 
@@ -164,24 +503,27 @@ int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wi
     *plan = nullptr;
     B200_REQUIRE(lanes >= 1, "b200_fm_plan_create: lanes must be positive");
     B200_REQUIRE(std::isfinite(sample_rate) && sample_rate > 0.0f && sample_rate <= 20e6f,
-                 "b200_fm_plan_create: sample rate must be finite, positive and <= 20 MHz");
+                 "[MODULE_FM] Sample rate must be finite, positive and must not exceed 20 MHz.");
     B200_REQUIRE(deemphasis_us == 0 || deemphasis_us == 50 || deemphasis_us == 75,
-                 "b200_fm_plan_create: de-emphasis must be 0 (none), 50 or 75 us");
-    B200_REQUIRE(!wide, "b200_fm_plan_create: wideband stereo mode is not implemented by this provider yet");
+                 "[MODULE_FM] De-emphasis must be 'none', '50us', or '75us'.");
+    B200_REQUIRE(!wide || sample_rate >= 200e3f,
+                 "[MODULE_FM] Wideband mode requires a sample rate of at least 200 kHz.");
     DeviceGuard guard(ctx);
     auto* pl = new b200_fm_plan();
     pl->ctx = ctx;
     pl->lanes = lanes;
-    // FmImpl::updateCoefficients (src/domains/dsp/fm/module_impl.cc:108-124), F32 arithmetic as written there.
-    const float kPi = 3.14159265358979323846f;   // JST_PI is a double literal; the products below round to F32
-    const float deviation = 100e3f;
+    pl->wide = wide != 0;
+    // FmImpl::updateCoefficients (src/domains/dsp/fm/module_impl.cc:108-155); F32/F64 mix as written there
+    // (JST_PI is a double literal, so `2.0f * JST_PI * x` is evaluated in F64 and rounded on assignment).
+    const double kPi = 3.14159265358979323846;
+    const float deviation = pl->wide ? 75e3f : 100e3f;
     const float kf = deviation / sample_rate;
-    pl->ref = static_cast<float>(1.0f / (2.0 * 3.14159265358979323846 * kf));
-    (void)kPi;
+    pl->ref = static_cast<float>(1.0f / (2.0f * kPi * kf));
     pl->deemphasis = deemphasis_us != 0;
+    const double sr = static_cast<double>(sample_rate);
     if (pl->deemphasis) {
         const double tau = deemphasis_us == 50 ? 50e-6 : 75e-6;
-        pl->alpha = static_cast<float>(1.0 - std::exp(-1.0 / (static_cast<double>(sample_rate) * tau)));
+        pl->alpha = static_cast<float>(1.0 - std::exp(-1.0 / (sr * tau)));
     } else {
         pl->alpha = 1.0f;
     }
@@ -193,6 +535,74 @@ int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wi
     pl->state = static_cast<FmState*>(st);
     pl->chunk_coeff = nullptr;
     pl->chunk_capacity = 0;
+    pl->wide_state = nullptr;
+    pl->power = nullptr;
+    pl->scratch = nullptr;
+    pl->scratch_total = pl->scratch_lane_len = 0;
+    if (pl->wide) {
+        FmWideCoeffs& w = pl->wc;
+        w.pilot_phase_increment = static_cast<float>(2.0f * kPi * 19e3f / sample_rate);
+        w.pilot_alpha = static_cast<float>(1.0 - std::exp(-2.0 * kPi * 200.0 / sr));
+        w.deemphasis_alpha = pl->alpha;
+        w.deemphasis = pl->deemphasis ? 1 : 0;
+        const double pilotOmega = 2.0 * kPi * 19e3 / sr;
+        const double pilotCosine = std::cos(pilotOmega), pilotSine = std::sin(pilotOmega);
+        const double pilotNotchAlpha = pilotSine / (2.0 * 20.0);
+        const double pilotNotchA0 = 1.0 + pilotNotchAlpha;
+        w.notch.b0 = static_cast<float>(1.0 / pilotNotchA0);
+        w.notch.b1 = static_cast<float>(-2.0 * pilotCosine / pilotNotchA0);
+        w.notch.b2 = w.notch.b0;
+        w.notch.a1 = w.notch.b1;
+        w.notch.a2 = static_cast<float>((1.0 - pilotNotchAlpha) / pilotNotchA0);
+        const double q[3] = {0.51763809, 0.70710678, 1.93185165};
+        const double omega = 2.0 * kPi * 15e3 / sr;
+        const double cosine = std::cos(omega), sine = std::sin(omega);
+        for (int section = 0; section < 3; ++section) {
+            const double alpha = sine / (2.0 * q[section]);
+            const double a0 = 1.0 + alpha;
+            Biquad& c = w.lowpass[section];
+            c.b0 = static_cast<float>((1.0 - cosine) * 0.5 / a0);
+            c.b1 = static_cast<float>((1.0 - cosine) / a0);
+            c.b2 = c.b0;
+            c.a1 = static_cast<float>(-2.0 * cosine / a0);
+            c.a2 = static_cast<float>((1.0 - alpha) / a0);
+        }
+        // Chunk transition matrices A^256 (F64 -> F32).
+        float host_power[16 + 64 + 4];
+        const double pa = w.pilot_alpha;
+        transition_power<4>([pa](double* s) {
+            s[0] += pa * (0.0 - s[0]);
+            s[1] += pa * (0.0 - s[1]);
+            s[2] += pa * (s[0] - s[2]);
+            s[3] += pa * (s[1] - s[3]);
+        }, host_power);
+        transition_power<8>([&w](double* s) {
+            double x = 0.0;
+            biquad_h(w.notch, s[0], s[1], x);
+            biquad_h(w.lowpass[0], s[2], s[3], x);
+            biquad_h(w.lowpass[1], s[4], s[5], x);
+            biquad_h(w.lowpass[2], s[6], s[7], x);
+        }, host_power + 16);
+        const double da = w.deemphasis ? static_cast<double>(w.deemphasis_alpha) : 0.0;
+        transition_power<2>([da](double* s) {
+            s[0] += da * (0.0 - s[0]);
+            s[1] += da * (0.0 - s[1]);
+        }, host_power + 80);
+        void* dev = nullptr;
+        void* wst = nullptr;
+        const size_t state_floats = 1 + lanes * 4 + 2 * lanes * 8 + lanes * 2;
+        if (b200_malloc(ctx, sizeof(host_power), &dev) != B200_SUCCESS ||
+            b200_malloc(ctx, state_floats * sizeof(float), &wst) != B200_SUCCESS ||
+            cudaMemcpy(dev, host_power, sizeof(host_power), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(dev);
+            cudaFree(wst);
+            cudaFree(pl->state);
+            delete pl;
+            return fail("b200_fm_plan_create: device setup failed");
+        }
+        pl->power = static_cast<float*>(dev);
+        pl->wide_state = static_cast<float*>(wst);
+    }
     *plan = pl;
     return B200_SUCCESS;
 }
@@ -201,6 +611,10 @@ int b200_fm_reset(b200_fm_plan* plan, b200_stream stream) {
     B200_REQUIRE(plan, "b200_fm_reset: null plan");
     DeviceGuard guard(plan->ctx);
     B200_CUDA_CHECK(cudaMemsetAsync(plan->state, 0, plan->lanes * sizeof(FmState), as_stream(stream)));
+    if (plan->wide) {
+        const size_t state_floats = 1 + plan->lanes * 4 + 2 * plan->lanes * 8 + plan->lanes * 2;
+        B200_CUDA_CHECK(cudaMemsetAsync(plan->wide_state, 0, state_floats * sizeof(float), as_stream(stream)));
+    }
     return B200_SUCCESS;
 }
 
@@ -216,11 +630,61 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
     const cudaStream_t s = as_stream(stream);
     const uint64_t blocks = (total + 255) / 256;
     const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * 8;
+    const uint64_t lane_len = frames * frame_len;
+
+    if (plan->wide) {
+        const uint64_t chunks_per_lane = (lane_len + kWideChunk - 1) / kWideChunk;
+        const uint64_t vlanes = 2 * plan->lanes;
+        if (plan->scratch_total < total || plan->scratch_lane_len < lane_len) {
+            cudaFree(plan->scratch);
+            plan->scratch = nullptr;
+            const uint64_t floats = 2 * total + lane_len + vlanes * chunks_per_lane * 8 + vlanes * chunks_per_lane;
+            B200_CUDA_CHECK(cudaMalloc(&plan->scratch, floats * sizeof(float)));
+            plan->scratch_total = total;
+            plan->scratch_lane_len = lane_len;
+        }
+        float* const sum = plan->scratch;
+        float* const diff = sum + total;
+        float* const phase = diff + total;
+        float* const chunk_resp = phase + lane_len;
+        int* const chunk_count = reinterpret_cast<int*>(chunk_resp + vlanes * chunks_per_lane * 8);
+        float* const phase_state = plan->wide_state;
+        float* const pilot_state = phase_state + 1;
+        float* const audio_state = pilot_state + plan->lanes * 4;
+        float* const stereo_state = audio_state + vlanes * 8;
+        const LaneIndex at{plan->lanes, frame_len};
+
+        fm_discriminator_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(
+            reinterpret_cast<const float2*>(x), sum, plan->state, frames, plan->lanes, frame_len, plan->ref);
+        B200_LAUNCH_CHECK();
+        fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
+        B200_LAUNCH_CHECK();
+        const unsigned ucap = static_cast<unsigned>(cap);
+        PilotSystem pilot{sum, phase, diff, at, plan->wc.pilot_alpha};
+        if (run_scan(pilot, chunk_resp, chunk_count, plan->power, pilot_state, plan->lanes, lane_len, chunks_per_lane,
+                     ucap, s) != B200_SUCCESS) {
+            return B200_ERROR;
+        }
+        AudioSystem audio{sum, diff, at, plan->wc.notch, {plan->wc.lowpass[0], plan->wc.lowpass[1], plan->wc.lowpass[2]}};
+        if (run_scan(audio, chunk_resp, chunk_count, plan->power + 16, audio_state, vlanes, lane_len, chunks_per_lane,
+                     ucap, s) != B200_SUCCESS) {
+            return B200_ERROR;
+        }
+        StereoSystem stereo{sum, diff, out, at, plan->wc.deemphasis_alpha, plan->wc.deemphasis};
+        if (run_scan(stereo, chunk_resp, chunk_count, plan->power + 80, stereo_state, plan->lanes, lane_len,
+                     chunks_per_lane, ucap, s) != B200_SUCCESS) {
+            return B200_ERROR;
+        }
+        fm_state_update_kernel<<<static_cast<unsigned>((plan->lanes + 63) / 64), 64, 0, s>>>(
+            reinterpret_cast<const float2*>(x), plan->state, frames, plan->lanes, frame_len);
+        B200_LAUNCH_CHECK();
+        return B200_SUCCESS;
+    }
+
     fm_discriminator_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(
         reinterpret_cast<const float2*>(x), out, plan->state, frames, plan->lanes, frame_len, plan->ref);
     B200_LAUNCH_CHECK();
     if (plan->deemphasis) {
-        const uint64_t lane_len = frames * frame_len;
         const uint64_t chunks_per_lane = (lane_len + kFmChunk - 1) / kFmChunk;
         const uint64_t total_chunks = chunks_per_lane * plan->lanes;
         if (total_chunks > plan->chunk_capacity) {
@@ -254,6 +718,9 @@ int b200_fm_plan_destroy(b200_fm_plan* plan) {
     DeviceGuard guard(plan->ctx);
     cudaFree(plan->state);
     cudaFree(plan->chunk_coeff);
+    cudaFree(plan->wide_state);
+    cudaFree(plan->power);
+    cudaFree(plan->scratch);
     delete plan;
     return B200_SUCCESS;
 }

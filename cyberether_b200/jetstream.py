@@ -1194,8 +1194,8 @@ class FirFilter(Module):
 
 @register_module
 class Fm(Module):
-    """`fm` — src/domains/dsp/fm/module_impl.cc:8-155 (+ native_cpu.cc:43-175). Narrow mode (optionally with
-    50/75 us de-emphasis); the wideband stereo decoder is not implemented by this provider yet."""
+    """`fm` — src/domains/dsp/fm/module_impl.cc:8-155 (+ native_cpu.cc:43-175): narrow (mono) and wide (stereo
+    multiplex decoder) modes, optional 50/75 us de-emphasis, per-lane state carried across cycles."""
     TYPE = "fm"
     DEFAULTS = {"mode": "narrow", "deemphasis": "none", "sampleRate": 240e3}
 
@@ -1225,10 +1225,8 @@ class Fm(Module):
         axes = resolve_signal_axes(t)
         if axes is None:
             return _error("[MODULE_FM] Input must contain valid signal axis metadata.")
-        if c["mode"] == "wide":
-            if axes.channel is not None:
-                return _error("[MODULE_FM] Wideband mode does not support channelized input.")
-            return _error("[MODULE_FM_B200] Wideband (stereo) mode is not implemented by this provider yet.")
+        if c["mode"] == "wide" and axes.channel is not None:
+            return _error("[MODULE_FM] Wideband mode does not support channelized input.")
         if axes.sample != t.rank - 1 or (axes.batch not in (None, 0)):
             return _error("[MODULE_FM_B200] Supported layouts: sample axis innermost, batch axis outermost.")
         self._axes = axes
@@ -1246,8 +1244,11 @@ class Fm(Module):
         self._frame_len = t.shape[-1]
         self._frames = t.shape[0] if (self._axes.batch == 0 and t.rank >= 2) else 1
         self._lanes = t.size // (self._frame_len * self._frames)
-        self.output = Tensor.create(t.device, "F32", t.shape)
+        wide = self.config["mode"] == "wide"
+        self.output = Tensor.create(t.device, "F32", tuple(t.shape) + ((2,) if wide else ()))
         self.output.propagate_attributes(t)
+        if wide:      # trailing [left, right] axis becomes the channel axis (fm/module_impl.cc:96-101)
+            self.output.set_attribute("channelAxis", t.rank)
         self.output.set_attribute("frequency", 0.0)
         self.outputs["signal"] = TensorLink()
         self.outputs["signal"].produced(self.name, "signal", self.output)

@@ -183,8 +183,9 @@ int b200_fir_plan_destroy(b200_fir_plan* plan);
 
 /* fm — FmImplNativeCpu::computeSubmit, src/domains/dsp/fm/module_impl_native_cpu.cc:43-175, coefficients of
  * src/domains/dsp/fm/module_impl.cc:108-155. x: [frames, lanes, frame_len] CF32 (frames consecutive in time,
- * lanes independent), out: same shape F32. wide != 0 (stereo) is not implemented yet -> ERROR.
- * deemphasis_us: 0 (none), 50 or 75. Per-lane state (previous sample, de-emphasis) lives in the plan. */
+ * lanes independent). out: same shape F32 (narrow) or [frames, lanes, frame_len, 2] = left/right (wide != 0:
+ * pilot NCO + pilot recovery, notch + 3 low-pass biquads on the sum and difference paths, evaluated as blocked
+ * linear-recurrence scans). deemphasis_us: 0 (none), 50 or 75. Per-lane state lives in the plan. */
 int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wide, int deemphasis_us,
                         b200_fm_plan** plan);
 int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t frames, uint64_t frame_len,
