@@ -10,6 +10,7 @@ range) — same outputs, one kernel per module.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Optional
 
 from .jetstream import (Module, Result, SynchronousScheduler, Tensor, TensorLink, build_module, _error,
@@ -185,9 +186,16 @@ class Filter(Block):
         signal_size = tensor.shape[axes.sample]
         centers = list(cfg["center"])[:heads] + [0.0] * max(0, heads - len(cfg["center"]))
         r = filter_resample_plan(float(cfg["sampleRate"]), float(cfg["bandwidth"]), int(cfg["taps"]), signal_size)
+        # Resampling heads with a non-zero centre are shifted to baseband before decimation: the reference rounds
+        # the centre to a bin of its M-point spectrum, M = T + taps - 1 (block_impl.cc:104-160).
+        center_bins = None
         if r > 1 and any(float(c) != 0.0 for c in centers):
-            return _error("[BLOCK_FILTER_B200] Resampling heads with a non-zero center (fold offsets + "
-                          "phase_correction) are not implemented by this provider yet.")
+            m = signal_size + int(cfg["taps"]) - 1
+            per_bin = float(cfg["sampleRate"]) / float(m)
+            center_bins = []
+            for c in centers:
+                cb_ = float(c) / per_bin
+                center_bins.append(int(math.floor(abs(cb_) + 0.5)) * (1 if cb_ >= 0 else -1))   # std::round
         self.resample = r > 1
         result = self.module_create("cast_signal", "cast", {"outputType": "CF32"}, {"buffer": port})
         if result != Result.SUCCESS:
@@ -197,7 +205,7 @@ class Filter(Block):
                                      "center": tuple(float(c) for c in centers), "taps": int(cfg["taps"])}, {})
         if result != Result.SUCCESS:
             return result
-        result = self.module_create("fir", "fir_filter", {"decimation": r},
+        result = self.module_create("fir", "fir_filter", {"decimation": r, "centerBins": center_bins},
                                     {"signal": self.module_get_output("cast_signal", "buffer"),
                                      "coeffs": self.module_get_output("filter_taps", "coeffs")})
         if result != Result.SUCCESS:

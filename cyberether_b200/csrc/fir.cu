@@ -37,6 +37,11 @@ struct FirParams {
     uint32_t qt;            // outputs per tile = blockDim.x * OB
     uint32_t plane_pitch;   // odd
     uint64_t frame_out;     // outputs per frame (T / R)
+    // Frequency-translating heads (resampling with a non-zero centre): y is multiplied by
+    // rot[head][m] * corr[head][frame]  (fold offsets + phase_correction of the reference), else nullptr.
+    const float2* rot;      // [heads, frame_out]   exp(-j 2 pi c_h (m R) / M), F64-evaluated
+    const float2* corr;     // [heads, frames]      exp(j (phase_h + inc_h frame)), F64-evaluated per call
+    uint64_t frames;
 };
 
 template <int OB, bool REAL_TAPS>
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 out_s[o0 + i] = acc[i];
             }
             __syncthreads();
-            if (p.heads == 1) {
+            if (p.heads == 1 && p.rot == nullptr) {
                 for (uint32_t o = tid; o < p.qt; o += nthreads) {
                     if (q0 + o < p.n_out) {
                         stg_stream_f2(p.y + q0 + o, out_s[o]);      // [frames, 1, frame_out] is the stream itself
@@ -178,7 +183,11 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 uint64_t m = (q0 + tid) - frame * p.frame_out;
                 for (uint32_t o = tid; o < p.qt; o += nthreads) {
                     if (q0 + o < p.n_out) {
-                        stg_stream_f2(p.y + (frame * p.heads + head) * p.frame_out + m, out_s[o]);
+                        float2 v = out_s[o];
+                        if (p.rot != nullptr) {
+                            v = cmul_exact(cmul_exact(v, p.rot[head * p.frame_out + m]), p.corr[head * p.frames + frame]);
+                        }
+                        stg_stream_f2(p.y + (frame * p.heads + head) * p.frame_out + m, v);
                     }
                     m += nthreads;
                     while (m >= p.frame_out) {
@@ -188,6 +197,28 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 }
             }
         }
+    }
+}
+
+// phase_correction (src/domains/dsp/phase_correction/module_impl_native_cpu.cc:81-115): per head and frame the
+// phasor exp(j (phase_h + inc_h * frame)) in F64 -> F32; afterwards phase_h <- remainder(phase_h + inc_h * frames, 2 pi).
+__global__ void fir_frame_corr_kernel(float2* __restrict__ corr, double* __restrict__ phases,
+                                      const double* __restrict__ increments, const uint64_t heads,
+                                      const uint64_t frames) {
+    const uint64_t total = heads * frames;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t head = i / frames, frame = i % frames;
+        const double ph = __dadd_rn(phases[head], __dmul_rn(increments[head], static_cast<double>(frame)));
+        corr[i] = make_float2(static_cast<float>(cos(ph)), static_cast<float>(sin(ph)));
+    }
+}
+__global__ void fir_phase_advance_kernel(double* __restrict__ phases, const double* __restrict__ increments,
+                                         const uint64_t heads, const uint64_t frames) {
+    const uint64_t head = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (head < heads) {
+        phases[head] = remainder(__dadd_rn(phases[head], __dmul_rn(increments[head], static_cast<double>(frames))),
+                                 2.0 * 3.14159265358979323846);
     }
 }
 
@@ -215,6 +246,14 @@ struct b200_fir_plan {
     float* taps_dev;
     float2* hist[2];
     int cur;
+    // frequency-translating heads
+    bool translate = false;
+    uint64_t frame_len = 0;
+    float2* rot_dev = nullptr;        // [heads, frame_len / R]
+    double* phases_dev = nullptr;     // [heads]
+    double* increments_dev = nullptr; // [heads]
+    float2* corr_dev = nullptr;       // [heads, corr_frames]
+    uint64_t corr_frames = 0;
 };
 
 template <int OB>
@@ -374,11 +413,59 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
     return B200_SUCCESS;
 }
 
+int b200_fir_plan_set_translation(b200_fir_plan* plan, uint64_t frame_len, const int64_t* center_bins) {
+    B200_REQUIRE(plan && center_bins, "b200_fir_plan_set_translation: null argument");
+    B200_REQUIRE(frame_len > 0 && frame_len % plan->R == 0,
+                 "b200_fir_plan_set_translation: frame length must be a positive multiple of the decimation");
+    DeviceGuard guard(plan->ctx);
+    const uint64_t M = frame_len + plan->L - 1;            // the reference's convolutionSize
+    const uint64_t frame_out = frame_len / plan->R;
+    const double kTwoPi = 2.0 * 3.14159265358979323846;
+    std::vector<float2> rot(static_cast<size_t>(plan->heads) * frame_out);
+    std::vector<double> inc(plan->heads);
+    for (uint32_t h = 0; h < plan->heads; ++h) {
+        // resamplerOffsets[head] = (-centerBin) mod M  (src/domains/dsp/filter/block_impl.cc:118-160)
+        const int64_t c = center_bins[h];
+        const uint64_t offset = static_cast<uint64_t>(((-c % static_cast<int64_t>(M)) + static_cast<int64_t>(M)) %
+                                                      static_cast<int64_t>(M));
+        // fold: bin j of the folded spectrum sums bins (j + g M/R - offset) mod M  ==  time-domain factor
+        // exp(+j 2 pi offset n / M) on the full-rate convolution at n = m R (offset == -c mod M).
+        for (uint64_t m = 0; m < frame_out; ++m) {
+            const uint64_t k = (offset * ((m * plan->R) % M)) % M;
+            const double a = kTwoPi * static_cast<double>(k) / static_cast<double>(M);
+            rot[static_cast<size_t>(h) * frame_out + m] = make_float2(static_cast<float>(std::cos(a)),
+                                                                     static_cast<float>(std::sin(a)));
+        }
+        // channelPhaseIncrements[head] = remainder(2 pi offset T / M, 2 pi)   (block_impl.cc:519-527), wrapped again
+        // by phase_correction (module_impl_native_cpu.cc:70-75)
+        inc[h] = std::remainder(std::remainder(kTwoPi * static_cast<double>(offset) * static_cast<double>(frame_len) /
+                                                   static_cast<double>(M), kTwoPi), kTwoPi);
+    }
+    cudaFree(plan->rot_dev);
+    cudaFree(plan->phases_dev);
+    cudaFree(plan->increments_dev);
+    plan->rot_dev = nullptr;
+    plan->phases_dev = nullptr;
+    plan->increments_dev = nullptr;
+    B200_CUDA_CHECK(cudaMalloc(&plan->rot_dev, rot.size() * sizeof(float2)));
+    B200_CUDA_CHECK(cudaMalloc(&plan->phases_dev, plan->heads * sizeof(double)));
+    B200_CUDA_CHECK(cudaMalloc(&plan->increments_dev, plan->heads * sizeof(double)));
+    B200_CUDA_CHECK(cudaMemcpy(plan->rot_dev, rot.data(), rot.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    B200_CUDA_CHECK(cudaMemcpy(plan->increments_dev, inc.data(), inc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    B200_CUDA_CHECK(cudaMemset(plan->phases_dev, 0, plan->heads * sizeof(double)));
+    plan->translate = true;
+    plan->frame_len = frame_len;
+    return B200_SUCCESS;
+}
+
 int b200_fir_reset(b200_fir_plan* plan, b200_stream stream) {
     B200_REQUIRE(plan, "b200_fir_reset: null plan");
     DeviceGuard guard(plan->ctx);
     const size_t hist_bytes = std::max<size_t>(1, plan->L - 1) * sizeof(float2);
     B200_CUDA_CHECK(cudaMemsetAsync(plan->hist[plan->cur], 0, hist_bytes, as_stream(stream)));
+    if (plan->translate) {
+        B200_CUDA_CHECK(cudaMemsetAsync(plan->phases_dev, 0, plan->heads * sizeof(double), as_stream(stream)));
+    }
     return B200_SUCCESS;
 }
 
@@ -408,6 +495,27 @@ int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_
     p.qt = plan->qt;
     p.plane_pitch = plan->plane_pitch;
     p.frame_out = frame_len / plan->R;
+    p.frames = frames;
+    const cudaStream_t s0 = as_stream(stream);
+    if (plan->translate) {
+        B200_REQUIRE(frame_len == plan->frame_len, "b200_fir_exec: frame length %llu differs from the translation plan (%llu)",
+                     static_cast<unsigned long long>(frame_len), static_cast<unsigned long long>(plan->frame_len));
+        if (plan->corr_frames < frames) {
+            cudaFree(plan->corr_dev);
+            plan->corr_dev = nullptr;
+            B200_CUDA_CHECK(cudaMalloc(&plan->corr_dev, plan->heads * frames * sizeof(float2)));
+            plan->corr_frames = frames;
+        }
+        const uint64_t n = plan->heads * frames;
+        fir_frame_corr_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 127) / 128, 1024)), 128, 0, s0>>>(
+            plan->corr_dev, plan->phases_dev, plan->increments_dev, plan->heads, frames);
+        B200_LAUNCH_CHECK();
+        fir_phase_advance_kernel<<<static_cast<unsigned>((plan->heads + 63) / 64), 64, 0, s0>>>(
+            plan->phases_dev, plan->increments_dev, plan->heads, frames);
+        B200_LAUNCH_CHECK();
+        p.rot = plan->rot_dev;
+        p.corr = plan->corr_dev;
+    }
     const uint64_t tiles = (p.n_out + p.qt - 1) / p.qt;
     const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(8, (220 * 1024) / (plan->smem + 1024)));
     const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * per_sm;
@@ -441,6 +549,10 @@ int b200_fir_plan_destroy(b200_fir_plan* plan) {
     cudaFree(plan->taps_dev);
     cudaFree(plan->hist[0]);
     cudaFree(plan->hist[1]);
+    cudaFree(plan->rot_dev);
+    cudaFree(plan->phases_dev);
+    cudaFree(plan->increments_dev);
+    cudaFree(plan->corr_dev);
     delete plan;
     return B200_SUCCESS;
 }

@@ -163,8 +163,6 @@ struct FmWideCoeffs {
 };
 
 constexpr int kWideChunk = 256;
-constexpr float kTwoPiF = 6.28318530717958647692f;   // (float)(2.0f * JST_PI): the reference compares/subtracts in double
-                                                     // of a float, see advance_phase
 
 // FmImpl::applyBiquad (src/domains/dsp/fm/module_impl.cc:157-164), transposed direct form II, no FMA.
 __device__ __forceinline__ float biquad_step(const float x, const Biquad& c, float& z1, float& z2) {

@@ -1107,7 +1107,7 @@ class FirFilter(Module):
     Inputs: `signal` CF32 [T] or [B, T] (batch = consecutive frames), `coeffs` CF32 [heads, taps] (settled).
     Output `buffer`: [B, heads, T / R] with channelAxis = old sample axis, sampleAxis = +1."""
     TYPE = "fir_filter"
-    DEFAULTS = {"decimation": 1}
+    DEFAULTS = {"decimation": 1, "centerBins": None}
 
     def __init__(self):
         super().__init__()
@@ -1170,9 +1170,14 @@ class FirFilter(Module):
         handle = ctypes.c_void_p()
         result = _call("b200_fir_plan_create", ctx.handle, host.ctypes.data_as(ctypes.c_void_p), self._taps,
                        self._heads, self._r, ctypes.byref(handle))
-        if result == Result.SUCCESS:
-            self._plan_handle = handle
-        return result
+        if result != Result.SUCCESS:
+            return result
+        self._plan_handle = handle
+        bins = self.config.get("centerBins")
+        if bins is not None and any(int(b) != 0 for b in bins):
+            arr = (ctypes.c_int64 * self._heads)(*[int(b) for b in bins])
+            return _call("b200_fir_plan_set_translation", self._plan_handle, self._frame_len, arr)
+        return Result.SUCCESS
 
     def compute_submit(self, stream):
         if self._plan_handle is None:

@@ -174,6 +174,11 @@ int b200_filter_taps_host(double sample_rate, double bandwidth, const double* ce
  * output tail in overlap_add, module_impl_native_cpu.cc:155-198); b200_fir_reset zeroes it. */
 int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t ntaps, uint64_t heads,
                          uint64_t decimation, b200_fir_plan** plan);
+/* Frequency-translating heads = the block's fold offsets + phase_correction module (block_impl.cc:118-160,
+ * 519-532; src/domains/dsp/fold/module_impl_native_cpu.cc:130-147; src/domains/dsp/phase_correction/
+ * module_impl_native_cpu.cc:81-115): head h is shifted down by center_bins[h] bins of the block's M-point spectrum
+ * (M = frame_len + ntaps - 1) before decimation; the per-frame phase is carried across calls in F64. */
+int b200_fir_plan_set_translation(b200_fir_plan* plan, uint64_t frame_len, const int64_t* center_bins);
 int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_t frames, uint64_t frame_len,
                   b200_stream stream);
 int b200_fir_reset(b200_fir_plan* plan, b200_stream stream);

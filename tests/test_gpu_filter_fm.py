@@ -211,3 +211,18 @@ def test_fm_wide_stereo_matches_reference(ref, shape, axes, deemphasis):
         assert np.array_equal(np.isnan(g), np.isnan(w))
         m = ~np.isnan(w)
         assert np.abs(g[m] - w[m]).max() <= 2e-5 * max(1.0, np.abs(w[m]).max())
+
+
+def test_filter_multi_head_channelizer_with_resampling(ref):
+    """Three heads, two with non-zero centres, decimate by 4: the reference shifts each head to baseband by
+    offsetting the spectral fold (fold channelOffsets) and keeps frames phase-continuous with phase_correction,
+    carried across cycles — the "multi-fm" flowgraph structure (examples/flowgraphs/multi-fm.yml)."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    config = {"sampleRate": 4e6, "bandwidth": 1e6, "taps": 33, "heads": 3, "center": [0.0, 1e6, -1.25e6]}
+    cycles = [gaussian_cf32((6, 1024), 90 + i) for i in range(3)]
+    want, info = _ref_filter(cycles, config)
+    got, attrs = _our_filter(cycles, config)
+    for c, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == w.shape == (6, 3, 256)
+        err = np.abs(g - w).max() / np.abs(w).max()
+        assert err <= 1e-5, (c, err)
