@@ -252,6 +252,59 @@ __global__ void copy_strided_kernel(const T* __restrict__ src, T* __restrict__ d
     }
 }
 
+// ---- real-input FFT helpers (R2C / FFTPACK packing around the C2C kernels) --------------------------------
+// pocketfft::r2c keeps bins 0..n/2; pocketfft::r2r_fftpack stores [Re X0, Re X1, Im X1, ..., (Re X_{n/2})]
+// (src/domains/dsp/fft/module_impl_native_cpu.cc:142-167).
+__global__ void fft_r2c_pack_kernel(const float2* __restrict__ full, float2* __restrict__ out, const uint64_t batch,
+                                    const uint64_t n) {
+    const uint64_t half = n / 2 + 1, total = batch * half;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t row = i / half, k = i - row * half;
+        out[i] = full[row * n + k];
+    }
+}
+__global__ void fftpack_pack_kernel(const float2* __restrict__ full, float* __restrict__ out, const uint64_t batch,
+                                    const uint64_t n) {
+    const uint64_t total = batch * n;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t row = i / n, j = i - row * n;
+        const uint64_t k = (j + 1) / 2;                      // j = 0 -> X0.re; j = 2k-1 -> Xk.re; j = 2k -> Xk.im
+        const float2 v = full[row * n + k];
+        out[i] = (j == 0 || (j & 1)) ? v.x : v.y;
+    }
+}
+// halfcomplex -> full Hermitian spectrum X[k], X[n-k] = conj(X[k])
+__global__ void fftpack_unpack_kernel(const float* __restrict__ in, float2* __restrict__ full, const uint64_t batch,
+                                      const uint64_t n) {
+    const uint64_t total = batch * n;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t row = i / n, k = i - row * n;
+        const float* r = in + row * n;
+        const uint64_t kk = k <= n / 2 ? k : n - k;          // mirror index
+        float re, im;
+        if (kk == 0) {
+            re = r[0];
+            im = 0.0f;
+        } else if (2 * kk == n) {
+            re = r[n - 1];
+            im = 0.0f;
+        } else {
+            re = r[2 * kk - 1];
+            im = r[2 * kk];
+        }
+        full[i] = make_float2(re, k <= n / 2 ? im : -im);
+    }
+}
+__global__ void real_part_kernel(const float2* __restrict__ in, float* __restrict__ out, const uint64_t count) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < count;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        out[i] = in[i].x;
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
@@ -425,6 +478,26 @@ int b200_range_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, f
     DeviceGuard guard(ctx);
     range_f32_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(in, out, count, scale,
                                                                                             offset);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+int b200_fft_real_helper(b200_ctx* ctx, int op, const void* in, void* out, uint64_t batch, uint64_t n,
+                         b200_stream stream) {
+    B200_REQUIRE(ctx && in && out, "b200_fft_real_helper: null argument");
+    B200_REQUIRE(op >= 0 && op <= 3, "b200_fft_real_helper: op must be 0..3");
+    if (batch * n == 0) {
+        return B200_SUCCESS;
+    }
+    DeviceGuard guard(ctx);
+    const int grid = stream_grid(ctx, batch * n, 256, 8);
+    const cudaStream_t s = as_stream(stream);
+    switch (op) {
+        case 0: fft_r2c_pack_kernel<<<grid, 256, 0, s>>>(static_cast<const float2*>(in), static_cast<float2*>(out), batch, n); break;
+        case 1: fftpack_pack_kernel<<<grid, 256, 0, s>>>(static_cast<const float2*>(in), static_cast<float*>(out), batch, n); break;
+        case 2: fftpack_unpack_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(in), static_cast<float2*>(out), batch, n); break;
+        default: real_part_kernel<<<grid, 256, 0, s>>>(static_cast<const float2*>(in), static_cast<float*>(out), batch * n); break;
+    }
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

@@ -718,9 +718,13 @@ class MultiplyConstant(Module):
 
 @register_module
 class Fft(Module):
-    """`fft` — src/domains/dsp/fft/module_impl.cc:8-96; unnormalised C2C along the sample axis. Any sample axis and
-    strided inputs are accepted (Taint::DISCONTIGUOUS): they are gathered into the contiguous [batch, n] layout of
-    the kernels and scattered back. Real-input transforms (R2C / FFTPACK) are not implemented yet."""
+    """`fft` — src/domains/dsp/fft/module_impl.cc:8-96: unnormalised DFT along the sample axis.
+      CF32 -> CF32                                  pocketfft::c2c
+      F32  -> CF32 [.., n/2+1] (forward, complexOutput)   pocketfft::r2c
+      F32  -> F32 FFTPACK half-complex (either direction)   pocketfft::r2r_fftpack
+    Any sample axis and strided inputs are accepted (Taint::DISCONTIGUOUS): they are gathered into the contiguous
+    [batch, n] layout of the kernels and scattered back. Real-input transforms are composed from the C2C kernels
+    plus pack/unpack steps (b200_fft_real_helper)."""
     TYPE = "fft"
     DEFAULTS = {"forward": True, "complexOutput": False}
 
@@ -739,9 +743,6 @@ class Fft(Module):
         axes = resolve_signal_axes(t)
         if axes is None:
             return _error("[MODULE_FFT] Input must contain valid signal axis metadata.")
-        if t.dtype != "CF32":
-            return _error("[MODULE_FFT_B200] Real-input transforms (R2C / FFTPACK R2R) are not implemented by "
-                          "this provider yet; cast to CF32 first.")
         self._axis = axes.sample
         return Result.SUCCESS
 
@@ -752,16 +753,35 @@ class Fft(Module):
 
     def create_impl(self):
         self.input = self.inputs["signal"].tensor
-        self.output = Tensor.create(self.input.device, "CF32", self.input.shape)
-        self.output.propagate_attributes(self.input)
+        t = self.input
+        self._n = t.shape[self._axis]
+        self._batch = t.size // self._n
+        real_in = t.dtype == "F32"
+        self._kind = "c2c"
+        out_shape, out_dtype = list(t.shape), "CF32"
+        if real_in and self.config["forward"] and self.config["complexOutput"]:
+            self._kind = "r2c"
+            out_shape[self._axis] = self._n // 2 + 1
+        elif real_in:
+            self._kind = "fftpack"
+            out_dtype = "F32"
+        self.output = Tensor.create(t.device, out_dtype, out_shape)
+        self.output.propagate_attributes(t)
         self.outputs["signal"] = TensorLink()
         self.outputs["signal"].produced(self.name, "signal", self.output)
-        self._n = self.input.shape[self._axis]
-        self._batch = self.input.size // self._n
-        self._layout = _Layout(self.input.data, self._axis)
-        self._staging = None
-        if not self._layout.direct:
-            self._staging = torch.empty(self._layout.shape_p, dtype=torch.complex64, device=self.input.device)
+        self._layout = _Layout(t.data, self._axis)
+        self._out_layout = _Layout(self.output.data, self._axis)
+        dev = t.device
+        rows = (self._batch, self._n)
+        self._stage_in = None if (self._layout.direct and not real_in) else \
+            torch.empty(self._layout.shape_p, dtype=t.data.dtype, device=dev)
+        # complex work buffer [batch, n] for every path that is not the direct in->out C2C
+        self._work = None
+        if self._kind != "c2c" or not self._layout.direct:
+            self._work = torch.empty(rows, dtype=torch.complex64, device=dev)
+        self._stage_out = None
+        if not self._out_layout.direct or self._kind == "r2c":
+            self._stage_out = torch.empty(self._out_layout.shape_p, dtype=self.output.data.dtype, device=dev)
         return Result.SUCCESS
 
     def compute_initialize(self):
@@ -781,17 +801,53 @@ class Fft(Module):
             if result != Result.SUCCESS:
                 return result
         forward = 1 if self.config["forward"] else 0
-        if self._layout.direct:
+        if self._kind == "c2c" and self._layout.direct:
             return _call("b200_fft_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), forward, stream)
         ctx = Context.get(self.input.device)
-        result = self._layout.gather(ctx, self.input.data, self._staging, stream)
-        if result != Result.SUCCESS:
-            return result
-        ptr = ctypes.c_void_p(self._staging.data_ptr())
-        result = _call("b200_fft_exec", self._plan_handle, ptr, ptr, forward, stream)      # in place
-        if result != Result.SUCCESS:
-            return result
-        return self._layout.scatter(ctx, self._staging, self.output.data, self._layout.shape_p, stream)
+        vp = lambda tensor: ctypes.c_void_p(tensor.data_ptr())
+
+        def ok(result):
+            return result == Result.SUCCESS
+
+        # 1. dense [batch, n] input
+        src = self.input.data
+        if not self._layout.direct:
+            if not ok(self._layout.gather(ctx, self.input.data, self._stage_in, stream)):
+                return Result.ERROR
+            src = self._stage_in
+        # 2. to the complex work buffer
+        if self._kind == "c2c":
+            work_in = src
+        elif self._kind == "fftpack" and not forward:
+            if not ok(_call("b200_fft_real_helper", ctx.handle, 2, vp(src), vp(self._work), self._batch, self._n, stream)):
+                return Result.ERROR
+            work_in = self._work
+        else:
+            if not ok(_call("b200_cast_f32_cf32", ctx.handle, vp(src), vp(self._work), self._batch * self._n, stream)):
+                return Result.ERROR
+            work_in = self._work
+        # 3. transform (into the work buffer; a C2C with a dense output layout writes the output directly)
+        if self._kind == "c2c" and self._out_layout.direct:
+            return _call("b200_fft_exec", self._plan_handle, vp(work_in), self.output.ptr(), forward, stream)
+        if not ok(_call("b200_fft_exec", self._plan_handle, vp(work_in), vp(self._work), forward, stream)):
+            return Result.ERROR
+        # 4. to the dense output layout
+        dense_out = self.output.data if self._out_layout.direct else self._stage_out
+        if self._kind == "c2c":
+            dense_out = self._work
+        elif self._kind == "r2c":
+            dense_out = self._stage_out if not self._out_layout.direct else self.output.data
+            if not ok(_call("b200_fft_real_helper", ctx.handle, 0, vp(self._work), vp(dense_out), self._batch, self._n,
+                            stream)):
+                return Result.ERROR
+        else:
+            op = 1 if forward else 3
+            if not ok(_call("b200_fft_real_helper", ctx.handle, op, vp(self._work), vp(dense_out), self._batch, self._n,
+                            stream)):
+                return Result.ERROR
+        if self._out_layout.direct:
+            return Result.SUCCESS
+        return self._out_layout.scatter(ctx, dense_out, self.output.data, self._out_layout.shape_p, stream)
 
     def compute_deinitialize(self):
         if self._plan_handle is not None:

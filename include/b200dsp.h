@@ -98,6 +98,15 @@ int b200_fft_exec(b200_fft_plan* plan, const b200_cf32* in, b200_cf32* out, int 
                   b200_stream stream);
 int b200_fft_plan_destroy(b200_fft_plan* plan);
 
+/* Real-input transforms (pocketfft::r2c / r2r_fftpack, src/domains/dsp/fft/module_impl_native_cpu.cc:142-167) are
+ * composed from the C2C kernels plus these layout steps over [batch, n] rows:
+ *   op 0: full CF32 spectrum -> first n/2+1 bins (R2C output, `complexOutput`)
+ *   op 1: full CF32 spectrum -> FFTPACK half-complex F32 [Re X0, Re X1, Im X1, ..., (Re X_{n/2})]
+ *   op 2: FFTPACK half-complex F32 -> full Hermitian CF32 spectrum (input of the inverse)
+ *   op 3: CF32 -> real part F32 */
+int b200_fft_real_helper(b200_ctx* ctx, int op, const void* in, void* out, uint64_t batch, uint64_t n,
+                         b200_stream stream);
+
 /* amplitude — src/domains/dsp/amplitude/module_impl_native_cpu.cc:73-99 with Backend::ApproxLog10
  * (include/jetstream/backend/devices/cpu/helpers.hh:61-74): out = |x|==0 ? -inf :
  * 20*ApproxLog10(|x|) + coeff, coeff = 20*log10f(1/N) (src/domains/dsp/amplitude/module_impl.cc:49-51).

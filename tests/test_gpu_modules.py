@@ -223,3 +223,31 @@ def test_amplitude_and_range_non_contiguous_bit_exact(ref):
     got = _run_view("range", fbase, lambda t: t[:, ::4], {}, {"min": -2.0, "max": 2.0})
     want = ref.range_(np.ascontiguousarray(fbase[:, ::4]), -2.0, 2.0)
     assert np.abs(got - want).max() <= 2.5e-7
+
+
+# ---- real-input transforms ("FFT - Complex Real Signal F32", "FFT - FFTPACK Real ...", fft/module_tests.cc:149-440) ----
+
+@pytest.mark.parametrize("shape,axes", [((256,), (0, -1, -1)), ((6, 1024), (1, 0, -1)), ((64, 5), (0, 1, -1))])
+def test_fft_r2c_complex_output(ref, shape, axes):
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal(shape).astype(np.float32)
+    want = ref.run_block("fft", {"signal": x}, {"forward": True, "complexOutput": True}, "signal", axes={"signal": axes})
+    names = dict(zip(("sampleAxis", "batchAxis", "channelAxis"), [a if a >= 0 else None for a in axes]))
+    got = _run_view("fft", x, lambda t: t, {k: v for k, v in names.items() if v is not None},
+                    {"forward": True, "complexOutput": True})
+    assert got.shape == want.shape and got.dtype == np.complex64
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n", [8, 64, 2048])
+def test_fft_fftpack_real_forward_inverse(ref, n):
+    rng = np.random.default_rng(32)
+    x = rng.standard_normal((4, n)).astype(np.float32)
+    fwd_want = ref.run_block("fft", {"signal": x}, {"forward": True}, "signal")
+    fwd = _run("fft", {"signal": x}, {"forward": True})
+    assert fwd.dtype == np.float32 and fwd.shape == (4, n)
+    assert np.abs(fwd - fwd_want).max() <= 2e-6 * np.abs(fwd_want).max()
+    inv_want = ref.run_block("fft", {"signal": fwd_want}, {"forward": False}, "signal")
+    inv = _run("fft", {"signal": fwd_want}, {"forward": False})
+    assert np.abs(inv - inv_want).max() <= 2e-6 * np.abs(inv_want).max()
+    assert np.abs(inv / n - x).max() <= 1e-5          # unnormalised round trip (reference tolerance 1e-2)
