@@ -5,6 +5,7 @@
 // Replaces pocketfft::c2c (src/domains/dsp/fft/module_impl_native_cpu.cc:129-140) / cuFFT
 // (src/domains/dsp/fft/module_impl_native_cuda.cc:321-333,433) and, for the chain, the module
 // sequence of src/domains/dsp/spectrum_engine/block_impl.cc:120-217.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(1024) fft_generic_kernel(const FftParams p, co
 
 constexpr uint64_t kMaxGenericN = 16384;
 
-static bool fft_size_supported(const uint64_t n) { return is_pow2(n) && n >= 2 && n <= kMaxGenericN; }
+static bool fft_size_supported(const uint64_t n) { return is_pow2(n) && n >= 2 && n <= kMaxGenericN; }   // fused chain kernels
 
 // CTAs per SM for the 4096 kernel (2: 3-deep TMA ring, <=128 regs; 3: 2-deep ring, <=80 regs).
 // Overridable for A/B measurements: B200_FFT4096_CTAS=2|3.
@@ -314,12 +315,117 @@ static int make_twiddle_table(b200_ctx* ctx, const uint64_t n, float2** out) {
 
 using namespace b200;
 
+enum FftPlanKind { FFT_DIRECT = 0, FFT_FOURSTEP = 1, FFT_BLUESTEIN = 2 };
+
 struct b200_fft_plan {
     b200_ctx* ctx;
     uint64_t n;
     uint64_t batch;
     float2* twiddle;
+    int kind = FFT_DIRECT;
+    // four-step (n = n1 n2, power of two above the single-CTA limit): transposes + two batched sub-transforms
+    uint64_t n1 = 0, n2 = 0;
+    b200_fft_plan* sub1 = nullptr;
+    b200_fft_plan* sub2 = nullptr;
+    float2* step_twiddle = nullptr;   // [n2][n1]: W_n^(n2 k1)
+    // Bluestein (any n): chirp-z through a power-of-two circular convolution of length m >= 2n - 1
+    uint64_t m = 0;
+    b200_fft_plan* subm = nullptr;
+    float2* chirp = nullptr;          // [n]  exp(-j pi k^2 / n)
+    float2* chirp_spec_fwd = nullptr; // [m]  FFT_m of the wrapped conj chirp (forward transform)
+    float2* chirp_spec_inv = nullptr; // [m]  same for the inverse transform (conjugated chirps)
+    float2* scratch_a = nullptr;
+    float2* scratch_b = nullptr;
 };
+
+namespace b200 {
+
+constexpr uint64_t kMaxDirectN = 8192;      // single-CTA register-radix kernel (fft_radix.cuh); 16384 via fft_generic_kernel
+
+// data[row][k1] *= tw[(row mod n2)][k1] (optionally conjugated): the four-step inter-stage twiddle.
+__global__ void fourstep_twiddle_kernel(float2* __restrict__ data, const float2* __restrict__ tw, const uint64_t total,
+                                        const uint64_t n1, const uint64_t n2, const int conj) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t k1 = i % n1, row = i / n1;
+        float2 w = tw[(row % n2) * n1 + k1];
+        if (conj) {
+            w.y = -w.y;
+        }
+        data[i] = cmul(data[i], w);
+    }
+}
+
+// [B][d1][d2] -> [B][d2][d1]
+__global__ void transpose_kernel(const float2* __restrict__ in, float2* __restrict__ out, const uint64_t batch,
+                                 const uint64_t d1, const uint64_t d2) {
+    __shared__ float2 tile[32][33];
+    const uint64_t tiles_x = (d2 + 31) / 32, tiles_y = (d1 + 31) / 32;
+    const uint64_t tiles = batch * tiles_x * tiles_y;
+    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint64_t b = t / (tiles_x * tiles_y), r = t % (tiles_x * tiles_y);
+        const uint64_t ty = r / tiles_x, tx = r % tiles_x;
+        const float2* src = in + b * d1 * d2;
+        float2* dst = out + b * d1 * d2;
+        __syncthreads();
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const uint64_t y = ty * 32 + j, x = tx * 32 + threadIdx.x;
+            if (y < d1 && x < d2) {
+                tile[j][threadIdx.x] = src[y * d2 + x];
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const uint64_t x = tx * 32 + j, y = ty * 32 + threadIdx.x;
+            if (x < d2 && y < d1) {
+                dst[x * d1 + y] = tile[threadIdx.x][j];
+            }
+        }
+    }
+}
+
+// Bluestein pre: u[row][j] = x[row][j] * chirp[j] (j < n), 0 (n <= j < m); post: X[row][k] = chirp[k] * v[row][k] / m
+__global__ void bluestein_pre_kernel(const float2* __restrict__ x, float2* __restrict__ u, const float2* __restrict__ chirp,
+                                     const uint64_t batch, const uint64_t n, const uint64_t m, const int conj) {
+    const uint64_t total = batch * m;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t row = i / m, j = i - row * m;
+        float2 v = make_float2(0.f, 0.f);
+        if (j < n) {
+            float2 c = chirp[j];
+            if (conj) {
+                c.y = -c.y;
+            }
+            v = cmul(x[row * n + j], c);
+        }
+        u[i] = v;
+    }
+}
+__global__ void bluestein_post_kernel(const float2* __restrict__ v, float2* __restrict__ out,
+                                      const float2* __restrict__ chirp, const uint64_t batch, const uint64_t n,
+                                      const uint64_t m, const float scale, const int conj) {
+    const uint64_t total = batch * n;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t row = i / n, k = i - row * n;
+        float2 c = chirp[k];
+        if (conj) {
+            c.y = -c.y;
+        }
+        const float2 r = cmul(v[row * m + k], c);
+        out[i] = make_float2(r.x * scale, r.y * scale);
+    }
+}
+__global__ void pointwise_rowbcast_mul_kernel(float2* __restrict__ data, const float2* __restrict__ spec,
+                                              const uint64_t total, const uint64_t m) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        data[i] = cmul(data[i], spec[i % m]);
+    }
+}
+
+}  // namespace b200
 
 struct b200_chain_plan {
     b200_ctx* ctx;
@@ -329,6 +435,9 @@ struct b200_chain_plan {
     float* win_re;    // non-null: window is purely real
     float2* win_c;    // non-null: general complex window
     const char* variant;
+    bool composite = false;           // lengths without a single-kernel path
+    b200_fft_plan* fft = nullptr;
+    float2* scratch = nullptr;
     // Host-buffer pipeline (b200_chain_exec_host): kHostSlots device staging slots, three streams.
     static constexpr int kHostSlots = 3;
     uint64_t host_chunk_rows = 0;
@@ -340,19 +449,181 @@ struct b200_chain_plan {
 
 extern "C" {
 
+static int fft_exec_impl(b200_fft_plan* plan, const float2* in, float2* out, int forward, cudaStream_t s);
+
+static int upload(b200_ctx* ctx, const std::vector<float2>& host, float2** dev) {
+    void* p = nullptr;
+    if (b200_malloc(ctx, host.size() * sizeof(float2), &p) != B200_SUCCESS) {
+        return B200_ERROR;
+    }
+    if (cudaMemcpy(p, host.data(), host.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(p);
+        return fail("device upload failed");
+    }
+    *dev = static_cast<float2*>(p);
+    return B200_SUCCESS;
+}
+
 int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan** plan) {
     B200_REQUIRE(ctx && plan, "b200_fft_plan_c2c: null argument");
     *plan = nullptr;
     B200_REQUIRE(n >= 1, "b200_fft_plan_c2c: transform length must be positive");
-    B200_REQUIRE(n == 1 || fft_size_supported(n),
-                 "b200_fft_plan_c2c: n=%llu unsupported (power of two up to %llu in this build)",
-                 static_cast<unsigned long long>(n), static_cast<unsigned long long>(kMaxGenericN));
+    B200_REQUIRE(n <= (1ull << 27), "b200_fft_plan_c2c: n=%llu exceeds the supported 2^27",
+                 static_cast<unsigned long long>(n));
     DeviceGuard guard(ctx);
-    float2* tw = nullptr;
-    if (n > 1 && make_twiddle_table(ctx, n, &tw) != B200_SUCCESS) {
+    auto* pl = new b200_fft_plan();
+    pl->ctx = ctx;
+    pl->n = n;
+    pl->batch = batch;
+    pl->twiddle = nullptr;
+    const double kPi = 3.14159265358979323846;
+    if (n == 1 || (is_pow2(n) && n <= kMaxDirectN)) {
+        pl->kind = FFT_DIRECT;
+        if (n > 1 && make_twiddle_table(ctx, n, &pl->twiddle) != B200_SUCCESS) {
+            delete pl;
+            return B200_ERROR;
+        }
+    } else if (is_pow2(n)) {
+        // four-step: n = n1 n2 with both factors <= kMaxDirectN
+        pl->kind = FFT_FOURSTEP;
+        const int k = ilog2(n);
+        pl->n1 = 1ull << (k / 2);
+        pl->n2 = n / pl->n1;
+        std::vector<float2> tw(n);
+        for (uint64_t a = 0; a < pl->n2; ++a) {
+            for (uint64_t c = 0; c < pl->n1; ++c) {
+                const double ang = -2.0 * kPi * static_cast<double>((a * c) % n) / static_cast<double>(n);
+                tw[a * pl->n1 + c] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+            }
+        }
+        int rc = upload(ctx, tw, &pl->step_twiddle);
+        rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, pl->n1, batch * pl->n2, &pl->sub1) : rc;
+        rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, pl->n2, batch * pl->n1, &pl->sub2) : rc;
+        void* a = nullptr;
+        void* b = nullptr;
+        if (rc == B200_SUCCESS && batch > 0) {
+            rc = b200_malloc(ctx, batch * n * sizeof(float2), &a);
+            rc = rc == B200_SUCCESS ? b200_malloc(ctx, batch * n * sizeof(float2), &b) : rc;
+        }
+        pl->scratch_a = static_cast<float2*>(a);
+        pl->scratch_b = static_cast<float2*>(b);
+        if (rc != B200_SUCCESS) {
+            b200_fft_plan_destroy(pl);
+            return B200_ERROR;
+        }
+    } else {
+        // Bluestein
+        pl->kind = FFT_BLUESTEIN;
+        uint64_t m = 1;
+        while (m < 2 * n - 1) {
+            m <<= 1;
+        }
+        pl->m = m;
+        std::vector<float2> chirp(n), wrapped(m, make_float2(0.f, 0.f)), wrapped_inv(m, make_float2(0.f, 0.f));
+        for (uint64_t j = 0; j < n; ++j) {
+            const uint64_t sq = (j * j) % (2 * n);                 // exact phase reduction
+            const double ang = -kPi * static_cast<double>(sq) / static_cast<double>(n);
+            chirp[j] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+            const float2 b = make_float2(chirp[j].x, -chirp[j].y);   // conj chirp
+            wrapped[j] = b;
+            wrapped_inv[j] = chirp[j];
+            if (j > 0) {
+                wrapped[m - j] = b;
+                wrapped_inv[m - j] = chirp[j];
+            }
+        }
+        int rc = upload(ctx, chirp, &pl->chirp);
+        rc = rc == B200_SUCCESS ? upload(ctx, wrapped, &pl->chirp_spec_fwd) : rc;
+        rc = rc == B200_SUCCESS ? upload(ctx, wrapped_inv, &pl->chirp_spec_inv) : rc;
+        b200_fft_plan* one = nullptr;
+        rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, m, 1, &one) : rc;
+        if (rc == B200_SUCCESS) {      // spectra of the two wrapped chirps (once)
+            rc = fft_exec_impl(one, pl->chirp_spec_fwd, pl->chirp_spec_fwd, 1, nullptr);
+            rc = rc == B200_SUCCESS ? fft_exec_impl(one, pl->chirp_spec_inv, pl->chirp_spec_inv, 1, nullptr) : rc;
+            cudaDeviceSynchronize();
+        }
+        b200_fft_plan_destroy(one);
+        rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, m, batch, &pl->subm) : rc;
+        void* a = nullptr;
+        if (rc == B200_SUCCESS && batch > 0) {
+            rc = b200_malloc(ctx, batch * m * sizeof(float2), &a);
+        }
+        pl->scratch_a = static_cast<float2*>(a);
+        if (rc != B200_SUCCESS) {
+            b200_fft_plan_destroy(pl);
+            return B200_ERROR;
+        }
+    }
+    *plan = pl;
+    return B200_SUCCESS;
+}
+
+static int fft_exec_impl(b200_fft_plan* plan, const float2* in, float2* out, int forward, cudaStream_t s) {
+    const b200_ctx* ctx = plan->ctx;
+    const unsigned cap = static_cast<unsigned>(ctx->sms * 8);
+    auto grid_for = [cap](uint64_t items) {
+        const uint64_t g = (items + 255) / 256;
+        return static_cast<unsigned>(g < cap ? (g ? g : 1) : cap);
+    };
+    if (plan->kind == FFT_DIRECT) {
+        if (plan->n == 1) {
+            if (in != out) {
+                B200_CUDA_CHECK(cudaMemcpyAsync(out, in, plan->batch * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+            }
+            return B200_SUCCESS;
+        }
+        FftParams p{};
+        p.in = in;
+        p.out = out;
+        p.rows = plan->batch;
+        p.n = static_cast<uint32_t>(plan->n);
+        p.inverse = forward ? 0 : 1;
+        p.twiddle = plan->twiddle;
+        return launch_fft<MODE_C2C, WIN_NONE>(plan->ctx, p, s);
+    }
+    const uint64_t B = plan->batch, n = plan->n;
+    if (plan->kind == FFT_FOURSTEP) {
+        const uint64_t n1 = plan->n1, n2 = plan->n2;
+        float2* a = plan->scratch_a;
+        float2* b = plan->scratch_b;
+        const dim3 tb(32, 8);
+        const unsigned tgrid = static_cast<unsigned>(std::min<uint64_t>(B * ((n1 + 31) / 32) * ((n2 + 31) / 32), cap * 4ull));
+        // x[b][n1][n2] -> a[b][n2][n1]
+        transpose_kernel<<<tgrid, tb, 0, s>>>(in, a, B, n1, n2);
+        B200_LAUNCH_CHECK();
+        if (fft_exec_impl(plan->sub1, a, a, forward, s) != B200_SUCCESS) {
+            return B200_ERROR;
+        }
+        fourstep_twiddle_kernel<<<grid_for(B * n), 256, 0, s>>>(a, plan->step_twiddle, B * n, n1, n2, forward ? 0 : 1);
+        B200_LAUNCH_CHECK();
+        // a[b][n2][k1] -> b[b][k1][n2]
+        transpose_kernel<<<tgrid, tb, 0, s>>>(a, b, B, n2, n1);
+        B200_LAUNCH_CHECK();
+        if (fft_exec_impl(plan->sub2, b, b, forward, s) != B200_SUCCESS) {
+            return B200_ERROR;
+        }
+        // b[b][k1][k2] -> out[b][k2][k1]   (k = k1 + n1 k2)
+        transpose_kernel<<<tgrid, tb, 0, s>>>(b, out, B, n1, n2);
+        B200_LAUNCH_CHECK();
+        return B200_SUCCESS;
+    }
+    // Bluestein
+    const uint64_t m = plan->m;
+    float2* u = plan->scratch_a;
+    const int conj = forward ? 0 : 1;
+    bluestein_pre_kernel<<<grid_for(B * m), 256, 0, s>>>(in, u, plan->chirp, B, n, m, conj);
+    B200_LAUNCH_CHECK();
+    if (fft_exec_impl(plan->subm, u, u, 1, s) != B200_SUCCESS) {
         return B200_ERROR;
     }
-    *plan = new b200_fft_plan{ctx, n, batch, tw};
+    pointwise_rowbcast_mul_kernel<<<grid_for(B * m), 256, 0, s>>>(u, forward ? plan->chirp_spec_fwd : plan->chirp_spec_inv,
+                                                                 B * m, m);
+    B200_LAUNCH_CHECK();
+    if (fft_exec_impl(plan->subm, u, u, 0, s) != B200_SUCCESS) {
+        return B200_ERROR;
+    }
+    bluestein_post_kernel<<<grid_for(B * n), 256, 0, s>>>(u, out, plan->chirp, B, n, m, 1.0f / static_cast<float>(m), conj);
+    B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
 
@@ -363,21 +634,8 @@ int b200_fft_exec(b200_fft_plan* plan, const b200_cf32* in, b200_cf32* out, int 
     }
     B200_REQUIRE(in && out, "b200_fft_exec: null buffer");
     DeviceGuard guard(plan->ctx);
-    if (plan->n == 1) {
-        if (in != out) {
-            B200_CUDA_CHECK(cudaMemcpyAsync(out, in, plan->batch * sizeof(float2), cudaMemcpyDeviceToDevice,
-                                            as_stream(stream)));
-        }
-        return B200_SUCCESS;
-    }
-    FftParams p{};
-    p.in = reinterpret_cast<const float2*>(in);
-    p.out = out;
-    p.rows = plan->batch;
-    p.n = static_cast<uint32_t>(plan->n);
-    p.inverse = forward ? 0 : 1;
-    p.twiddle = plan->twiddle;
-    return launch_fft<MODE_C2C, WIN_NONE>(plan->ctx, p, as_stream(stream));
+    return fft_exec_impl(plan, reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), forward,
+                         as_stream(stream));
 }
 
 int b200_fft_plan_destroy(b200_fft_plan* plan) {
@@ -385,7 +643,16 @@ int b200_fft_plan_destroy(b200_fft_plan* plan) {
         return B200_SUCCESS;
     }
     DeviceGuard guard(plan->ctx);
+    b200_fft_plan_destroy(plan->sub1);
+    b200_fft_plan_destroy(plan->sub2);
+    b200_fft_plan_destroy(plan->subm);
     cudaFree(plan->twiddle);
+    cudaFree(plan->step_twiddle);
+    cudaFree(plan->chirp);
+    cudaFree(plan->chirp_spec_fwd);
+    cudaFree(plan->chirp_spec_inv);
+    cudaFree(plan->scratch_a);
+    cudaFree(plan->scratch_b);
     delete plan;
     return B200_SUCCESS;
 }
@@ -394,9 +661,8 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
                            b200_chain_plan** plan) {
     B200_REQUIRE(ctx && plan, "b200_chain_plan_create: null argument");
     *plan = nullptr;
-    B200_REQUIRE(fft_size_supported(n),
-                 "b200_chain_plan_create: n=%llu unsupported (power of two, 2..%llu in this build)",
-                 static_cast<unsigned long long>(n), static_cast<unsigned long long>(kMaxGenericN));
+    B200_REQUIRE(n >= 1 && n <= (1ull << 27), "b200_chain_plan_create: n=%llu out of range",
+                 static_cast<unsigned long long>(n));
     DeviceGuard guard(ctx);
     auto* pl = new b200_chain_plan();
     pl->ctx = ctx;
@@ -406,6 +672,31 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
     pl->win_re = nullptr;
     pl->win_c = nullptr;
     pl->variant = "";
+    if (!fft_size_supported(n)) {
+        // Lengths the single-kernel paths do not cover (not a power of two, or > 16384): the reference's own module
+        // sequence on this provider — multiply -> fft (four-step / Bluestein plan) -> amplitude -> range — through a
+        // plan-owned CF32 scratch. Same results, 4+ passes over the data instead of one.
+        B200_REQUIRE(window_dev != nullptr, "b200_chain_plan_create: the composite path needs a window");
+        pl->composite = true;
+        void* w = nullptr;
+        void* sc = nullptr;
+        int rc = b200_malloc(ctx, n * sizeof(float2), &w);
+        rc = rc == B200_SUCCESS ? b200_malloc(ctx, std::max<uint64_t>(1, max_batch) * n * sizeof(float2), &sc) : rc;
+        rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, n, max_batch, &pl->fft) : rc;
+        if (rc == B200_SUCCESS &&
+            cudaMemcpy(w, window_dev, n * sizeof(float2), cudaMemcpyDeviceToDevice) != cudaSuccess) {
+            rc = fail("b200_chain_plan_create: window copy failed");
+        }
+        pl->win_c = static_cast<float2*>(w);
+        pl->scratch = static_cast<float2*>(sc);
+        if (rc != B200_SUCCESS) {
+            b200_chain_plan_destroy(pl);
+            return B200_ERROR;
+        }
+        pl->variant = "composite<multiply,fft(four-step|bluestein),amplitude,range>";
+        *plan = pl;
+        return B200_SUCCESS;
+    }
     if (make_twiddle_table(ctx, n, &pl->twiddle) != B200_SUCCESS) {
         delete pl;
         return B200_ERROR;
@@ -447,7 +738,9 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
             return fail("b200_chain_plan_create: window upload failed: %s", cudaGetErrorString(e));
         }
     }
-    pl->variant = n == kFft4096N ? "fft4096_kernel<tma,radix16x3>" : "fft_generic_kernel<stockham4>";
+    pl->variant = n == kFft4096N ? "fft4096_kernel<tma,radix16x3>"
+                                 : (n >= 16 && n <= 8192 ? "fft_radix_kernel<tma,radix16 stockham>"
+                                                         : "fft_generic_kernel<stockham4>");
     *plan = pl;
     return B200_SUCCESS;
 }
@@ -456,6 +749,27 @@ const char* b200_chain_plan_variant(const b200_chain_plan* plan) { return plan ?
 
 static int chain_launch(b200_chain_plan* plan, const float2* x, float* out, uint64_t batch, float amp_coeff,
                         int enable_range, float scale, float offset, cudaStream_t s) {
+    if (plan->composite) {
+        B200_REQUIRE(batch <= plan->max_batch, "b200_chain_exec: batch %llu exceeds the plan's max_batch %llu",
+                     static_cast<unsigned long long>(batch), static_cast<unsigned long long>(plan->max_batch));
+        const uint64_t shape[2] = {batch, plan->n}, sa[2] = {plan->n, 1}, sb[2] = {0, 1};
+        b200_fft_plan* fft = plan->fft;
+        const uint64_t saved = fft->batch;
+        int rc = b200_multiply_cf32(plan->ctx, reinterpret_cast<const b200_cf32*>(x),
+                                    reinterpret_cast<const b200_cf32*>(plan->win_c),
+                                    reinterpret_cast<b200_cf32*>(plan->scratch), 2, shape, sa, sb, s);
+        if (rc == B200_SUCCESS && batch != saved) {
+            rc = fail("b200_chain_exec: the composite path runs whole plans only (batch %llu, planned %llu)",
+                      static_cast<unsigned long long>(batch), static_cast<unsigned long long>(saved));
+        }
+        rc = rc == B200_SUCCESS ? fft_exec_impl(fft, plan->scratch, plan->scratch, 1, s) : rc;
+        rc = rc == B200_SUCCESS ? b200_amplitude_cf32(plan->ctx, reinterpret_cast<const b200_cf32*>(plan->scratch), out,
+                                                     batch * plan->n, amp_coeff, s) : rc;
+        if (rc == B200_SUCCESS && enable_range) {
+            rc = b200_range_f32(plan->ctx, out, out, batch * plan->n, scale, offset, s);
+        }
+        return rc;
+    }
     FftParams p{};
     p.in = x;
     p.out = out;
@@ -590,6 +904,8 @@ int b200_chain_plan_destroy(b200_chain_plan* plan) {
     cudaFree(plan->twiddle);
     cudaFree(plan->win_re);
     cudaFree(plan->win_c);
+    cudaFree(plan->scratch);
+    b200_fft_plan_destroy(plan->fft);
     for (int i = 0; i < b200_chain_plan::kHostSlots; ++i) {
         cudaFree(plan->stage_in[i]);
         cudaFree(plan->stage_out[i]);

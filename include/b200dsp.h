@@ -91,7 +91,9 @@ int b200_multiply_constant_f32(b200_ctx* ctx, const float* in, float* out, uint6
 
 /* fft — src/domains/dsp/fft/module_impl_native_cpu.cc:129-140 (pocketfft::c2c, scale 1.0 in both
  * directions, forward sign exp(-j2*pi*kn/N)). Batched 1-D C2C over the last (contiguous) axis:
- * in/out [batch, n] CF32; in == out allowed. Replaces cufftMakePlanMany64 + cufftExecC2C of
+ * in/out [batch, n] CF32; in == out allowed. Any n >= 1: powers of two up to 8192 run the single-pass TMA-staged
+ * register-radix kernel; larger powers of two a four-step plan (transposes + two batched sub-transforms); every
+ * other length Bluestein's chirp-z through a power-of-two convolution (pocketfft does the same for large primes). Replaces cufftMakePlanMany64 + cufftExecC2C of
  * src/domains/dsp/fft/module_impl_native_cuda.cc:321-333,433. */
 int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan** plan);
 int b200_fft_exec(b200_fft_plan* plan, const b200_cf32* in, b200_cf32* out, int forward,
@@ -147,8 +149,9 @@ int b200_cast_f32_cf32(b200_ctx* ctx, const float* in, b200_cf32* out, uint64_t 
  * produce (already sign-flipped); it is captured at plan creation (static, settled output).
  *   x   : [batch, n] CF32 contiguous, 16-byte aligned       out : [batch, n] F32
  *   amp_coeff = 20*log10f(1/n); enable_range != 0 applies range(scale, offset).
- * n must be a power of two, 2 <= n <= 16384 in this build (n == 4096 runs the TMA-staged single-pass
- * kernel, other sizes the shared-memory Stockham kernel with the same fused prologue/epilogue). */
+ * Powers of two 2 <= n <= 16384 run ONE fused kernel (n == 4096: fft4096_kernel; 16..8192: fft_radix_kernel;
+ * 2..8, 16384: fft_generic_kernel). Any other length runs the module sequence multiply -> fft -> amplitude ->
+ * range through a plan-owned scratch (exec must then use batch == max_batch). */
 int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const b200_cf32* window_dev,
                            b200_chain_plan** plan);
 int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch,

@@ -251,3 +251,44 @@ def test_fft_fftpack_real_forward_inverse(ref, n):
     inv = _run("fft", {"signal": fwd_want}, {"forward": False})
     assert np.abs(inv - inv_want).max() <= 2e-6 * np.abs(inv_want).max()
     assert np.abs(inv / n - x).max() <= 1e-5          # unnormalised round trip (reference tolerance 1e-2)
+
+
+@pytest.mark.parametrize("n", [16384, 32768, 65536])
+def test_fft_large_power_of_two_four_step(ref, n):
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((3, n), n)
+    for forward in (True, False):
+        got = _run("fft", {"signal": x}, {"forward": forward})
+        want = ref.fft(x, forward=forward)
+        assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n", [3, 5, 7, 12, 100, 1000, 4095, 4099, 8320])
+def test_fft_arbitrary_length_bluestein(ref, n):
+    """Non-power-of-two lengths (8320 = 8192 + 128 is what the reference's filter block feeds its fft)."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((4, n), 7 * n)
+    for forward in (True, False):
+        got = _run("fft", {"signal": x}, {"forward": forward})
+        want = ref.fft(x, forward=forward)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()     # north-star tolerance
+
+
+def test_chain_non_power_of_two_length(ref):
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from parity import assert_db_close, true_spectrum
+    import cyberether_b200 as cb
+    from cyberether_b200.blocks import SpectrumEngine
+    from cyberether_b200.synthetic import spectral_rows
+    n = 1000
+    x = spectral_rows(3, 6, n=n)
+    want = ref.spectrum_engine(x, enable_scale=True)
+    block = SpectrumEngine(enableScale=True)
+    assert block.create("s", {"buffer": cb.Tensor.from_numpy(x, sampleAxis=1, batchAxis=0)}) == cb.Result.SUCCESS
+    assert block.compute() == cb.Result.SUCCESS, cb.last_error()
+    got = block.output("buffer").numpy()
+    block.destroy()
+    w = ref.window(n).copy()
+    w[1::2] *= -1
+    assert_db_close(got, want, true_spectrum(x, w), scale=2.0 / 120.0, floor=3e-7)
