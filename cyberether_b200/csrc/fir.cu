@@ -137,32 +137,46 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 }
                 const float2* xq = xp;      // xq[-(s+1)] is the element tap (m0 + s + 1) slides in
                 const float* hq = hp;
-                for (uint32_t m0 = 0; m0 < p.lp_pad; m0 += OB) {
+                // taps actually present in this plane: k = kp0 + m R < L  (the padded tail is skipped, not multiplied)
+                const uint32_t kp0 = plane == 0 ? 0 : p.R - plane;
+                const uint32_t lp_plane = kp0 < p.L ? (p.L - kp0 + p.R - 1) / p.R : 0;
+                const uint32_t full = lp_plane / OB * OB;
+                auto tap_step = [&](const int s) {
+                    // logical window element i lives in w[(i - s) mod OB]
+                    if constexpr (REAL_TAPS) {
+                        const float h = hq[s];
+                        const float2 hh = make_float2(h, h);
+#pragma unroll
+                        for (int i = 0; i < OB; ++i) {
+                            acc[i] = __ffma2_rn(w[(i - s + OB) % OB], hh, acc[i]);
+                        }
+                    } else {
+                        const float2 h = reinterpret_cast<const float2*>(hq)[s];
+                        const float2 hr = make_float2(h.x, h.x), hi = make_float2(-h.y, h.y);
+#pragma unroll
+                        for (int i = 0; i < OB; ++i) {
+                            const float2 v = w[(i - s + OB) % OB];
+                            acc[i] = __ffma2_rn(v, hr, acc[i]);
+                            acc[i] = __ffma2_rn(make_float2(v.y, v.x), hi, acc[i]);
+                        }
+                    }
+                    // slide: next tap (m+1) needs row offset one lower
+                    w[(OB - 1 - s) % OB] = xq[-s - 1];
+                };
+                for (uint32_t m0 = 0; m0 < full; m0 += OB) {
 #pragma unroll
                     for (int s = 0; s < OB; ++s) {
-                        // logical window element i lives in w[(i - s) mod OB]
-                        if constexpr (REAL_TAPS) {
-                            const float h = hq[s];
-                            const float2 hh = make_float2(h, h);
-#pragma unroll
-                            for (int i = 0; i < OB; ++i) {
-                                acc[i] = __ffma2_rn(w[(i - s + OB) % OB], hh, acc[i]);
-                            }
-                        } else {
-                            const float2 h = reinterpret_cast<const float2*>(hq)[s];
-                            const float2 hr = make_float2(h.x, h.x), hi = make_float2(-h.y, h.y);
-#pragma unroll
-                            for (int i = 0; i < OB; ++i) {
-                                const float2 v = w[(i - s + OB) % OB];
-                                acc[i] = __ffma2_rn(v, hr, acc[i]);
-                                acc[i] = __ffma2_rn(make_float2(v.y, v.x), hi, acc[i]);
-                            }
-                        }
-                        // slide: next tap (m+1) needs row offset one lower
-                        w[(OB - 1 - s) % OB] = xq[-s - 1];
+                        tap_step(s);
                     }
                     xq -= OB;
                     hq += OB * (REAL_TAPS ? 1 : 2);
+                }
+                const uint32_t rem = lp_plane - full;       // CTA-uniform
+#pragma unroll
+                for (int s = 0; s < OB - 1; ++s) {
+                    if (static_cast<uint32_t>(s) < rem) {
+                        tap_step(s);
+                    }
                 }
             }
             // ---- stage the tile's outputs, then store coalesced

@@ -30,36 +30,38 @@ __device__ __forceinline__ float discriminate(const float2 p, const float2 c, co
     return __fmul_rn(atan2f(im, re), ref);
 }
 
+// grid: (segments of the row, rows); row = frame * lanes + lane. No per-element index division.
 __global__ void fm_discriminator_kernel(const float2* __restrict__ x, float* __restrict__ out,
                                         const FmState* __restrict__ state, const uint64_t frames,
                                         const uint64_t lanes, const uint64_t frame_len, const float ref) {
-    const uint64_t total = frames * lanes * frame_len;
-    for (uint64_t e = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; e < total;
-         e += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-        const uint64_t s = e % frame_len;
-        const uint64_t row = e / frame_len;          // frame * lanes + lane
-        const uint64_t lane = row % lanes;
-        const uint64_t frame = row / lanes;
-        const float2 cur = x[e];
-        float2 prev;
-        bool has_prev = true;
-        if (s > 0) {
-            prev = x[e - 1];
-        } else if (frame > 0) {
-            prev = x[((frame - 1) * lanes + lane) * frame_len + frame_len - 1];
-        } else {
-            prev = state[lane].previous;
-            has_prev = state[lane].has_previous != 0;
+    const uint64_t rows = frames * lanes;
+    for (uint64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const uint64_t lane = row % lanes, frame = row / lanes;
+        const float2* const xr = x + row * frame_len;
+        float* const outr = out + row * frame_len;
+        for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < frame_len;
+             s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+            const float2 cur = ldg_stream_f2(xr + s);
+            float2 prev;
+            bool has_prev = true;
+            if (s > 0) {
+                prev = xr[s - 1];
+            } else if (frame > 0) {
+                prev = x[((frame - 1) * lanes + lane) * frame_len + frame_len - 1];
+            } else {
+                prev = state[lane].previous;
+                has_prev = state[lane].has_previous != 0;
+            }
+            float d;
+            if (!has_prev) {
+                d = 0.0f;
+            } else if (finite2(cur) && finite2(prev)) {
+                d = discriminate(prev, cur, ref);
+            } else {
+                d = __int_as_float(0x7fc00000);
+            }
+            outr[s] = d;
         }
-        float d;
-        if (!has_prev) {
-            d = 0.0f;
-        } else if (finite2(cur) && finite2(prev)) {
-            d = discriminate(prev, cur, ref);
-        } else {
-            d = __int_as_float(0x7fc00000);
-        }
-        out[e] = d;
     }
 }
 
@@ -78,30 +80,71 @@ __global__ void fm_deemph_reduce_kernel(const float* __restrict__ d, float2* __r
         const uint64_t n0 = (c % chunks_per_lane) * kFmChunk;
         float y = 0.0f, gain = 1.0f;
         const float keep = 1.0f - alpha;
-        for (uint64_t n = n0; n < n0 + kFmChunk && n < lane_len; ++n) {
-            const uint64_t frame = n / frame_len, s = n % frame_len;
-            const float v = d[(frame * lanes + lane) * frame_len + s];
-            if (isfinite(v)) {
-                y = __fadd_rn(y, __fmul_rn(alpha, __fsub_rn(v, y)));
-                gain *= keep;
+        for (uint64_t nb = n0; nb < n0 + kFmChunk && nb < lane_len; nb += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {      // independent loads first, then the sequential recurrence
+                const uint64_t n = nb + u;
+                v[u] = __int_as_float(0x7fc00000);
+                if (n < lane_len) {
+                    const uint64_t frame = n / frame_len, s = n - frame * frame_len;
+                    v[u] = d[(frame * lanes + lane) * frame_len + s];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                if (isfinite(v[u])) {
+                    y = __fadd_rn(y, __fmul_rn(alpha, __fsub_rn(v[u], y)));
+                    gain *= keep;
+                }
             }
         }
         chunk_coeff[c] = make_float2(gain, y);
     }
 }
 
-// Phase 2: carries. One thread per lane walks its chunks: carry[c+1] = gain_c * carry[c] + offset_c.
-__global__ void fm_deemph_carry_kernel(float2* __restrict__ chunk_coeff, const FmState* __restrict__ state,
-                                       const uint64_t lanes, const uint64_t chunks_per_lane) {
-    const uint64_t lane = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (lane >= lanes) {
-        return;
-    }
-    float carry = state[lane].deemphasis;
-    for (uint64_t c = 0; c < chunks_per_lane; ++c) {
-        const float2 k = chunk_coeff[lane * chunks_per_lane + c];
-        chunk_coeff[lane * chunks_per_lane + c].x = carry;       // carry-in of chunk c
-        carry = fmaf(k.x, carry, k.y);
+// Phase 2: carries, one CTA per lane. Chunk maps y -> gain*y + offset compose associatively, so the CTA's 256
+// threads each fold a contiguous segment of chunks, a shared-memory scan combines the 256 segment maps, and each
+// thread replays its segment from its exclusive prefix, leaving the carry-in of every chunk in chunk_coeff[c].x.
+__global__ void __launch_bounds__(256) fm_deemph_carry_kernel(float2* __restrict__ chunk_coeff,
+                                                             const FmState* __restrict__ state, const uint64_t lanes,
+                                                             const uint64_t chunks_per_lane) {
+    __shared__ float sg[256], so[256];
+    for (uint64_t lane = blockIdx.x; lane < lanes; lane += gridDim.x) {
+        float2* const cc = chunk_coeff + lane * chunks_per_lane;
+        const uint64_t seg = (chunks_per_lane + 255) / 256;
+        const uint64_t c0 = threadIdx.x * seg;
+        const uint64_t c1 = c0 + seg < chunks_per_lane ? c0 + seg : chunks_per_lane;
+        float g = 1.0f, o = 0.0f;
+        for (uint64_t c = c0; c < c1; ++c) {
+            const float2 k = cc[c];
+            o = fmaf(k.x, o, k.y);
+            g *= k.x;
+        }
+        __syncthreads();
+        sg[threadIdx.x] = g;
+        so[threadIdx.x] = o;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {       // inclusive scan of map composition (later o earlier)
+            float pg = 1.0f, po = 0.0f;
+            if (static_cast<int>(threadIdx.x) >= d) {
+                pg = sg[threadIdx.x - d];
+                po = so[threadIdx.x - d];
+            }
+            __syncthreads();
+            const float ng = sg[threadIdx.x] * pg;
+            const float no = fmaf(sg[threadIdx.x], po, so[threadIdx.x]);
+            sg[threadIdx.x] = ng;
+            so[threadIdx.x] = no;
+            __syncthreads();
+        }
+        const float y0 = state[lane].deemphasis;
+        float carry = threadIdx.x == 0 ? y0 : fmaf(sg[threadIdx.x - 1], y0, so[threadIdx.x - 1]);
+        for (uint64_t c = c0; c < c1; ++c) {
+            const float2 k = cc[c];
+            cc[c].x = carry;                       // carry-in of chunk c
+            carry = fmaf(k.x, carry, k.y);
+        }
     }
 }
 
@@ -118,13 +161,26 @@ __global__ void fm_deemph_apply_kernel(float* __restrict__ d, const float2* __re
         const uint64_t ci = c % chunks_per_lane;
         const uint64_t n0 = ci * kFmChunk;
         float y = chunk_coeff[c].x;
-        for (uint64_t n = n0; n < n0 + kFmChunk && n < lane_len; ++n) {
-            const uint64_t frame = n / frame_len, s = n % frame_len;
-            float* const slot = d + (frame * lanes + lane) * frame_len + s;
-            const float v = *slot;
-            if (isfinite(v)) {
-                y = __fadd_rn(y, __fmul_rn(alpha, __fsub_rn(v, y)));
-                *slot = y;
+        for (uint64_t nb = n0; nb < n0 + kFmChunk && nb < lane_len; nb += 16) {
+            float v[16];
+            float* slot[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const uint64_t n = nb + u;
+                v[u] = __int_as_float(0x7fc00000);
+                slot[u] = nullptr;
+                if (n < lane_len) {
+                    const uint64_t frame = n / frame_len, s = n - frame * frame_len;
+                    slot[u] = d + (frame * lanes + lane) * frame_len + s;
+                    v[u] = *slot[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                if (isfinite(v[u])) {
+                    y = __fadd_rn(y, __fmul_rn(alpha, __fsub_rn(v[u], y)));
+                    *slot[u] = y;
+                }
             }
         }
         if (ci == chunks_per_lane - 1) {
@@ -629,6 +685,10 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
     const uint64_t blocks = (total + 255) / 256;
     const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * 8;
     const uint64_t lane_len = frames * frame_len;
+    (void)blocks;
+    const unsigned seg = static_cast<unsigned>(std::min<uint64_t>((frame_len + 255) / 256, 64));
+    const unsigned rows_y = static_cast<unsigned>(std::min<uint64_t>(frames * plan->lanes, std::max<uint64_t>(1, cap / seg)));
+    const dim3 disc_grid(seg, rows_y);
 
     if (plan->wide) {
         const uint64_t chunks_per_lane = (lane_len + kWideChunk - 1) / kWideChunk;
@@ -652,7 +712,7 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
         float* const stereo_state = audio_state + vlanes * 8;
         const LaneIndex at{plan->lanes, frame_len};
 
-        fm_discriminator_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(
+        fm_discriminator_kernel<<<disc_grid, 256, 0, s>>>(
             reinterpret_cast<const float2*>(x), sum, plan->state, frames, plan->lanes, frame_len, plan->ref);
         B200_LAUNCH_CHECK();
         fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
@@ -679,7 +739,7 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
         return B200_SUCCESS;
     }
 
-    fm_discriminator_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(
+    fm_discriminator_kernel<<<disc_grid, 256, 0, s>>>(
         reinterpret_cast<const float2*>(x), out, plan->state, frames, plan->lanes, frame_len, plan->ref);
     B200_LAUNCH_CHECK();
     if (plan->deemphasis) {
@@ -696,7 +756,7 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
         fm_deemph_reduce_kernel<<<cgrid, 128, 0, s>>>(out, plan->chunk_coeff, frames, plan->lanes, frame_len,
                                                      chunks_per_lane, plan->alpha);
         B200_LAUNCH_CHECK();
-        fm_deemph_carry_kernel<<<static_cast<unsigned>((plan->lanes + 63) / 64), 64, 0, s>>>(
+        fm_deemph_carry_kernel<<<static_cast<unsigned>(std::min<uint64_t>(plan->lanes, cap)), 256, 0, s>>>(
             plan->chunk_coeff, plan->state, plan->lanes, chunks_per_lane);
         B200_LAUNCH_CHECK();
         fm_deemph_apply_kernel<<<cgrid, 128, 0, s>>>(out, plan->chunk_coeff, plan->state, frames, plan->lanes,
