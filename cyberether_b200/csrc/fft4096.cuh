@@ -283,4 +283,5 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
     }
 }
 
+
 }  // namespace b200
