@@ -15,6 +15,7 @@ c_u64 = ctypes.c_uint64
 c_vp = ctypes.c_void_p
 c_int = ctypes.c_int
 c_f32 = ctypes.c_float
+c_f64 = ctypes.c_double
 P = ctypes.POINTER
 
 # name -> (restype, argtypes); mirrors include/b200dsp.h one to one.
@@ -51,9 +52,13 @@ SIGNATURES = {
     "b200_amplitude_scaling_coeff": (c_int, [c_u64, P(c_f32)]),
     "b200_range_coefficients": (c_int, [c_f32, c_f32, P(c_f32), P(c_f32)]),
     "b200_cast_f32_cf32": (c_int, [c_vp, c_vp, c_vp, c_u64, c_vp]),
+    "b200_cast_int": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_vp]),
+    "b200_agc_scratch_bytes": (c_int, [c_u64, c_u64, c_u64, c_vp]),
+    "b200_agc": (c_int, [c_vp, c_vp, c_vp, c_int, c_u64, c_u64, c_u64, c_f64, c_f64, c_f64, c_f64, c_f64, c_vp, c_vp]),
     "b200_copy_strided": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, P(c_u64), P(c_u64), P(c_u64), c_vp]),
     "b200_chain_plan_create": (c_int, [c_vp, c_u64, c_u64, c_vp, P(c_vp)]),
     "b200_chain_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_vp]),
+    "b200_chain_exec_typed": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_vp]),
     "b200_chain_exec_host": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_u64]),
     "b200_chain_plan_destroy": (c_int, [c_vp]),
     "b200_chain_plan_variant": (ctypes.c_char_p, [c_vp]),

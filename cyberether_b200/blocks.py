@@ -105,9 +105,6 @@ class SpectrumEngine(Block):
         axes = resolve_signal_axes(tensor)
         if axes is None:
             return _error("[BLOCK_SPECTRUM_ENGINE] Input signal axis metadata is invalid.")
-        if self.config["enableAgc"]:
-            return _error("[BLOCK_SPECTRUM_ENGINE_B200] enableAgc is not implemented by this provider "
-                          "(out of scope, SURVEY.md §2.2).")
         axis = axes.sample
         size = tensor.shape[axis]
 
@@ -123,7 +120,9 @@ class SpectrumEngine(Block):
         if r != Result.SUCCESS:
             return r
 
-        if self.config["fused"] and axis == tensor.rank - 1:
+        # enableAgc puts an `agc` module (one RMS tile per spectrum) between fft and amplitude
+        # (block_impl.cc:186-200): that graph runs module by module; the fused kernel covers the default chain.
+        if self.config["fused"] and axis == tensor.rank - 1 and not self.config["enableAgc"]:
             r = self.module_create("spectral_chain", "spectral_chain",
                                    {"enableScale": bool(self.config["enableScale"]),
                                     "rangeMin": float(self.config["rangeMin"]),
@@ -146,7 +145,13 @@ class SpectrumEngine(Block):
         r = self.module_create("fft", "fft", {"forward": True}, {"signal": self.module_get_output("multiply", "product")})
         if r != Result.SUCCESS:
             return r
-        r = self.module_create("amplitude", "amplitude", None, {"signal": self.module_get_output("fft", "signal")})
+        spectrum = self.module_get_output("fft", "signal")
+        if self.config["enableAgc"]:
+            r = self.module_create("agc", "agc", {"tileSize": size}, {"signal": spectrum})
+            if r != Result.SUCCESS:
+                return r
+            spectrum = self.module_get_output("agc", "signal")
+        r = self.module_create("amplitude", "amplitude", None, {"signal": spectrum})
         if r != Result.SUCCESS:
             return r
         if self.config["enableScale"]:
@@ -215,6 +220,26 @@ class Filter(Block):
             import numpy as np
             self.outputs["buffer"].tensor.set_attribute("sampleRate", float(np.float32(float(cfg["sampleRate"]) / r)))
         return Result.SUCCESS
+
+
+class AgcBlock(Block):
+    """`agc` block — src/domains/dsp/agc/block_impl.cc: one `agc` module."""
+    TYPE = "agc"
+    DEFAULTS = {"tileSize": 1024, "reference": 1.0, "epsilon": 1e-12, "minGain": 0.01, "maxGain": 100.0,
+                "maxGainChange": 4.0}
+
+    def create_impl(self) -> Result:
+        port = self.inputs.get("signal")
+        if port is None or not port.resolved():
+            return Result.INCOMPLETE
+        # the block's parameters are F32 (include/jetstream/domains/dsp/agc/block.hh:9-14) widened into the module's
+        # F64 config (block_impl.cc:17-24): minGain is (double)0.01f, not 0.01
+        import numpy as np
+        config = {k: (int(v) if k == "tileSize" else float(np.float32(v))) for k, v in self.config.items()}
+        result = self.module_create("agc", "agc", config, {"signal": port})
+        if result != Result.SUCCESS:
+            return result
+        return self.module_expose_output("signal", "agc", "signal")
 
 
 class FmBlock(Block):

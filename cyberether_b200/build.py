@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["context.cu", "elementwise.cu", "fft.cu", "fir.cu", "fm.cu"]
+SOURCES = ["context.cu", "elementwise.cu", "fft.cu", "fir.cu", "fm.cu", "agc.cu"]
 OUT = os.path.join(HERE, "libb200dsp.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

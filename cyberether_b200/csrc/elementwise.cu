@@ -224,6 +224,34 @@ __global__ void cast_f32_cf32_kernel(const float* __restrict__ in, float2* __res
     }
 }
 
+// ---- cast integer -> F32 (complex integers are two scalars) ------------------------------------------------------
+// src/domains/core/cast/module_impl_native_cpu.cc:163-330: out = static_cast<F32>(in) / scaler. The scaler is a power
+// of two, so the IEEE division is exact; cvt.rn is the C++ int->float conversion. 16 bytes of input per thread.
+template <typename T>
+__global__ void cast_int_f32_kernel(const T* __restrict__ in, float* __restrict__ out, const uint64_t scalars,
+                                    const float scaler) {
+    constexpr int PER = 16 / sizeof(T);
+    const uint64_t vecs = (reinterpret_cast<uintptr_t>(in) & 15) == 0 ? scalars / PER : 0;
+    const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    const uint64_t step = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t v = tid; v < vecs; v += step) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in) + v);
+        T lane[PER];
+        memcpy(lane, &raw, 16);
+        float4* dst = reinterpret_cast<float4*>(out + v * PER);
+#pragma unroll
+        for (int q = 0; q < PER / 4; ++q) {
+            stg_stream_f4(dst + q, make_float4(__fdiv_rn(static_cast<float>(lane[4 * q + 0]), scaler),
+                                               __fdiv_rn(static_cast<float>(lane[4 * q + 1]), scaler),
+                                               __fdiv_rn(static_cast<float>(lane[4 * q + 2]), scaler),
+                                               __fdiv_rn(static_cast<float>(lane[4 * q + 3]), scaler)));
+        }
+    }
+    for (uint64_t i = vecs * PER + tid; i < scalars; i += step) {
+        out[i] = __fdiv_rn(static_cast<float>(in[i]), scaler);
+    }
+}
+
 // ---- strided copy (layout gather / scatter) ----------------------------------------------------------
 // The role of the reference's fft_layout kernel (src/domains/dsp/fft/module_impl_native_cuda.cc:31-141): bring a
 // strided / permuted view into the contiguous [batch, n] layout the fast kernels use, and scatter results back.
@@ -540,6 +568,50 @@ int b200_cast_f32_cf32(b200_ctx* ctx, const float* in, b200_cf32* out, uint64_t 
     DeviceGuard guard(ctx);
     cast_f32_cf32_kernel<<<stream_grid(ctx, count, 256, 8), 256, 0, as_stream(stream)>>>(
         in, reinterpret_cast<float2*>(out), count);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+int b200_cast_int(b200_ctx* ctx, const void* in, int in_dtype, void* out, uint64_t count, b200_stream stream) {
+    B200_REQUIRE(ctx && (count == 0 || (in && out)), "b200_cast_int: null argument");
+    B200_REQUIRE(in_dtype >= B200_DTYPE_I8 && in_dtype <= B200_DTYPE_CU32,
+                 "[MODULE_CAST_B200] Unsupported conversion from dtype code %d.", in_dtype);
+    if (count == 0) {
+        return B200_SUCCESS;
+    }
+    const bool is_complex = in_dtype >= B200_DTYPE_CI8;
+    const int base = is_complex ? in_dtype - (B200_DTYPE_CI8 - B200_DTYPE_I8) : in_dtype;
+    const uint64_t scalars = is_complex ? count * 2 : count;
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "b200_cast_int: output must be 16-byte aligned");
+    DeviceGuard guard(ctx);
+    float* dst = static_cast<float*>(out);
+    const cudaStream_t s = as_stream(stream);
+    switch (base) {
+        case B200_DTYPE_I8:
+            cast_int_f32_kernel<int8_t><<<stream_grid(ctx, scalars / 16 + 1, 256, 8), 256, 0, s>>>(
+                static_cast<const int8_t*>(in), dst, scalars, 128.0f);
+            break;
+        case B200_DTYPE_U8:
+            cast_int_f32_kernel<uint8_t><<<stream_grid(ctx, scalars / 16 + 1, 256, 8), 256, 0, s>>>(
+                static_cast<const uint8_t*>(in), dst, scalars, 128.0f);
+            break;
+        case B200_DTYPE_I16:
+            cast_int_f32_kernel<int16_t><<<stream_grid(ctx, scalars / 8 + 1, 256, 8), 256, 0, s>>>(
+                static_cast<const int16_t*>(in), dst, scalars, 32768.0f);
+            break;
+        case B200_DTYPE_U16:
+            cast_int_f32_kernel<uint16_t><<<stream_grid(ctx, scalars / 8 + 1, 256, 8), 256, 0, s>>>(
+                static_cast<const uint16_t*>(in), dst, scalars, 32768.0f);
+            break;
+        case B200_DTYPE_I32:
+            cast_int_f32_kernel<int32_t><<<stream_grid(ctx, scalars / 4 + 1, 256, 8), 256, 0, s>>>(
+                static_cast<const int32_t*>(in), dst, scalars, 2147483648.0f);
+            break;
+        default:
+            cast_int_f32_kernel<uint32_t><<<stream_grid(ctx, scalars / 4 + 1, 256, 8), 256, 0, s>>>(
+                static_cast<const uint32_t*>(in), dst, scalars, 2147483648.0f);
+            break;
+    }
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

@@ -175,6 +175,23 @@ static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_
     return B200_SUCCESS;
 }
 
+// Fused complex-integer ingest (cast -> window -> fft -> amplitude -> range in one kernel), real window only.
+template <int MODE, int ITYPE>
+static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE>;
+    constexpr int smem = fft4096_int_smem_bytes(ITYPE);
+    static bool configured[64] = {};
+    if (!configured[ctx->device & 63]) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[ctx->device & 63] = true;
+    }
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
+    const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
+    kernel<<<grid, kFft4096Threads, smem, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
 template <int MODE, int WIN>
 static int launch_4096(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
     if (fft4096_ctas() == 3) {
@@ -438,6 +455,8 @@ struct b200_chain_plan {
     bool composite = false;           // lengths without a single-kernel path
     b200_fft_plan* fft = nullptr;
     float2* scratch = nullptr;
+    float2* cast_scratch = nullptr;   // typed input without a fused path: cast -> CF32 here, then the CF32 chain
+    uint64_t cast_rows = 0;
     // Host-buffer pipeline (b200_chain_exec_host): kHostSlots device staging slots, three streams.
     static constexpr int kHostSlots = 3;
     uint64_t host_chunk_rows = 0;
@@ -747,6 +766,36 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
 
 const char* b200_chain_plan_variant(const b200_chain_plan* plan) { return plan ? plan->variant : ""; }
 
+static void chain_params(const b200_chain_plan* plan, const float2* x, float* out, uint64_t batch, float amp_coeff,
+                         int enable_range, float scale, float offset, FftParams* q) {
+    q->in = x;
+    q->out = out;
+    q->rows = batch;
+    q->n = static_cast<uint32_t>(plan->n);
+    q->twiddle = plan->twiddle;
+    q->win_re = plan->win_re;
+    q->win_c = plan->win_c;
+    // dB = 20 * (Y * log10(2)) + coeff
+    const double kDbPerLog2 = 20.0 * 0.3010299956639812;
+    q->amp_scale = static_cast<float>(kDbPerLog2);
+    q->amp_coeff = amp_coeff;
+    if (enable_range) {
+        // 0.5 + 0.5 tanh(z), z = 4 ((dB s + o) - 0.5)  ==  1 / (1 + 2^(-2 z log2(e)))
+        const double kLog2e = 1.4426950408889634;
+        const double a = -8.0 * kLog2e * static_cast<double>(scale);
+        const double b = -8.0 * kLog2e * (static_cast<double>(offset) - 0.5);
+        if (scale == 0.0f) {  // RangeImplNativeCpu::kernelF32: scale == 0 -> 0.5 everywhere
+            q->k1 = 0.0f;
+            q->k0 = 0.0f;
+            q->zero_value = 0.5f;
+        } else {
+            q->k1 = static_cast<float>(a * kDbPerLog2);
+            q->k0 = static_cast<float>(a * static_cast<double>(amp_coeff) + b);
+            q->zero_value = 0.0f;
+        }
+    }
+}
+
 static int chain_launch(b200_chain_plan* plan, const float2* x, float* out, uint64_t batch, float amp_coeff,
                         int enable_range, float scale, float offset, cudaStream_t s) {
     if (plan->composite) {
@@ -771,32 +820,7 @@ static int chain_launch(b200_chain_plan* plan, const float2* x, float* out, uint
         return rc;
     }
     FftParams p{};
-    p.in = x;
-    p.out = out;
-    p.rows = batch;
-    p.n = static_cast<uint32_t>(plan->n);
-    p.twiddle = plan->twiddle;
-    p.win_re = plan->win_re;
-    p.win_c = plan->win_c;
-    // dB = 20 * (Y * log10(2)) + coeff
-    const double kDbPerLog2 = 20.0 * 0.3010299956639812;
-    p.amp_scale = static_cast<float>(kDbPerLog2);
-    p.amp_coeff = amp_coeff;
-    if (enable_range) {
-        // 0.5 + 0.5 tanh(z), z = 4 ((dB s + o) - 0.5)  ==  1 / (1 + 2^(-2 z log2(e)))
-        const double kLog2e = 1.4426950408889634;
-        const double a = -8.0 * kLog2e * static_cast<double>(scale);
-        const double b = -8.0 * kLog2e * (static_cast<double>(offset) - 0.5);
-        if (scale == 0.0f) {  // RangeImplNativeCpu::kernelF32: scale == 0 -> 0.5 everywhere
-            p.k1 = 0.0f;
-            p.k0 = 0.0f;
-            p.zero_value = 0.5f;
-        } else {
-            p.k1 = static_cast<float>(a * kDbPerLog2);
-            p.k0 = static_cast<float>(a * static_cast<double>(amp_coeff) + b);
-            p.zero_value = 0.0f;
-        }
-    }
+    chain_params(plan, x, out, batch, amp_coeff, enable_range, scale, offset, &p);
     const int win = plan->win_re ? WIN_REAL : (plan->win_c ? WIN_COMPLEX : WIN_NONE);
 #define B200_CHAIN_DISPATCH(MODE)                                                   \
     switch (win) {                                                                  \
@@ -822,6 +846,59 @@ int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint6
     DeviceGuard guard(plan->ctx);
     return chain_launch(plan, reinterpret_cast<const float2*>(x), out, batch, amp_coeff, enable_range, scale, offset,
                         as_stream(stream));
+}
+
+int b200_chain_exec_typed(b200_chain_plan* plan, const void* x, int in_dtype, float* out, uint64_t batch,
+                          float amp_coeff, int enable_range, float scale, float offset, b200_stream stream) {
+    B200_REQUIRE(plan, "b200_chain_exec_typed: null plan");
+    if (in_dtype == B200_DTYPE_CF32) {
+        return b200_chain_exec(plan, static_cast<const b200_cf32*>(x), out, batch, amp_coeff, enable_range, scale,
+                               offset, stream);
+    }
+    B200_REQUIRE(in_dtype >= B200_DTYPE_CI8 && in_dtype <= B200_DTYPE_CU32,
+                 "b200_chain_exec_typed: input dtype code %d is not CF32 or a complex integer type", in_dtype);
+    if (batch == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(x && out, "b200_chain_exec_typed: null buffer");
+    DeviceGuard guard(plan->ctx);
+    const cudaStream_t s = as_stream(stream);
+    const bool fused = !plan->composite && plan->n == kFft4096N && plan->win_re != nullptr &&
+                       in_dtype <= B200_DTYPE_CU16 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                       !fft4096_use_generic();
+    if (!fused) {
+        // cast module, then the CF32 chain (one extra pass over the data)
+        if (plan->cast_rows < batch) {
+            cudaFree(plan->cast_scratch);
+            plan->cast_scratch = nullptr;
+            plan->cast_rows = 0;
+            void* sc = nullptr;
+            if (b200_malloc(plan->ctx, batch * plan->n * sizeof(float2), &sc) != B200_SUCCESS) {
+                return B200_ERROR;
+            }
+            plan->cast_scratch = static_cast<float2*>(sc);
+            plan->cast_rows = batch;
+        }
+        const int rc = b200_cast_int(plan->ctx, x, in_dtype, plan->cast_scratch, batch * plan->n, stream);
+        return rc != B200_SUCCESS ? rc
+                                  : chain_launch(plan, plan->cast_scratch, out, batch, amp_coeff, enable_range, scale,
+                                                 offset, s);
+    }
+    FftParams p{};
+    chain_params(plan, static_cast<const float2*>(x), out, batch, amp_coeff, enable_range, scale, offset, &p);
+#define B200_INT_DISPATCH(MODE)                                                                  \
+    switch (in_dtype) {                                                                          \
+        case B200_DTYPE_CI8: return launch_4096_int<MODE, IN_CI8>(plan->ctx, p, s);              \
+        case B200_DTYPE_CU8: return launch_4096_int<MODE, IN_CU8>(plan->ctx, p, s);              \
+        case B200_DTYPE_CI16: return launch_4096_int<MODE, IN_CI16>(plan->ctx, p, s);            \
+        default: return launch_4096_int<MODE, IN_CU16>(plan->ctx, p, s);                         \
+    }
+    if (enable_range) {
+        B200_INT_DISPATCH(MODE_AMP_RANGE)
+    } else {
+        B200_INT_DISPATCH(MODE_AMP)
+    }
+#undef B200_INT_DISPATCH
 }
 
 int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* out_host, uint64_t batch,
@@ -905,6 +982,7 @@ int b200_chain_plan_destroy(b200_chain_plan* plan) {
     cudaFree(plan->win_re);
     cudaFree(plan->win_c);
     cudaFree(plan->scratch);
+    cudaFree(plan->cast_scratch);
     b200_fft_plan_destroy(plan->fft);
     for (int i = 0; i < b200_chain_plan::kHostSlots; ++i) {
         cudaFree(plan->stage_in[i]);

@@ -38,6 +38,36 @@ __host__ __device__ constexpr int fft4096_smem_bytes(const int ctas) {
     return fft4096_stages(ctas) * kFft4096StageBytes + 64;
 }
 
+// Input sample formats of the fused chain. IN_CF32 is the module-level contract; the complex-integer formats fuse
+// the reference's `cast` module (src/domains/core/cast/module_impl_native_cpu.cc:270-330, scaler 128 / 32768) into the
+// pass-1 load, so an SDR's native samples are read from HBM once at 2 or 4 bytes instead of being expanded to CF32 first.
+enum : int { IN_CF32 = 0, IN_CI8 = 1, IN_CU8 = 2, IN_CI16 = 3, IN_CU16 = 4 };
+__host__ __device__ constexpr int fft4096_in_bytes(const int itype) {
+    return itype == IN_CF32 ? 8 : (itype <= IN_CU8 ? 2 : 4);
+}
+// Integer rows land in their own 3-deep ring (8 or 16 KiB per row) and the exchanges alternate between two buffers.
+constexpr int kFft4096IntLandStages = 3;
+__host__ __device__ constexpr int fft4096_int_smem_bytes(const int itype) {
+    return 2 * kFft4096StageBytes + kFft4096IntLandStages * kFft4096N * fft4096_in_bytes(itype) + 64;
+}
+template <int ITYPE>
+__device__ __forceinline__ float2 load_int_sample(const unsigned char* land, const uint32_t index) {
+    // (F32)v / 2^k: the power-of-two reciprocal is exact, so the product equals the reference's division bit for bit
+    if constexpr (ITYPE == IN_CI8) {
+        const char2 c = *reinterpret_cast<const char2*>(land + 2 * index);
+        return make_float2(static_cast<float>(c.x) * 0.0078125f, static_cast<float>(c.y) * 0.0078125f);
+    } else if constexpr (ITYPE == IN_CU8) {
+        const uchar2 c = *reinterpret_cast<const uchar2*>(land + 2 * index);
+        return make_float2(static_cast<float>(c.x) * 0.0078125f, static_cast<float>(c.y) * 0.0078125f);
+    } else if constexpr (ITYPE == IN_CI16) {
+        const short2 c = *reinterpret_cast<const short2*>(land + 4 * index);
+        return make_float2(static_cast<float>(c.x) * 3.0517578125e-05f, static_cast<float>(c.y) * 3.0517578125e-05f);
+    } else {
+        const ushort2 c = *reinterpret_cast<const ushort2*>(land + 4 * index);
+        return make_float2(static_cast<float>(c.x) * 3.0517578125e-05f, static_cast<float>(c.y) * 3.0517578125e-05f);
+    }
+}
+
 // ---- mbarrier / TMA (bulk async copy) PTX wrappers ------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -114,11 +144,15 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const TwiddleSet
     }
 }
 
-template <int MODE, int WIN, int CTAS>
+template <int MODE, int WIN, int CTAS, int ITYPE = IN_CF32>
 __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const FftParams p) {
-    constexpr int kFft4096Stages = fft4096_stages(CTAS);
+    constexpr bool kInt = ITYPE != IN_CF32;
+    constexpr int kFft4096Stages = kInt ? kFft4096IntLandStages : fft4096_stages(CTAS);   // TMA ring depth
+    constexpr int kLandBytes = kFft4096N * fft4096_in_bytes(ITYPE);                        // bytes of one input row
+    constexpr int kLandPitch = kInt ? kLandBytes : kFft4096StageBytes;
+    constexpr int kLandBase = kInt ? 2 * kFft4096StageBytes : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kFft4096Stages * kFft4096StageBytes);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kLandBase + kFft4096Stages * kLandPitch);
     uint64_t* const reads_done = full + kFft4096Stages;   // split barrier (B): 8 warp arrivals per row
 
     const uint32_t t = threadIdx.x;
@@ -137,15 +171,15 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
     }
     __syncthreads();
 
-    const float2* next_src = p.in + first * kFft4096N;   // thread 0: next row to request
-    const uint64_t src_step = stride * kFft4096N;
+    const unsigned char* next_src = reinterpret_cast<const unsigned char*>(p.in) + first * kLandBytes;   // thread 0
+    const uint64_t src_step = stride * kLandBytes;
     uint32_t issued = 0;
     if (t == 0) {
 #pragma unroll
         for (int s = 0; s < kFft4096Stages; ++s) {
             if (issued < my_rows) {
-                mbar_expect_tx(&full[s], kFft4096RowBytes);
-                tma_load_row(smem_raw + s * kFft4096StageBytes, next_src, kFft4096RowBytes, &full[s]);
+                mbar_expect_tx(&full[s], kLandBytes);
+                tma_load_row(smem_raw + kLandBase + s * kLandPitch, next_src, kLandBytes, &full[s]);
                 next_src += src_step;
                 ++issued;
             }
@@ -182,14 +216,23 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
     const uint64_t out_step = stride * kFft4096N * (MODE == MODE_C2C ? 8 : 4);
 
     for (uint32_t i = 0; i < my_rows; ++i) {
-        unsigned char* const buf = smem_raw + stage * kFft4096StageBytes;
+        // CF32: the row's landing buffer is also its exchange buffer. Integer input: a separate landing ring, the
+        // exchanges alternate between two buffers (row i+1 may write its exchange-1 while slow warps still read the
+        // exchange-2 of row i).
+        unsigned char* const buf = smem_raw + (kInt ? (i & 1u) : stage) * kFft4096StageBytes;
+        const unsigned char* const land = smem_raw + kLandBase + stage * kLandPitch;
         mbar_wait(&full[stage], parity);
 
         // ---- pass 1 -------------------------------------------------------------------------
         float2 v[16];
 #pragma unroll
         for (int a = 0; a < 16; ++a) {
-            float2 x = *reinterpret_cast<const float2*>(buf + off_p1 + 2048 * a);
+            float2 x;
+            if constexpr (kInt) {
+                x = load_int_sample<ITYPE>(land, t + 256 * a);
+            } else {
+                x = *reinterpret_cast<const float2*>(buf + off_p1 + 2048 * a);
+            }
             if constexpr (MODE == MODE_C2C) {
                 if (p.inverse) {
                     x = make_float2(x.y, x.x);  // IFFT(x) = swap(FFT(swap(x)))
@@ -212,12 +255,13 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
         __syncthreads();  // (A)
 
         // The previous row's buffer is free now (every thread finished its pass-3 reads before
-        // arriving at (A)): refill it with the row kStages-1 ahead.
-        if (t == 0 && i >= 1 && issued < my_rows) {
+        // arriving at (A)): refill it with the row kStages-1 ahead. Integer input: the landing slot of THIS row is
+        // free (every thread has converted its 16 samples), refill it with the row kStages ahead.
+        if (t == 0 && (kInt || i >= 1) && issued < my_rows) {
+            const uint32_t slot = kInt ? stage : refill_stage;
             fence_proxy_async();
-            mbar_expect_tx(&full[refill_stage], kFft4096RowBytes);
-            tma_load_row(smem_raw + refill_stage * kFft4096StageBytes, next_src, kFft4096RowBytes,
-                         &full[refill_stage]);
+            mbar_expect_tx(&full[slot], kLandBytes);
+            tma_load_row(smem_raw + kLandBase + slot * kLandPitch, next_src, kLandBytes, &full[slot]);
             next_src += src_step;
             ++issued;
         }

@@ -65,8 +65,15 @@ def _error(msg: str) -> Result:
     return Result.ERROR
 
 
-DTYPES = {"F32": torch.float32, "CF32": torch.complex64}
+DTYPES = {"F32": torch.float32, "CF32": torch.complex64,
+          "I8": torch.int8, "U8": torch.uint8, "I16": torch.int16, "U16": torch.uint16,
+          "I32": torch.int32, "U32": torch.uint32}
 DTYPE_NAMES = {v: k for k, v in DTYPES.items()}
+# Complex integers (CI8 ... CU32, include/jetstream/memory/types.hh) have no torch dtype: they are stored as the
+# real integer type with a trailing axis of 2 (re, im) that the Tensor handle hides from shape/rank/size.
+COMPLEX_INT_DTYPES = {"CI8": "I8", "CU8": "U8", "CI16": "I16", "CU16": "U16", "CI32": "I32", "CU32": "U32"}
+DTYPE_CODES = {"F32": 0, "CF32": 1, "I8": 2, "U8": 3, "I16": 4, "U16": 5, "I32": 6, "U32": 7,
+               "CI8": 8, "CU8": 9, "CI16": 10, "CU16": 11, "CI32": 12, "CU32": 13}      # include/b200dsp.h
 
 
 # ---------------------------------------------------------------------------------------------
@@ -107,28 +114,42 @@ def current_stream_ptr(device) -> ctypes.c_void_p:
 class Tensor:
     """Handle over shared storage with signal-axis attributes (sampleAxis/batchAxis/channelAxis)."""
 
-    def __init__(self, data: Optional[torch.Tensor] = None, attributes: Optional[dict] = None):
+    def __init__(self, data: Optional[torch.Tensor] = None, attributes: Optional[dict] = None,
+                 complex_int: bool = False):
         self.data = data
         self.attributes: Dict[str, object] = dict(attributes or {})
+        self.complex_int = bool(complex_int)
+        if self.complex_int and (data is None or data.dim() < 1 or data.shape[-1] != 2 or
+                                 "C" + DTYPE_NAMES.get(data.dtype, "?") not in COMPLEX_INT_DTYPES):
+            raise TypeError("complex-integer tensors are integer storage with a trailing axis of 2")
 
     # -- construction
     @staticmethod
     def create(device, dtype: str, shape: Sequence[int]) -> "Tensor":
+        if dtype in COMPLEX_INT_DTYPES:
+            return Tensor(torch.zeros(tuple(int(s) for s in shape) + (2,), dtype=DTYPES[COMPLEX_INT_DTYPES[dtype]],
+                                      device=device), complex_int=True)
         return Tensor(torch.zeros(tuple(int(s) for s in shape), dtype=DTYPES[dtype], device=device))
 
     @staticmethod
-    def from_numpy(array: np.ndarray, device="cuda", **axes) -> "Tensor":
+    def from_numpy(array: np.ndarray, device="cuda", dtype: Optional[str] = None, **axes) -> "Tensor":
+        """`dtype="CI8"` (… "CU32") marks an integer array whose last axis holds (re, im)."""
         t = torch.from_numpy(np.ascontiguousarray(array))
         if t.dtype not in DTYPE_NAMES:
             raise TypeError(f"unsupported dtype {array.dtype}")
-        out = Tensor(t.to(device))
+        complex_int = dtype in COMPLEX_INT_DTYPES
+        if dtype is not None and not complex_int and DTYPES.get(dtype) != t.dtype:
+            raise TypeError(f"array dtype {array.dtype} does not match '{dtype}'")
+        if complex_int and DTYPES[COMPLEX_INT_DTYPES[dtype]] != t.dtype:
+            raise TypeError(f"array dtype {array.dtype} does not match '{dtype}'")
+        out = Tensor(t.to(device), complex_int=complex_int)
         for key, value in axes.items():
             if value is not None:
                 out.set_attribute(key, int(value))
         return out
 
     def clone(self) -> "Tensor":  # new handle, same storage (Tensor::clone)
-        return Tensor(self.data, self.attributes)
+        return Tensor(self.data, self.attributes, self.complex_int)
 
     # -- introspection
     def valid(self) -> bool:
@@ -136,19 +157,20 @@ class Tensor:
 
     @property
     def shape(self) -> Tuple[int, ...]:
-        return tuple(self.data.shape)
+        return tuple(self.data.shape[:-1]) if self.complex_int else tuple(self.data.shape)
 
     @property
     def rank(self) -> int:
-        return self.data.dim()
+        return self.data.dim() - (1 if self.complex_int else 0)
 
     @property
     def dtype(self) -> str:
-        return DTYPE_NAMES[self.data.dtype]
+        name = DTYPE_NAMES[self.data.dtype]
+        return "C" + name if self.complex_int else name
 
     @property
     def size(self) -> int:
-        return self.data.numel()
+        return self.data.numel() // (2 if self.complex_int else 1)
 
     @property
     def device(self):
@@ -563,13 +585,16 @@ class Reshape(Module):
 @register_module
 class Cast(Module):
     """`cast` — bypass (alias) when the dtype already matches (src/domains/core/cast/module_impl.cc:23,98-101);
-    F32 -> CF32 otherwise."""
+    otherwise the conversions of the reference's native implementations
+    (module_impl_native_cpu.cc:60-75): integer -> F32 and F32 / complex integer -> CF32, scaled by
+    128 / 32768 / 2147483648 (module_impl.cc:50-72)."""
     TYPE = "cast"
     DEFAULTS = {"outputType": "CF32"}
+    REAL_INTS = ("I8", "U8", "I16", "U16", "I32", "U32")
 
     def validate(self):
-        if self.config["outputType"] not in ("CF32", "F32"):
-            return _error(f"[MODULE_CAST_B200] Unsupported output type '{self.config['outputType']}'.")
+        if self.config["outputType"] not in DTYPE_CODES:
+            return _error(f"[MODULE_CAST] Invalid output type '{self.config['outputType']}'.")
         return Result.SUCCESS
 
     def define(self):
@@ -579,13 +604,19 @@ class Cast(Module):
 
     def create_impl(self):
         self.input = self.inputs["buffer"].tensor
-        self.bypass = self.input.dtype == self.config["outputType"]
+        out_type = self.config["outputType"]
+        self.bypass = self.input.dtype == out_type
         if self.bypass:
             self.output = self.input.clone()
         else:
-            if not (self.input.dtype == "F32" and self.config["outputType"] == "CF32"):
-                return _error(f"[MODULE_CAST_B200] Unsupported cast {self.input.dtype} -> {self.config['outputType']}.")
-            self.output = Tensor.create(self.input.device, "CF32", self.input.shape)
+            in_type = self.input.dtype
+            supported = (out_type == "F32" and in_type in self.REAL_INTS) or \
+                        (out_type == "CF32" and (in_type == "F32" or in_type in COMPLEX_INT_DTYPES))
+            if not supported:
+                return _error(f"[MODULE_CAST_B200] Unsupported conversion '{in_type}' -> '{out_type}'.")
+            if self.input.rank == 0:
+                return _error("[MODULE_CAST] Cannot allocate a rank-zero cast output.")
+            self.output = Tensor.create(self.input.device, out_type, self.input.shape)
             self.output.propagate_attributes(self.input)
         self.outputs["buffer"] = TensorLink()
         self.outputs["buffer"].produced(self.name, "buffer", self.output)
@@ -598,7 +629,11 @@ class Cast(Module):
         if err:
             return err
         ctx = Context.get(self.input.device)
-        return _call("b200_cast_f32_cf32", ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size, stream)
+        if self.input.dtype == "F32":
+            return _call("b200_cast_f32_cf32", ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size,
+                         stream)
+        return _call("b200_cast_int", ctx.handle, self.input.ptr(), DTYPE_CODES[self.input.dtype],
+                     self.output.ptr(), self.input.size, stream)
 
 
 def merge_broadcast_signal_axes(a: Tensor, b: Tensor, rank: int) -> Optional[Dict[str, int]]:
@@ -859,6 +894,92 @@ class Fft(Module):
         return self.compute_deinitialize()
 
 
+@register_module
+class Agc(Module):
+    """`agc` — tiled RMS automatic gain control (include/jetstream/domains/dsp/agc/module.hh:8-19,
+    src/domains/dsp/agc/module_impl.cc:7-87, module_impl_native_cpu.cc:76-160). F32 or CF32, any sample axis
+    (other layouts are gathered to [lanes, samples] and scattered back). Stateless."""
+    TYPE = "agc"
+    DEFAULTS = {"tileSize": 1024, "reference": 1.0, "epsilon": 1e-12, "minGain": 0.01, "maxGain": 100.0,
+                "maxGainChange": 4.0}
+
+    def validate(self):
+        c = self.config
+        if int(c["tileSize"]) == 0:
+            return _error("[MODULE_AGC] Tile size must be greater than zero.")
+        if not math.isfinite(float(c["reference"])) or float(c["reference"]) <= 0.0:
+            return _error("[MODULE_AGC] Reference must be finite and positive.")
+        if not math.isfinite(float(c["epsilon"])) or float(c["epsilon"]) <= 0.0:
+            return _error("[MODULE_AGC] Epsilon must be finite and positive.")
+        if not math.isfinite(float(c["minGain"])) or float(c["minGain"]) <= 0.0:
+            return _error("[MODULE_AGC] Minimum gain must be finite and positive.")
+        if not math.isfinite(float(c["maxGain"])) or float(c["maxGain"]) < float(c["minGain"]):
+            return _error("[MODULE_AGC] Maximum gain must be finite and no less than minimum gain.")
+        if not math.isfinite(float(c["maxGainChange"])) or float(c["maxGainChange"]) < 1.0:
+            return _error("[MODULE_AGC] Maximum gain change must be finite and at least one.")
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        axes = resolve_signal_axes(t)
+        if axes is None:
+            return _error("[MODULE_AGC] Input must contain valid signal axis metadata.")
+        if t.dtype not in ("F32", "CF32"):
+            return _error(f"[MODULE_AGC_B200] Unsupported data type '{t.dtype}'.")
+        self._axis = axes.sample
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.STATELESS)
+        self.define_interface_input("signal")
+        return self.define_interface_output("signal")
+
+    def create_impl(self):
+        self.input = self.inputs["signal"].tensor
+        t = self.input
+        self._samples = t.shape[self._axis]
+        self._lanes = t.size // self._samples
+        self.output = Tensor.create(t.device, t.dtype, t.shape)
+        self.output.propagate_attributes(t)
+        self.outputs["signal"] = TensorLink()
+        self.outputs["signal"].produced(self.name, "signal", self.output)
+        self._layout = _Layout(t.data, self._axis)
+        self._out_layout = _Layout(self.output.data, self._axis)
+        self._stage_in = None if self._layout.direct else torch.empty(self._layout.shape_p, dtype=t.data.dtype,
+                                                                      device=t.device)
+        self._stage_out = None if self._out_layout.direct else torch.empty(self._out_layout.shape_p,
+                                                                           dtype=t.data.dtype, device=t.device)
+        self._scratch = None
+        return Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.output)
+        if err:
+            return err
+        c = self.config
+        ctx = Context.get(self.input.device)
+        tile = int(c["tileSize"])
+        need = ctypes.c_uint64()
+        result = _call("b200_agc_scratch_bytes", self._lanes, self._samples, tile, ctypes.byref(need))
+        if result != Result.SUCCESS:
+            return result
+        if self._scratch is None or self._scratch.numel() < need.value:
+            self._scratch = torch.empty(max(16, need.value), dtype=torch.uint8, device=self.input.device)
+        src = self.input.data
+        if not self._layout.direct:
+            if self._layout.gather(ctx, src, self._stage_in, stream) != Result.SUCCESS:
+                return Result.ERROR
+            src = self._stage_in
+        dst = self.output.data if self._out_layout.direct else self._stage_out
+        vp = lambda tensor: ctypes.c_void_p(tensor.data_ptr())
+        result = _call("b200_agc", ctx.handle, vp(src), vp(dst), 1 if self.input.dtype == "CF32" else 0, self._lanes,
+                       self._samples, tile, float(c["reference"]), float(c["epsilon"]), float(c["minGain"]),
+                       float(c["maxGain"]), float(c["maxGainChange"]), vp(self._scratch), stream)
+        if result != Result.SUCCESS or self._out_layout.direct:
+            return result
+        return self._out_layout.scatter(ctx, dst, self.output.data, self._out_layout.shape_p, stream)
+
+
 def amplitude_scaling_coeff(n: int) -> float:
     """scalingCoeff = 20 * log10f(1 / (F32)N) (src/domains/dsp/amplitude/module_impl.cc:49-51). Evaluated by
     the library with the host libm's log10f — the same function the reference calls — because other F32
@@ -995,7 +1116,9 @@ class SpectralChain(Module):
     """`spectral_chain` — B200-only fused module: multiply(window) -> fft -> amplitude -> [range] in one
     kernel (b200_chain_exec). It is what the `spectrum_engine` block creates on this provider instead of
     the 9-module chain of src/domains/dsp/spectrum_engine/block_impl.cc:120-217. Inputs: `buffer`
-    (CF32, sample axis innermost) and `window` (CF32 [n], the settled window->invert output)."""
+    (CF32, sample axis innermost) and `window` (CF32 [n], the settled window->invert output).
+    `buffer` may also be a complex-integer tensor (CI8 ... CU32): the `cast` module an SDR flowgraph puts in front of
+    spectrum_engine is then folded into the kernel's load (b200_chain_exec_typed)."""
     TYPE = "spectral_chain"
     DEFAULTS = {"enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0}
 
@@ -1008,8 +1131,8 @@ class SpectralChain(Module):
         if link is None or not link.resolved() or link.tensor.size == 0:
             return Result.SUCCESS
         t = link.tensor
-        if t.dtype != "CF32":
-            return _error("[MODULE_SPECTRAL_CHAIN_B200] Input must have data type CF32.")
+        if t.dtype != "CF32" and t.dtype not in COMPLEX_INT_DTYPES:
+            return _error("[MODULE_SPECTRAL_CHAIN_B200] Input must have data type CF32 or a complex integer type.")
         axes = resolve_signal_axes(t)
         if axes is None:
             return _error("[MODULE_SPECTRAL_CHAIN_B200] Input signal axis metadata is invalid.")
@@ -1064,9 +1187,10 @@ class SpectralChain(Module):
             result = self._create_plan()
             if result != Result.SUCCESS:
                 return result
-        return _call("b200_chain_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), self._batch,
-                     ctypes.c_float(self.amp_coeff), 1 if self.config["enableScale"] else 0,
-                     ctypes.c_float(self.scale), ctypes.c_float(self.offset), stream)
+        return _call("b200_chain_exec_typed", self._plan_handle, self.input.ptr(), DTYPE_CODES[self.input.dtype],
+                     self.output.ptr(), self._batch, ctypes.c_float(self.amp_coeff),
+                     1 if self.config["enableScale"] else 0, ctypes.c_float(self.scale), ctypes.c_float(self.offset),
+                     stream)
 
     def compute_deinitialize(self):
         if self._plan_handle is not None:
@@ -1512,9 +1636,9 @@ class TestContext:
         self.outputs: Dict[str, np.ndarray] = {}
         self.output_tensors: Dict[str, Tensor] = {}
 
-    def set_input(self, name: str, array: np.ndarray, **axes):
+    def set_input(self, name: str, array: np.ndarray, dtype: Optional[str] = None, **axes):
         target = self.device if (self.device != "cuda" or torch.cuda.is_available()) else "cpu"
-        self.inputs[name] = Tensor.from_numpy(array, device=target, **axes)
+        self.inputs[name] = Tensor.from_numpy(array, device=target, dtype=dtype, **axes)
 
     def set_config(self, **config):
         self.config = dict(config)

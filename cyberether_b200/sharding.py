@@ -35,6 +35,28 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def scatter_rows(whole, total_rows: int, row_shape, dtype, device, src: int = 0) -> torch.Tensor:
+    """Graph-boundary scatter: `src` holds the whole [total_rows, ...] batch (None elsewhere); every rank receives
+    its contiguous slab (`shard_bounds`). The counterpart of `gather_rows`; one collective per graph input, none
+    inside the data path."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return whole
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bounds = all_shards(total_rows, world)
+    largest = max(e - b for b, e in bounds)
+    recv = torch.empty((largest,) + tuple(row_shape), dtype=dtype, device=device)
+    parts = None
+    if rank == src:
+        parts = []
+        for b, e in bounds:
+            part = torch.zeros_like(recv)
+            part[: e - b] = whole[b:e]
+            parts.append(part)
+    dist.scatter(recv, parts, src=src)
+    begin, end = bounds[rank]
+    return recv[: end - begin]
+
+
 def gather_rows(local: torch.Tensor, total_rows: int, dst: int = 0):
     """Graph-boundary gather: concatenates every rank's [rows_r, n] slab on `dst` in rank order (None elsewhere).
     Slabs may differ by one row, so they are padded to the largest slab for the collective."""

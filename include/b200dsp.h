@@ -140,6 +140,35 @@ int b200_copy_strided(b200_ctx* ctx, const void* src, void* dst, int elem_bytes,
 /* cast F32 -> CF32 (imag 0) — src/domains/core/cast/module_impl_native_cpu.cc (CF32 input bypasses). */
 int b200_cast_f32_cf32(b200_ctx* ctx, const float* in, b200_cf32* out, uint64_t count, b200_stream stream);
 
+/* agc — tiled RMS automatic gain control, src/domains/dsp/agc/module_impl_native_cpu.cc:76-160 (AgcImpl config:
+ * include/jetstream/domains/dsp/agc/module.hh:8-19; validation module_impl.cc:7-45). in/out are [lanes, samples]
+ * contiguous (sample axis innermost), F32 (is_complex = 0) or CF32. All gain arithmetic in F64 as the reference.
+ * `scratch` is caller-owned device memory of b200_agc_scratch_bytes() bytes. Stateless across calls. */
+int b200_agc_scratch_bytes(uint64_t lanes, uint64_t samples, uint64_t tile_size, uint64_t* bytes);
+int b200_agc(b200_ctx* ctx, const void* in, void* out, int is_complex, uint64_t lanes, uint64_t samples,
+             uint64_t tile_size, double reference, double epsilon, double min_gain, double max_gain,
+             double max_gain_change, void* scratch, b200_stream stream);
+
+/* cast integer -> F32 / complex integer -> CF32 — src/domains/core/cast/module_impl_native_cpu.cc:163-330 with the
+ * scaler of module_impl.cc:50-72: out = (F32)in / 128 (I8, U8, CI8, CU8), / 32768 (16-bit), / 2147483648 (32-bit).
+ * Unsigned types are NOT re-centred (the reference does not either). `count` is in ELEMENTS of `in_dtype`
+ * (a complex element is two scalars); `out` holds count F32 or count CF32. */
+#define B200_DTYPE_F32   0
+#define B200_DTYPE_CF32  1
+#define B200_DTYPE_I8    2
+#define B200_DTYPE_U8    3
+#define B200_DTYPE_I16   4
+#define B200_DTYPE_U16   5
+#define B200_DTYPE_I32   6
+#define B200_DTYPE_U32   7
+#define B200_DTYPE_CI8   8
+#define B200_DTYPE_CU8   9
+#define B200_DTYPE_CI16  10
+#define B200_DTYPE_CU16  11
+#define B200_DTYPE_CI32  12
+#define B200_DTYPE_CU32  13
+int b200_cast_int(b200_ctx* ctx, const void* in, int in_dtype, void* out, uint64_t count, b200_stream stream);
+
 /* ---- fused spectral chain: the spectrum_engine block ------------------------------------ */
 
 /* Replaces the module sequence wired by SpectrumEngineImpl::create
@@ -156,6 +185,15 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
                            b200_chain_plan** plan);
 int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch,
                     float amp_coeff, int enable_range, float scale, float offset, b200_stream stream);
+/* The same chain reading complex-integer samples (in_dtype = B200_DTYPE_CI8 ... CU32; B200_DTYPE_CF32 forwards to
+ * b200_chain_exec): the `cast` module that precedes spectrum_engine in an SDR flowgraph
+ * (src/domains/core/cast/module_impl_native_cpu.cc:270-330) folded into the kernel's load. n = 4096 with a real
+ * window and CI8/CU8/CI16/CU16 input is ONE kernel (2 or 4 B/sample read instead of cast's 2+8 write/read);
+ * everything else runs b200_cast_int into a plan-owned scratch and then the CF32 chain. Results are bit-identical
+ * to cast -> b200_chain_exec. */
+int b200_chain_exec_typed(b200_chain_plan* plan, const void* x, int in_dtype, float* out, uint64_t batch,
+                          float amp_coeff, int enable_range, float scale, float offset, b200_stream stream);
+
 /* Same computation for HOST-resident tensors (what the reference's TestContext hands a CUDA module:
  * host memory mapped onto the device, src/testing.cc:136, src/memory/buffer_cuda.cc:188). x_host and
  * out_host should be pinned (b200_host_alloc) for full PCIe rate. The batch is cut into chunks of

@@ -19,10 +19,90 @@ from __future__ import annotations
 
 import ctypes
 
+import math
+
 import numpy as np
 
 F32 = np.float32
 JST_PI = 3.14159265358979323846
+
+
+CAST_SCALERS = {1: np.float32(128.0), 2: np.float32(32768.0), 4: np.float32(2147483648.0)}
+
+
+def cast(x: np.ndarray, complex_pairs: bool = False) -> np.ndarray:
+    """src/domains/core/cast/module_impl_native_cpu.cc:163-330 with the scaler of module_impl.cc:50-72:
+    integer -> F32 as static_cast<F32>(v) / scaler (128 / 32768 / 2^31 by integer width; unsigned types are not
+    re-centred); `complex_pairs`: the last axis holds (re, im) of a complex-integer tensor -> CF32.
+    F32 -> CF32 sets imag = 0."""
+    if x.dtype == np.float32:
+        return x.astype(np.complex64)
+    y = x.astype(np.float32) / CAST_SCALERS[x.dtype.itemsize]
+    if complex_pairs:
+        out = np.empty(x.shape[:-1], np.complex64)
+        out.real, out.imag = y[..., 0], y[..., 1]
+        return out
+    return y
+
+
+def agc(x: np.ndarray, tile_size: int = 1024, reference: float = 1.0, epsilon: float = 1e-12,
+        min_gain: float = 0.01, max_gain: float = 100.0, max_gain_change: float = 4.0, axis: int = -1) -> np.ndarray:
+    """src/domains/dsp/agc/module_impl_native_cpu.cc:76-160 (ApplyTiledRmsAgc) with the helpers of :16-74: per lane,
+    tile target gain = clamp(reference / sqrt(mean power + eps)); the gain inside tile t is interpolated from the gain
+    at its start to the rate-limited (LimitGainChange) target of tile t+1; products are limited to the finite F32 range.
+    F64 throughout, sequential power sums like the reference (math.fsum is NOT used: the reference adds in order)."""
+    xm = np.moveaxis(np.asarray(x), axis, -1)
+    lanes = xm.reshape(-1, xm.shape[-1])
+    out = np.empty_like(lanes)
+    n = lanes.shape[1]
+    tiles = 1 + (n - 1) // tile_size
+    fmax = float(np.finfo(np.float32).max)
+    cmax = float(np.nextafter(np.float32(fmax), np.float32(0)))
+    is_complex = np.iscomplexobj(lanes)
+
+    def clamp(v, lo, hi):
+        return lo if v < lo else (hi if hi < v else v)
+
+    for li in range(lanes.shape[0]):
+        lane = lanes[li]
+        power = (lane.real.astype(np.float64) ** 2 + lane.imag.astype(np.float64) ** 2) if is_complex \
+            else lane.astype(np.float64) ** 2
+
+        def target(t):
+            seg = power[t * tile_size:(t + 1) * tile_size]
+            total = 0.0
+            for v in seg:                       # sequential F64 sum, as the reference
+                total += float(v)
+            return clamp(reference / math.sqrt(total / len(seg) + epsilon), min_gain, max_gain)
+
+        start = target(0)
+        for t in range(tiles):
+            lo_i, hi_i = t * tile_size, min((t + 1) * tile_size, n)
+            length = hi_i - lo_i
+            if t + 1 < tiles:
+                lowest = max(min_gain, start / max_gain_change)
+                highest = max_gain if start > max_gain / max_gain_change else start * max_gain_change
+                end = clamp(target(t + 1), lowest, highest)
+            else:
+                end = start
+            step = (end - start) / float(length)
+            gains = start + step * np.arange(length, dtype=np.float64)
+            seg = lane[lo_i:hi_i]
+            if is_complex:
+                re, im = seg.real.astype(np.float64), seg.imag.astype(np.float64)
+                mag = np.hypot(re, im)
+                with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                    safe = np.where(mag > cmax / gains, np.nextafter(cmax / mag, 0.0), gains)
+                    o = np.clip(re * safe, -fmax, fmax).astype(np.float32) + \
+                        1j * np.clip(im * safe, -fmax, fmax).astype(np.float32)
+                out[li, lo_i:hi_i] = o.astype(np.complex64)
+            else:
+                v = seg.astype(np.float64)
+                with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                    safe = np.where(np.abs(v) > fmax / gains, np.nextafter(fmax / np.abs(v), 0.0), gains)
+                    out[li, lo_i:hi_i] = np.clip(v * safe, -fmax, fmax).astype(np.float32)
+            start = end
+    return np.moveaxis(out.reshape(xm.shape), -1, axis)
 
 
 def window(n: int) -> np.ndarray:

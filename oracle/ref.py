@@ -104,17 +104,31 @@ class Session:
         if rc != 0:
             raise RefError(self._L.jst_ref_last_error().decode())
 
+    _INT_CODES = {"I8": (2, np.int8), "U8": (3, np.uint8), "I16": (4, np.int16), "U16": (5, np.uint16),
+                  "I32": (6, np.int32), "U32": (7, np.uint32), "CI8": (8, np.int8), "CU8": (9, np.uint8),
+                  "CI16": (10, np.int16), "CU16": (11, np.uint16), "CI32": (12, np.int32), "CU32": (13, np.uint32)}
+
     def add_source(self, name: str, array: np.ndarray, sample_axis: int = -1, batch_axis: int = -1,
-                   channel_axis: int = -1):
+                   channel_axis: int = -1, dtype: Optional[str] = None):
+        """`dtype` names an integer tensor type ("I8" ... "CU32"); complex integers are passed as an integer
+        array whose last axis holds (re, im)."""
         array = np.ascontiguousarray(array)
-        if array.dtype == np.float32:
+        shape_logical = array.shape
+        if dtype is not None:
+            dt, np_type = self._INT_CODES[dtype]
+            if array.dtype != np_type:
+                raise TypeError(f"{dtype} source needs a {np_type} array")
+            if dtype.startswith("C"):
+                assert array.shape[-1] == 2
+                shape_logical = array.shape[:-1]
+        elif array.dtype == np.float32:
             dt = 0
         elif array.dtype == np.complex64:
             dt = 1
         else:
-            raise TypeError("source must be float32 or complex64")
-        shape = (ctypes.c_uint64 * array.ndim)(*array.shape)
-        self._check(self._L.jst_ref_add_source(self._h, name.encode(), dt, array.ndim, shape,
+            raise TypeError("source must be float32 or complex64 (or pass dtype=...)")
+        shape = (ctypes.c_uint64 * len(shape_logical))(*shape_logical)
+        self._check(self._L.jst_ref_add_source(self._h, name.encode(), dt, len(shape_logical), shape,
                                                sample_axis, batch_axis, channel_axis))
         self._sources[name] = (array.dtype, array.shape)
         self.write_source(name, array)
@@ -182,16 +196,21 @@ def _axes_for(x: np.ndarray, sample_axis: Optional[int]):
 
 def run_block(type_: str, inputs: Dict[str, np.ndarray], config: Optional[dict] = None,
               out_port: str = "signal", sample_axis: Optional[int] = None, cycles: int = 1,
-              axes: Optional[Dict[str, Tuple[int, int, int]]] = None) -> np.ndarray:
+              axes: Optional[Dict[str, Tuple[int, int, int]]] = None,
+              dtypes: Optional[Dict[str, str]] = None) -> np.ndarray:
     with Session() as s:
         wiring = {}
         for port, arr in inputs.items():
+            dtype = (dtypes or {}).get(port)
             if axes and port in axes:
                 sa, ba, ca = axes[port]
+            elif dtype is not None and dtype.startswith("C"):
+                sa, ba = _axes_for(arr[..., 0], sample_axis)
+                ca = -1
             else:
                 sa, ba = _axes_for(arr, sample_axis)
                 ca = -1
-            s.add_source("src_" + port, arr, sa, ba, ca)
+            s.add_source("src_" + port, arr, sa, ba, ca, dtype=dtype)
             wiring[port] = f"src_{port}.signal"
         s.add_block("dut", type_, config, wiring)
         for _ in range(cycles):

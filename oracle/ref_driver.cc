@@ -70,7 +70,10 @@ struct OracleSourceImpl : public Module::Impl,
     }
 
     Result create() override {
-        const DataType dtype = dataType == "F32" ? DataType::F32 : DataType::CF32;
+        const DataType dtype = NameToDataType(dataType);
+        if (dtype == DataType::None) {
+            return Result::ERROR;
+        }
         JST_CHECK(signal.create(device(), dtype, ParseDims(shape)));
         if (sampleAxis >= 0) {
             JST_CHECK(signal.setAttribute("sampleAxis", Index{static_cast<U64>(sampleAxis)}));
@@ -234,7 +237,8 @@ void jst_ref_destroy(void* handle) {
     delete s;
 }
 
-// dtype: 0 = F32, 1 = CF32. axes: -1 = attribute absent.
+// dtype: the codes of include/b200dsp.h (0 F32, 1 CF32, 2 I8, 3 U8, 4 I16, 5 U16, 6 I32, 7 U32, 8 CI8 ... 13 CU32).
+// axes: -1 = attribute absent.
 int jst_ref_add_source(void* handle, const char* name, int dtype, int rank, const uint64_t* shape,
                        int64_t sampleAxis, int64_t batchAxis, int64_t channelAxis) {
     auto* s = static_cast<Session*>(handle);
@@ -244,7 +248,13 @@ int jst_ref_add_source(void* handle, const char* name, int dtype, int rank, cons
     }
     Parser::Map config;
     config["shape"] = dims;
-    config["dataType"] = std::string(dtype == 0 ? "F32" : "CF32");
+    static const char* const kNames[] = {"F32", "CF32", "I8", "U8", "I16", "U16", "I32", "U32",
+                                         "CI8", "CU8", "CI16", "CU16", "CI32", "CU32"};
+    if (dtype < 0 || dtype > 13) {
+        g_error = "add_source: unknown dtype code";
+        return -1;
+    }
+    config["dataType"] = std::string(kNames[dtype]);
     config["sampleAxis"] = std::to_string(sampleAxis);
     config["batchAxis"] = std::to_string(batchAxis);
     config["channelAxis"] = std::to_string(channelAxis);

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cyberether_b200.sharding import all_shards, gather_rows, max_over_ranks, shard_bounds
+from cyberether_b200.sharding import all_shards, gather_rows, max_over_ranks, scatter_rows, shard_bounds
 
 
 def test_shards_partition_the_batch_exactly():
@@ -37,6 +37,10 @@ def _worker(rank, world, port, total_rows, n, results):
         begin, end = shard_bounds(total_rows, world, rank)
         # each rank "processes" its slab: row r of the result holds r (so order is checkable)
         local = torch.arange(begin, end, dtype=torch.float32)[:, None].repeat(1, n)
+        # graph-boundary scatter: rank 0 owns the whole input, every rank must receive exactly its slab
+        whole_in = torch.arange(total_rows, dtype=torch.float32)[:, None].repeat(1, n) if rank == 0 else None
+        mine = scatter_rows(whole_in, total_rows, (n,), torch.float32, "cpu", src=0)
+        assert mine.shape == (end - begin, n) and torch.equal(mine, local)
         slowest = max_over_ranks(10.0 + rank)                 # rank 1 is slower: everyone must see 11.0
         whole = gather_rows(local, total_rows, dst=0)
         dist.barrier()

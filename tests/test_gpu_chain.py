@@ -97,3 +97,86 @@ def test_chain_flat_range(ref):
     want = ref.spectrum_engine(x, enable_scale=True, range_min=-50.0, range_max=-50.0)
     got = _run_chain(x, True, -50.0, -50.0)
     assert np.array_equal(got, want) and np.all(got == 0.5)
+
+
+def _chain_module(buffer, window, dtype=None, enable_scale=True):
+    import cyberether_b200 as cb
+    ctx = cb.TestContext("spectral_chain")
+    shape_rank = buffer.ndim - (1 if dtype and dtype.startswith("C") else 0)
+    ctx.set_input("buffer", buffer, dtype=dtype, sampleAxis=shape_rank - 1, batchAxis=0 if shape_rank > 1 else None)
+    ctx.set_input("window", window, sampleAxis=0)
+    ctx.set_config(enableScale=enable_scale, rangeMin=-120.0, rangeMax=0.0)
+    assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
+    return ctx.output("buffer")
+
+
+@pytest.mark.parametrize("name,np_type,n,rows", [("CI8", np.int8, 4096, 300), ("CU8", np.uint8, 4096, 37),
+                                                 ("CI16", np.int16, 4096, 300), ("CU16", np.uint16, 4096, 5),
+                                                 ("CI32", np.int32, 4096, 9), ("CI8", np.int8, 1024, 40),
+                                                 ("CI16", np.int16, 8192, 6)])
+@pytest.mark.parametrize("enable_scale", [True, False])
+def test_chain_integer_ingest_equals_cast_then_chain(ref, name, np_type, n, rows, enable_scale):
+    """Fused complex-integer ingest (one kernel for n = 4096 / 8- and 16-bit samples, cast + chain otherwise):
+    bit-identical to the provider's own cast module followed by the CF32 chain, and within the chain allowance of
+    the reference's cast -> spectrum_engine flowgraph."""
+    import cyberether_b200 as cb
+    from oracle import port
+    info = np.iinfo(np_type)
+    rng = np.random.default_rng(n + rows)
+    # a few tones + noise, quantised to the integer range (an SDR capture)
+    t = np.arange(n)
+    sig = sum(a * np.exp(2j * np.pi * f * t / n) for a, f in [(0.5, 100.25), (0.05, 1500.5), (0.002, 3000.0)])
+    sig = sig[None, :] * np.exp(2j * np.pi * rng.random((rows, 1))) + 0.01 * (rng.standard_normal((rows, n)) +
+                                                                              1j * rng.standard_normal((rows, n)))
+    half = (float(info.max) - float(info.min) + 1) / 2
+    mid = 0.0 if info.min < 0 else half
+    x = np.stack([sig.real, sig.imag], axis=-1) * half * 0.9 + mid
+    x = np.clip(np.rint(x), info.min, info.max).astype(np_type)
+    w = _window(ref, n)
+    got = _chain_module(x, w, dtype=name, enable_scale=enable_scale)
+    xf = port.cast(x, complex_pairs=True)                    # bit-exact restatement of the reference cast (test_oracle)
+    two_step = _chain_module(xf, w, enable_scale=enable_scale)
+    assert got.shape == (rows, n) and got.dtype == np.float32
+    assert np.array_equal(got, two_step)
+    with ref.Session() as s:
+        s.add_source("src", x, sample_axis=1, batch_axis=0, dtype=name)
+        s.add_block("c", "cast", {"outputType": "CF32"}, {"buffer": "src.signal"})
+        s.add_block("se", "spectrum_engine", {"enableScale": enable_scale, "rangeMin": -120.0, "rangeMax": 0.0},
+                    {"buffer": "c.buffer"})
+        s.compute()
+        s.compute()
+        want = s.output("se", "buffer")
+    spec = true_spectrum(xf, w)
+    if enable_scale:
+        assert_db_close(got, want, spec, scale=_range_slope(-120.0, 0.0), floor=3e-7)
+    else:
+        assert_db_close(got, want, spec)
+
+
+@pytest.mark.parametrize("enable_scale", [True, False])
+@pytest.mark.parametrize("fused", [True, False])
+def test_spectrum_engine_with_agc(ref, enable_scale, fused):
+    """enableAgc: an `agc` module (one RMS tile per spectrum) between fft and amplitude (block_impl.cc:186-200).
+    The provider runs that graph module by module (the fused flag has no effect); same allowance as the chain plus
+    the dB image of the gain's last-bit differences."""
+    import cyberether_b200 as cb
+    from cyberether_b200.blocks import SpectrumEngine
+    from cyberether_b200.synthetic import spectral_rows
+    x = spectral_rows(7, 48) * np.float32(0.03)
+    block = SpectrumEngine(enableAgc=True, enableScale=enable_scale, fused=fused)
+    inp = cb.Tensor.from_numpy(x, sampleAxis=1, batchAxis=0)
+    assert block.create("spec", {"buffer": inp}) == cb.Result.SUCCESS, cb.last_error()
+    for _ in range(2):
+        assert block.compute() == cb.Result.SUCCESS, cb.last_error()
+    got = block.output("buffer").numpy()
+    assert "agc" in block.modules and "spectral_chain" not in block.modules
+    block.destroy()
+    want = ref.run_block("spectrum_engine", {"buffer": x}, {"enableAgc": True, "enableScale": enable_scale,
+                                                           "rangeMin": -120.0, "rangeMax": 0.0}, "buffer")
+    spec = true_spectrum(x, _window(ref, 4096))
+    # the AGC gain is common to a row: it moves every bin by the same dB, the allowance is relative to the row peak
+    # exactly as without AGC
+    if enable_scale:
+        assert_db_close(got, want, spec, scale=_range_slope(-120.0, 0.0), floor=3e-7)
+    else:
+        assert_db_close(got, want, spec)

@@ -292,3 +292,116 @@ def test_chain_non_power_of_two_length(ref):
     w = ref.window(n).copy()
     w[1::2] *= -1
     assert_db_close(got, want, true_spectrum(x, w), scale=2.0 / 120.0, floor=3e-7)
+
+
+CAST_CASES = [("I8", np.int8, False), ("U8", np.uint8, False), ("I16", np.int16, False), ("U16", np.uint16, False),
+              ("I32", np.int32, False), ("U32", np.uint32, False), ("CI8", np.int8, True), ("CU8", np.uint8, True),
+              ("CI16", np.int16, True), ("CU16", np.uint16, True), ("CI32", np.int32, True), ("CU32", np.uint32, True)]
+
+
+@pytest.mark.parametrize("name,np_type,is_complex", CAST_CASES)
+@pytest.mark.parametrize("shape", [(1,), (5, 37), (3, 4096)])
+def test_cast_integer_bit_exact(ref, name, np_type, is_complex, shape):
+    """cast: every integer / complex-integer conversion of the reference's native module, bit-exact, including the
+    extreme values and sizes that exercise the vector body and the scalar tail."""
+    import cyberether_b200 as cb
+    info = np.iinfo(np_type)
+    rng = np.random.default_rng(hash(name) % 1000)
+    full = shape + (2,) if is_complex else shape
+    x = rng.integers(info.min, info.max, size=full, endpoint=True, dtype=np_type)
+    x.flat[0] = info.min
+    x.flat[-1] = info.max
+    out_type = "CF32" if is_complex else "F32"
+    ctx = cb.TestContext("cast")
+    ctx.set_input("buffer", x, dtype=name, sampleAxis=len(shape) - 1)
+    ctx.set_config(outputType=out_type)
+    assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
+    got = ctx.output("buffer")
+    want = ref.run_block("cast", {"buffer": x}, {"outputType": out_type}, "buffer", dtypes={"buffer": name})
+    assert got.dtype == want.dtype and got.shape == want.shape == shape
+    assert np.array_equal(got, want)
+
+
+def test_cast_unsupported_pair_is_an_error():
+    import cyberether_b200 as cb
+    ctx = cb.TestContext("cast")
+    ctx.set_input("buffer", np.zeros((4, 2), np.int8), dtype="CI8", sampleAxis=0)
+    ctx.set_config(outputType="F32")                       # complex integer -> real float is not a reference pair
+    assert ctx.run() == cb.Result.ERROR
+    assert "Unsupported conversion" in cb.last_error()
+
+
+def _assert_agc_equal(got, want):
+    """Gains are F64 on both sides and differ only by the order of the F64 power sum (a few F64 ulp), so the F32
+    outputs are identical except for rare last-bit rounding flips."""
+    assert got.shape == want.shape and got.dtype == want.dtype
+    g = got.view(np.float32) if np.iscomplexobj(got) else got
+    w = want.view(np.float32) if np.iscomplexobj(want) else want
+    both_nan = np.isnan(g) & np.isnan(w)
+    diff = (g != w) & ~both_nan
+    assert float(diff.mean()) <= 1e-4, f"{int(diff.sum())} of {diff.size} values differ"
+    if diff.any():
+        assert np.all(np.abs(g[diff] - w[diff]) <= np.spacing(np.abs(w[diff])))
+
+
+@pytest.mark.parametrize("complex_input", [True, False])
+@pytest.mark.parametrize("shape,tile,axis", [((3, 1000), 256, 1), ((64, 4096), 4096, 1), ((1, 77), 1024, 1),
+                                             ((4, 5000), 64, 1), ((300, 6), 4, 0), ((2, 3, 520), 128, 2)])
+def test_agc_matches_reference(ref, complex_input, shape, tile, axis):
+    """agc module vs the reference's agc block (parameters chosen exactly representable in F32, because the
+    reference BLOCK stores them as F32) and vs the pinned numpy restatement with the module's F64 defaults."""
+    import cyberether_b200 as cb
+    from oracle import port
+    rng = np.random.default_rng(sum(shape) + tile)
+    n = shape[axis]
+    env_shape = [1] * len(shape)
+    env_shape[axis] = n
+    step = (1 + 7 * (np.arange(n) > n // 2)).reshape(env_shape)             # a level jump the rate limit must follow
+    lane_shape = [s if d != axis else 1 for d, s in enumerate(shape)]
+    env = np.exp(rng.uniform(-6, 6, size=lane_shape)) * step
+    x = rng.standard_normal(shape) * env
+    x = (x + 1j * rng.standard_normal(shape) * env).astype(np.complex64) if complex_input else x.astype(np.float32)
+    axes = dict(sampleAxis=axis, batchAxis=None)
+    exact = dict(tileSize=tile, reference=0.5, epsilon=2.0 ** -40, minGain=0.0625, maxGain=64.0, maxGainChange=2.0)
+    ctx = cb.TestContext("agc")
+    ctx.set_input("signal", x, **axes)
+    ctx.set_config(**exact)
+    assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
+    want = ref.run_block("agc", {"signal": x}, exact, "signal", axes={"signal": (axis, -1, -1)})
+    _assert_agc_equal(ctx.output("signal"), want)
+    ctx = cb.TestContext("agc")
+    ctx.set_input("signal", x, **axes)
+    ctx.set_config(tileSize=tile)                                             # module defaults (F64 0.01, 1e-12, ...)
+    assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
+    _assert_agc_equal(ctx.output("signal"), port.agc(x, tile_size=tile, axis=axis))
+
+
+def test_agc_keeps_huge_inputs_finite_like_reference(ref):
+    """ApplyGain limits every product to the finite F32 range (module_impl_native_cpu.cc:36-60)."""
+    import cyberether_b200 as cb
+    big = np.float32(3.0e38)
+    x = np.zeros((2, 512), np.complex64)
+    x[0, :] = 1e-3
+    x[0, 100] = big + 1j * big            # |z| beyond FLT_MAX
+    x[1, :] = (np.arange(512) % 7) * 1e-3
+    x[1, 5] = -big
+    cfg = dict(tileSize=128, reference=1.0, epsilon=2.0 ** -40, minGain=0.5, maxGain=64.0, maxGainChange=4.0)
+    ctx = cb.TestContext("agc")
+    ctx.set_input("signal", x, sampleAxis=1, batchAxis=0)
+    ctx.set_config(**cfg)
+    assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
+    got = ctx.output("signal")
+    want = ref.run_block("agc", {"signal": x}, cfg, "signal")
+    assert np.all(np.isfinite(got.view(np.float32)))
+    _assert_agc_equal(got, want)
+
+
+def test_agc_rejects_bad_config_like_reference():
+    import cyberether_b200 as cb
+    for bad, text in ((dict(tileSize=0), "Tile size"), (dict(reference=0.0), "Reference"),
+                      (dict(minGain=2.0, maxGain=1.0), "Maximum gain"), (dict(maxGainChange=0.5), "gain change")):
+        ctx = cb.TestContext("agc")
+        ctx.set_input("signal", np.ones((2, 8), np.float32), sampleAxis=1, batchAxis=0)
+        ctx.set_config(**bad)
+        assert ctx.run() == cb.Result.ERROR
+        assert text in cb.last_error()

@@ -104,7 +104,11 @@ def test_spectrum_engine_wiring_fused_and_unfused():
     sched = unfused.scheduler
     static = {m.name.split(":")[1] for m in sched.order if sched.is_static(m)}
     assert static == {"window", "invert", "reshape_window"}     # settle after cycle 1 (block_tests.cc:103-122)
-    assert SpectrumEngine(enableAgc=True).create("s", {"buffer": x}) == cb.Result.ERROR
+    with_agc = SpectrumEngine(enableAgc=True)                   # agc sits between fft and amplitude (block_impl.cc:186-200)
+    assert with_agc.create("s", {"buffer": x}) == cb.Result.SUCCESS
+    names = list(with_agc.modules)
+    assert names.index("fft") < names.index("agc") < names.index("amplitude") and "spectral_chain" not in names
+    assert with_agc.modules["agc"].config["tileSize"] == 4096   # one RMS tile per spectrum
     assert SpectrumEngine().create("s", {"buffer": tensor((4, 8))}) == cb.Result.ERROR
 
 

@@ -122,3 +122,36 @@ def test_known_answer_amplitude_and_range():
     assert np.abs(out[[0, 1, 3]] - exact[[0, 1, 3]]).max() < 0.1
     r = port.range_(np.array([-1.0, 0.0, 1.0], np.float32), -1.0, 1.0)
     assert np.abs(r - (0.5 + 0.5 * np.tanh(4 * (np.array([0, 0.5, 1.0]) - 0.5)))).max() < 1e-6
+
+
+@pytest.mark.parametrize("name,np_type,is_complex", [("I8", np.int8, False), ("U16", np.uint16, False),
+                                                     ("I32", np.int32, False), ("CI8", np.int8, True),
+                                                     ("CU8", np.uint8, True), ("CI16", np.int16, True),
+                                                     ("CU32", np.uint32, True)])
+def test_port_cast_matches_reference(ref, name, np_type, is_complex):
+    info = np.iinfo(np_type)
+    shape = (7, 33, 2) if is_complex else (7, 33)
+    x = np.random.default_rng(3).integers(info.min, info.max, size=shape, endpoint=True, dtype=np_type)
+    want = ref.run_block("cast", {"buffer": x}, {"outputType": "CF32" if is_complex else "F32"}, "buffer",
+                         dtypes={"buffer": name})
+    assert np.array_equal(port.cast(x, complex_pairs=is_complex), want)
+
+
+@pytest.mark.parametrize("complex_input", [True, False])
+@pytest.mark.parametrize("shape,tile", [((3, 1000), 256), ((2, 4096), 4096), ((1, 77), 1024), ((4, 513), 64)])
+def test_port_agc_matches_reference(ref, complex_input, shape, tile):
+    rng = np.random.default_rng(sum(shape) + tile)
+    env = np.exp(rng.uniform(-6, 6, size=(shape[0], 1))) * (1 + 5 * (np.arange(shape[1]) > shape[1] // 2))
+    x = rng.standard_normal(shape) * env
+    if complex_input:
+        x = (x + 1j * rng.standard_normal(shape) * env).astype(np.complex64)
+    else:
+        x = x.astype(np.float32)
+    want = ref.run_block("agc", {"signal": x}, {"tileSize": tile}, "signal")
+    # the agc BLOCK holds its parameters as F32 (include/jetstream/domains/dsp/agc/block.hh:9-14) and widens them
+    # into the module's F64 config (block_impl.cc:17-24): minGain is (double)0.01f, epsilon (double)1e-12f
+    f32 = lambda v: float(np.float32(v))
+    got = port.agc(x, tile_size=tile, reference=f32(1.0), epsilon=f32(1e-12), min_gain=f32(0.01), max_gain=f32(100.0),
+                   max_gain_change=f32(4.0))
+    assert got.dtype == want.dtype
+    assert np.array_equal(got, want)
