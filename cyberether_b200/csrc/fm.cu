@@ -4,10 +4,9 @@
 //     first sample ever -> 0; non-finite x[n] or x[n-1] -> NaN (and the de-emphasis state is not touched)
 //     optional one-pole de-emphasis y += alpha (d - y), state carried per lane across frames and cycles.
 // Tensor layout [frames, lanes, frame_len]: frames (the batch axis) are consecutive in time, lanes
-// (channel axis, e.g. filter heads) are independent. The discriminator is elementwise (12 B/sample);
-// the de-emphasis recurrence is evaluated as a blocked linear-recurrence scan: per-chunk (gain, offset)
-// pairs -> serial carry propagation over chunks -> each chunk replayed sequentially from its carry in the
-// reference's own operation order.
+// (channel axis, e.g. filter heads) are independent. Discriminator and de-emphasis are ONE pass over the data
+// (12 B/sample): the recurrence is a scan of affine maps y -> g y + o with a decoupled look-back between tiles, each
+// thread replaying its own samples from its carry-in in the reference's operation order.
 #include <algorithm>
 #include <cmath>
 
@@ -30,161 +29,244 @@ __device__ __forceinline__ float discriminate(const float2 p, const float2 c, co
     return __fmul_rn(atan2f(im, re), ref);
 }
 
-// grid: (segments of the row, rows); row = frame * lanes + lane. No per-element index division.
-__global__ void fm_discriminator_kernel(const float2* __restrict__ x, float* __restrict__ out,
-                                        const FmState* __restrict__ state, const uint64_t frames,
-                                        const uint64_t lanes, const uint64_t frame_len, const float ref) {
-    const uint64_t rows = frames * lanes;
-    for (uint64_t row = blockIdx.y; row < rows; row += gridDim.y) {
-        const uint64_t lane = row % lanes, frame = row / lanes;
-        const float2* const xr = x + row * frame_len;
-        float* const outr = out + row * frame_len;
-        for (uint64_t s = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; s < frame_len;
-             s += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-            const float2 cur = ldg_stream_f2(xr + s);
-            float2 prev;
-            bool has_prev = true;
-            if (s > 0) {
-                prev = xr[s - 1];
+// ---- narrow mode in ONE pass: discriminator + de-emphasis with a decoupled look-back scan ---------------------
+// 12 B/sample (8 read, 4 written) instead of the 24 of discriminator + reduce + carry + apply. A CTA takes tiles of
+// 2048 consecutive samples of one row (frame, lane), 8 samples per thread:
+//   1. 16-byte loads, d[k] in registers (the reference's rounding sequence + atan2f);
+//   2. each thread folds its 8 samples into the affine map y -> g y + o of the recurrence (zero-state response o in
+//      the reference's operation order, g = (1-alpha)^#finite), a warp-shuffle + shared-memory scan composes them;
+//   3. the tile publishes its aggregate map, warp 0 looks back over the predecessor tiles of the same lane (tiles are
+//      numbered time-major, lanes innermost: predecessor = id - lanes) combining aggregates until it meets a tile whose
+//      inclusive carry is known, publishes its own carry, and
+//   4. every thread replays its 8 samples from its own carry-in — again the reference's operation order.
+// Slots carry a launch epoch, so nothing is cleared between launches. The grid never exceeds the number of co-resident
+// CTAs (a CTA only ever waits on tiles with smaller ids, which are running or done).
+constexpr int kFmTileThreads = 256;
+constexpr int kFmPerThread = 8;
+constexpr int kFmTile = kFmTileThreads * kFmPerThread;
+
+// Two self-validating 64-bit words per tile (64-bit accesses are single-copy atomic, so no fence is needed):
+//   a = (epoch << 2 | state) << 32 | bits(g or y)      state 1: aggregate map (g, o) published, 2: carry-out y published
+//   b = (epoch << 2 | 1)     << 32 | bits(o)
+struct FmScanSlot {
+    unsigned long long a, b;
+};
+__device__ __forceinline__ unsigned long long pack_slot(const uint32_t tag, const float value) {
+    return (static_cast<unsigned long long>(tag) << 32) | __float_as_uint(value);
+}
+__device__ __forceinline__ unsigned long long ld_slot(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void st_slot(unsigned long long* p, const unsigned long long v) {
+    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+struct FmNarrowParams {
+    const float2* x;
+    float* out;
+    FmState* state;
+    FmScanSlot* slots;
+    uint64_t frames, lanes, frame_len, tiles_per_row, items;
+    float ref, alpha;
+    uint32_t epoch;
+};
+
+template <bool DEEMPH, bool VEC>
+__global__ void __launch_bounds__(kFmTileThreads) fm_narrow_fused_kernel(const FmNarrowParams p) {
+    __shared__ float warp_g[kFmTileThreads / 32], warp_o[kFmTileThreads / 32];
+    const uint32_t t = threadIdx.x, lane_id = t & 31, warp = t >> 5;
+    const float keep = 1.0f - p.alpha;
+    for (uint64_t id = blockIdx.x; id < p.items; id += gridDim.x) {
+        // id = ((frame * tiles_per_row) + tile) * lanes + lane
+        const uint64_t lane = id % p.lanes;
+        const uint64_t ft = id / p.lanes;
+        const uint64_t frame = ft / p.tiles_per_row, tile = ft - frame * p.tiles_per_row;
+        const uint64_t row = frame * p.lanes + lane;
+        const float2* const xr = p.x + row * p.frame_len;
+        float* const outr = p.out + row * p.frame_len;
+        const uint64_t s0 = tile * kFmTile + static_cast<uint64_t>(t) * kFmPerThread;
+
+        // ---- 1. samples s0-1 .. s0+7 -----------------------------------------------------------------------
+        float2 v[kFmPerThread + 1];
+        bool has_prev = true;
+        if (s0 < p.frame_len) {
+            if (s0 > 0) {
+                v[0] = xr[s0 - 1];
             } else if (frame > 0) {
-                prev = x[((frame - 1) * lanes + lane) * frame_len + frame_len - 1];
+                v[0] = p.x[((frame - 1) * p.lanes + lane) * p.frame_len + p.frame_len - 1];
             } else {
-                prev = state[lane].previous;
-                has_prev = state[lane].has_previous != 0;
+                v[0] = p.state[lane].previous;
+                has_prev = p.state[lane].has_previous != 0;
             }
-            float d;
-            if (!has_prev) {
-                d = 0.0f;
-            } else if (finite2(cur) && finite2(prev)) {
-                d = discriminate(prev, cur, ref);
-            } else {
-                d = __int_as_float(0x7fc00000);
-            }
-            outr[s] = d;
+        } else {
+            v[0] = make_float2(0.f, 0.f);
         }
-    }
-}
-
-// ---- de-emphasis: y[n] = y[n-1] + alpha (d[n] - y[n-1]) over finite d, blocked scan ------------------
-constexpr int kFmChunk = 256;
-
-// Phase 1: per chunk, zero-state response at the chunk end (offset) and the state gain (1-alpha)^#finite.
-__global__ void fm_deemph_reduce_kernel(const float* __restrict__ d, float2* __restrict__ chunk_coeff,
-                                        const uint64_t frames, const uint64_t lanes, const uint64_t frame_len,
-                                        const uint64_t chunks_per_lane, const float alpha) {
-    const uint64_t total_chunks = chunks_per_lane * lanes;
-    const uint64_t lane_len = frames * frame_len;
-    for (uint64_t c = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; c < total_chunks;
-         c += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-        const uint64_t lane = c / chunks_per_lane;
-        const uint64_t n0 = (c % chunks_per_lane) * kFmChunk;
-        float y = 0.0f, gain = 1.0f;
-        const float keep = 1.0f - alpha;
-        for (uint64_t nb = n0; nb < n0 + kFmChunk && nb < lane_len; nb += 16) {
-            float v[16];
+        if (VEC && s0 + kFmPerThread <= p.frame_len) {
+            const float4* const src = reinterpret_cast<const float4*>(xr + s0);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {      // independent loads first, then the sequential recurrence
-                const uint64_t n = nb + u;
-                v[u] = __int_as_float(0x7fc00000);
-                if (n < lane_len) {
-                    const uint64_t frame = n / frame_len, s = n - frame * frame_len;
-                    v[u] = d[(frame * lanes + lane) * frame_len + s];
+            for (int k = 0; k < kFmPerThread / 2; ++k) {
+                const float4 q = __ldcs(src + k);
+                v[1 + 2 * k] = make_float2(q.x, q.y);
+                v[2 + 2 * k] = make_float2(q.z, q.w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kFmPerThread; ++k) {
+                v[1 + k] = s0 + k < p.frame_len ? xr[s0 + k] : make_float2(0.f, 0.f);
+            }
+        }
+        float d[kFmPerThread];
+#pragma unroll
+        for (int k = 0; k < kFmPerThread; ++k) {
+            if (k == 0 && !has_prev) {
+                d[k] = 0.0f;
+            } else if (finite2(v[k + 1]) && finite2(v[k])) {
+                d[k] = discriminate(v[k], v[k + 1], p.ref);
+            } else {
+                d[k] = __int_as_float(0x7fc00000);
+            }
+        }
+
+        float y_start = 0.0f;
+        if constexpr (DEEMPH) {
+            // ---- 2. this thread's map, then the tile-wide scan of map compositions ---------------------------------
+            float g = 1.0f, o = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kFmPerThread; ++k) {
+                if (s0 + k < p.frame_len && isfinite(d[k])) {
+                    o = __fadd_rn(o, __fmul_rn(p.alpha, __fsub_rn(d[k], o)));
+                    g *= keep;
                 }
             }
+            float sg = g, so = o;                                  // inclusive scan inside the warp
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                if (isfinite(v[u])) {
-                    y = __fadd_rn(y, __fmul_rn(alpha, __fsub_rn(v[u], y)));
-                    gain *= keep;
+            for (int off = 1; off < 32; off <<= 1) {
+                const float pg = __shfl_up_sync(0xffffffffu, sg, off);
+                const float po = __shfl_up_sync(0xffffffffu, so, off);
+                if (lane_id >= static_cast<uint32_t>(off)) {
+                    so = fmaf(sg, po, so);                         // later map after earlier map
+                    sg *= pg;
                 }
             }
-        }
-        chunk_coeff[c] = make_float2(gain, y);
-    }
-}
-
-// Phase 2: carries, one CTA per lane. Chunk maps y -> gain*y + offset compose associatively, so the CTA's 256
-// threads each fold a contiguous segment of chunks, a shared-memory scan combines the 256 segment maps, and each
-// thread replays its segment from its exclusive prefix, leaving the carry-in of every chunk in chunk_coeff[c].x.
-__global__ void __launch_bounds__(256) fm_deemph_carry_kernel(float2* __restrict__ chunk_coeff,
-                                                             const FmState* __restrict__ state, const uint64_t lanes,
-                                                             const uint64_t chunks_per_lane) {
-    __shared__ float sg[256], so[256];
-    for (uint64_t lane = blockIdx.x; lane < lanes; lane += gridDim.x) {
-        float2* const cc = chunk_coeff + lane * chunks_per_lane;
-        const uint64_t seg = (chunks_per_lane + 255) / 256;
-        const uint64_t c0 = threadIdx.x * seg;
-        const uint64_t c1 = c0 + seg < chunks_per_lane ? c0 + seg : chunks_per_lane;
-        float g = 1.0f, o = 0.0f;
-        for (uint64_t c = c0; c < c1; ++c) {
-            const float2 k = cc[c];
-            o = fmaf(k.x, o, k.y);
-            g *= k.x;
-        }
-        __syncthreads();
-        sg[threadIdx.x] = g;
-        so[threadIdx.x] = o;
-        __syncthreads();
-        for (int d = 1; d < 256; d <<= 1) {       // inclusive scan of map composition (later o earlier)
-            float pg = 1.0f, po = 0.0f;
-            if (static_cast<int>(threadIdx.x) >= d) {
-                pg = sg[threadIdx.x - d];
-                po = so[threadIdx.x - d];
+            __syncthreads();                                       // previous tile's shared values are consumed
+            if (lane_id == 31) {
+                warp_g[warp] = sg;
+                warp_o[warp] = so;
             }
             __syncthreads();
-            const float ng = sg[threadIdx.x] * pg;
-            const float no = fmaf(sg[threadIdx.x], po, so[threadIdx.x]);
-            sg[threadIdx.x] = ng;
-            so[threadIdx.x] = no;
-            __syncthreads();
-        }
-        const float y0 = state[lane].deemphasis;
-        float carry = threadIdx.x == 0 ? y0 : fmaf(sg[threadIdx.x - 1], y0, so[threadIdx.x - 1]);
-        for (uint64_t c = c0; c < c1; ++c) {
-            const float2 k = cc[c];
-            cc[c].x = carry;                       // carry-in of chunk c
-            carry = fmaf(k.x, carry, k.y);
-        }
-    }
-}
+            // exclusive prefix of this thread inside the tile: (warps before) then (lanes before)
+            float eg = 1.0f, eo = 0.0f, tg = 1.0f, to = 0.0f;      // (eg, eo): warps before mine; (tg, to): whole tile
+#pragma unroll
+            for (int w = 0; w < kFmTileThreads / 32; ++w) {
+                if (w == static_cast<int>(warp)) {
+                    eg = tg;
+                    eo = to;
+                }
+                to = fmaf(warp_g[w], to, warp_o[w]);
+                tg *= warp_g[w];
+            }
+            float lg = __shfl_up_sync(0xffffffffu, sg, 1), lo = __shfl_up_sync(0xffffffffu, so, 1);
+            if (lane_id == 0) {
+                lg = 1.0f;
+                lo = 0.0f;
+            }
+            const float xg = lg * eg, xo = fmaf(lg, eo, lo);       // map of everything before this thread in the tile
 
-// Phase 3: replay each chunk from its carry in the reference's operation order; the last chunk of each
-// lane publishes the new state.
-__global__ void fm_deemph_apply_kernel(float* __restrict__ d, const float2* __restrict__ chunk_coeff,
-                                       FmState* __restrict__ state, const uint64_t frames, const uint64_t lanes,
-                                       const uint64_t frame_len, const uint64_t chunks_per_lane, const float alpha) {
-    const uint64_t total_chunks = chunks_per_lane * lanes;
-    const uint64_t lane_len = frames * frame_len;
-    for (uint64_t c = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; c < total_chunks;
-         c += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-        const uint64_t lane = c / chunks_per_lane;
-        const uint64_t ci = c % chunks_per_lane;
-        const uint64_t n0 = ci * kFmChunk;
-        float y = chunk_coeff[c].x;
-        for (uint64_t nb = n0; nb < n0 + kFmChunk && nb < lane_len; nb += 16) {
-            float v[16];
-            float* slot[16];
+            // ---- 3. decoupled look-back, the whole CTA: 256 predecessors per round ---------------------------------
+            // A predecessor that already knows its carry-out y is the constant map (0, y); composing nearest-first, the
+            // first such map annihilates everything older, so the rounds stop as soon as one was seen.
+            FmScanSlot* const mine = p.slots + id;
+            if (t == 0) {
+                st_slot(&mine->b, pack_slot((p.epoch << 2) | 1u, to));
+                st_slot(&mine->a, pack_slot((p.epoch << 2) | 1u, tg));
+            }
+            float ag = 1.0f, ao = 0.0f;                              // map of the tiles looked at so far (nearest applied last)
+            for (uint64_t back = 1;; back += kFmTileThreads) {
+                const uint64_t steps = back + t;
+                float mg, mo;
+                bool is_carry;
+                if (steps * p.lanes > id) {                          // before the lane's first tile: the carried state
+                    is_carry = true;
+                    mg = 0.0f;
+                    mo = p.state[lane].deemphasis;
+                } else {
+                    const FmScanSlot* const slot = p.slots + (id - steps * p.lanes);
+                    unsigned long long a = ld_slot(&slot->a);
+                    while (static_cast<uint32_t>(a >> 34) != p.epoch) {
+                        a = ld_slot(&slot->a);
+                    }
+                    is_carry = ((a >> 32) & 3u) == 2u;
+                    if (is_carry) {
+                        mg = 0.0f;
+                        mo = __uint_as_float(static_cast<uint32_t>(a));
+                    } else {
+                        unsigned long long b = ld_slot(&slot->b);
+                        while (static_cast<uint32_t>(b >> 34) != p.epoch) {
+                            b = ld_slot(&slot->b);
+                        }
+                        mg = __uint_as_float(static_cast<uint32_t>(a));
+                        mo = __uint_as_float(static_cast<uint32_t>(b));
+                    }
+                }
+                // warp total, nearest (lowest lane) applied last: cur = cur o (cur of lane + off)
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const uint64_t n = nb + u;
-                v[u] = __int_as_float(0x7fc00000);
-                slot[u] = nullptr;
-                if (n < lane_len) {
-                    const uint64_t frame = n / frame_len, s = n - frame * frame_len;
-                    slot[u] = d + (frame * lanes + lane) * frame_len + s;
-                    v[u] = *slot[u];
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float fg = __shfl_down_sync(0xffffffffu, mg, off);
+                    const float fo = __shfl_down_sync(0xffffffffu, mo, off);
+                    if (lane_id + off < 32) {
+                        mo = fmaf(mg, fo, mo);
+                        mg *= fg;
+                    }
+                }
+                __syncthreads();                                     // warp_g / warp_o free again
+                if (lane_id == 0) {
+                    warp_g[warp] = mg;
+                    warp_o[warp] = mo;
+                }
+                const int any_carry = __syncthreads_or(is_carry ? 1 : 0);
+#pragma unroll
+                for (int w = 0; w < kFmTileThreads / 32; ++w) {      // acc = acc o W_0 o W_1 ... (every thread, redundantly)
+                    ao = fmaf(ag, warp_o[w], ao);
+                    ag *= warp_g[w];
+                }
+                if (any_carry) {
+                    break;
                 }
             }
+            const float carry = ao;                                  // ag == 0 by construction: constant map
+            if (t == 0) {
+                const float y_out = fmaf(tg, carry, to);
+                st_slot(&mine->a, pack_slot((p.epoch << 2) | 2u, y_out));
+                // (the lane's new state is taken from its last tile's slot by fm_state_update_kernel AFTER this kernel:
+                // tiles still looking back may read state[lane].deemphasis until the very end)
+            }
+            y_start = fmaf(xg, carry, xo);
+        }
+
+        // ---- 4. replay / store -----------------------------------------------------------------------------------------
+        float r[kFmPerThread];
+        float y = y_start;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                if (isfinite(v[u])) {
-                    y = __fadd_rn(y, __fmul_rn(alpha, __fsub_rn(v[u], y)));
-                    *slot[u] = y;
+        for (int k = 0; k < kFmPerThread; ++k) {
+            r[k] = d[k];
+            if constexpr (DEEMPH) {
+                if (s0 + k < p.frame_len && isfinite(d[k])) {
+                    y = __fadd_rn(y, __fmul_rn(p.alpha, __fsub_rn(d[k], y)));
+                    r[k] = y;
                 }
             }
         }
-        if (ci == chunks_per_lane - 1) {
-            state[lane].deemphasis = y;
+        if (VEC && s0 + kFmPerThread <= p.frame_len) {
+            float4* const dst = reinterpret_cast<float4*>(outr + s0);
+            __stcs(dst, make_float4(r[0], r[1], r[2], r[3]));
+            __stcs(dst + 1, make_float4(r[4], r[5], r[6], r[7]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < kFmPerThread; ++k) {
+                if (s0 + k < p.frame_len) {
+                    outr[s0 + k] = r[k];
+                }
+            }
         }
     }
 }
@@ -478,11 +560,15 @@ struct StereoSystem {
 };
 
 __global__ void fm_state_update_kernel(const float2* __restrict__ x, FmState* __restrict__ state,
-                                       const uint64_t frames, const uint64_t lanes, const uint64_t frame_len) {
+                                       const uint64_t frames, const uint64_t lanes, const uint64_t frame_len,
+                                       const FmScanSlot* __restrict__ last_tiles) {
     const uint64_t lane = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (lane < lanes) {
         state[lane].previous = x[((frames - 1) * lanes + lane) * frame_len + frame_len - 1];
         state[lane].has_previous = 1;
+        if (last_tiles != nullptr) {          // one-pass narrow kernel: carry-out of the lane's last tile
+            state[lane].deemphasis = __uint_as_float(static_cast<uint32_t>(last_tiles[lane].a));
+        }
     }
 }
 
@@ -498,8 +584,9 @@ struct b200_fm_plan {
     bool deemphasis;
     bool wide;
     FmState* state;
-    float2* chunk_coeff;
-    uint64_t chunk_capacity;
+    FmScanSlot* slots = nullptr;          // look-back slots of the fused narrow kernel
+    uint64_t slot_capacity = 0;
+    uint32_t epoch = 0;
     // wide mode
     FmWideCoeffs wc;
     float* wide_state;        // [phase(1) | pilot lanes*4 | audio 2*lanes*8 | stereo lanes*2]
@@ -549,6 +636,47 @@ static int run_scan(const System& sys, float* chunk_resp, int* chunk_count, cons
     return B200_SUCCESS;
 }
 
+// Launch of the one-pass narrow kernel (discriminator, optional de-emphasis). `out` may be any F32 [frames, lanes, T].
+static int launch_narrow_fused(b200_fm_plan* plan, const float2* x, float* out, uint64_t frames, uint64_t frame_len,
+                               bool deemph, cudaStream_t s) {
+    FmNarrowParams q{};
+    q.x = x;
+    q.out = out;
+    q.state = plan->state;
+    q.frames = frames;
+    q.lanes = plan->lanes;
+    q.frame_len = frame_len;
+    q.tiles_per_row = (frame_len + kFmTile - 1) / kFmTile;
+    q.items = frames * q.tiles_per_row * plan->lanes;
+    q.ref = plan->ref;
+    q.alpha = plan->alpha;
+    if (deemph) {
+        if (plan->slot_capacity < q.items || plan->epoch >= (1u << 29)) {
+            cudaFree(plan->slots);
+            plan->slots = nullptr;
+            plan->slot_capacity = 0;
+            B200_CUDA_CHECK(cudaMalloc(&plan->slots, q.items * sizeof(FmScanSlot)));
+            B200_CUDA_CHECK(cudaMemsetAsync(plan->slots, 0, q.items * sizeof(FmScanSlot), s));
+            plan->slot_capacity = q.items;
+            plan->epoch = 0;
+        }
+        q.slots = plan->slots;
+        q.epoch = ++plan->epoch;
+    }
+    const bool vec = frame_len % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    void (*kernel)(FmNarrowParams) =
+        deemph ? (vec ? fm_narrow_fused_kernel<true, true> : fm_narrow_fused_kernel<true, false>)
+               : (vec ? fm_narrow_fused_kernel<false, true> : fm_narrow_fused_kernel<false, false>);
+    int per_sm = 1;
+    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFmTileThreads, 0));
+    // every CTA must be resident: a tile only waits on tiles with smaller ids, which then are running or done
+    const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * static_cast<uint64_t>(per_sm < 1 ? 1 : per_sm);
+    kernel<<<static_cast<unsigned>(std::min<uint64_t>(q.items, cap)), kFmTileThreads, 0, s>>>(q);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
 extern "C" {
 
 int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wide, int deemphasis_us,
@@ -587,8 +715,6 @@ int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wi
         return B200_ERROR;
     }
     pl->state = static_cast<FmState*>(st);
-    pl->chunk_coeff = nullptr;
-    pl->chunk_capacity = 0;
     pl->wide_state = nullptr;
     pl->power = nullptr;
     pl->scratch = nullptr;
@@ -686,9 +812,6 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
     const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * 8;
     const uint64_t lane_len = frames * frame_len;
     (void)blocks;
-    const unsigned seg = static_cast<unsigned>(std::min<uint64_t>((frame_len + 255) / 256, 64));
-    const unsigned rows_y = static_cast<unsigned>(std::min<uint64_t>(frames * plan->lanes, std::max<uint64_t>(1, cap / seg)));
-    const dim3 disc_grid(seg, rows_y);
 
     if (plan->wide) {
         const uint64_t chunks_per_lane = (lane_len + kWideChunk - 1) / kWideChunk;
@@ -712,9 +835,10 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
         float* const stereo_state = audio_state + vlanes * 8;
         const LaneIndex at{plan->lanes, frame_len};
 
-        fm_discriminator_kernel<<<disc_grid, 256, 0, s>>>(
-            reinterpret_cast<const float2*>(x), sum, plan->state, frames, plan->lanes, frame_len, plan->ref);
-        B200_LAUNCH_CHECK();
+        if (launch_narrow_fused(plan, reinterpret_cast<const float2*>(x), sum, frames, frame_len, false, s) !=
+            B200_SUCCESS) {
+            return B200_ERROR;
+        }
         fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
         B200_LAUNCH_CHECK();
         const unsigned ucap = static_cast<unsigned>(cap);
@@ -734,37 +858,22 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
             return B200_ERROR;
         }
         fm_state_update_kernel<<<static_cast<unsigned>((plan->lanes + 63) / 64), 64, 0, s>>>(
-            reinterpret_cast<const float2*>(x), plan->state, frames, plan->lanes, frame_len);
+            reinterpret_cast<const float2*>(x), plan->state, frames, plan->lanes, frame_len, nullptr);
         B200_LAUNCH_CHECK();
         return B200_SUCCESS;
     }
 
-    fm_discriminator_kernel<<<disc_grid, 256, 0, s>>>(
-        reinterpret_cast<const float2*>(x), out, plan->state, frames, plan->lanes, frame_len, plan->ref);
-    B200_LAUNCH_CHECK();
+    if (launch_narrow_fused(plan, reinterpret_cast<const float2*>(x), out, frames, frame_len, plan->deemphasis, s) !=
+        B200_SUCCESS) {
+        return B200_ERROR;
+    }
+    const FmScanSlot* last_tiles = nullptr;
     if (plan->deemphasis) {
-        const uint64_t chunks_per_lane = (lane_len + kFmChunk - 1) / kFmChunk;
-        const uint64_t total_chunks = chunks_per_lane * plan->lanes;
-        if (total_chunks > plan->chunk_capacity) {
-            cudaFree(plan->chunk_coeff);
-            plan->chunk_coeff = nullptr;
-            plan->chunk_capacity = 0;
-            B200_CUDA_CHECK(cudaMalloc(&plan->chunk_coeff, total_chunks * sizeof(float2)));
-            plan->chunk_capacity = total_chunks;
-        }
-        const unsigned cgrid = static_cast<unsigned>(std::min<uint64_t>((total_chunks + 127) / 128, cap));
-        fm_deemph_reduce_kernel<<<cgrid, 128, 0, s>>>(out, plan->chunk_coeff, frames, plan->lanes, frame_len,
-                                                     chunks_per_lane, plan->alpha);
-        B200_LAUNCH_CHECK();
-        fm_deemph_carry_kernel<<<static_cast<unsigned>(std::min<uint64_t>(plan->lanes, cap)), 256, 0, s>>>(
-            plan->chunk_coeff, plan->state, plan->lanes, chunks_per_lane);
-        B200_LAUNCH_CHECK();
-        fm_deemph_apply_kernel<<<cgrid, 128, 0, s>>>(out, plan->chunk_coeff, plan->state, frames, plan->lanes,
-                                                    frame_len, chunks_per_lane, plan->alpha);
-        B200_LAUNCH_CHECK();
+        const uint64_t items = frames * ((frame_len + kFmTile - 1) / kFmTile) * plan->lanes;
+        last_tiles = plan->slots + (items - plan->lanes);
     }
     fm_state_update_kernel<<<static_cast<unsigned>((plan->lanes + 63) / 64), 64, 0, s>>>(
-        reinterpret_cast<const float2*>(x), plan->state, frames, plan->lanes, frame_len);
+        reinterpret_cast<const float2*>(x), plan->state, frames, plan->lanes, frame_len, last_tiles);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -775,7 +884,7 @@ int b200_fm_plan_destroy(b200_fm_plan* plan) {
     }
     DeviceGuard guard(plan->ctx);
     cudaFree(plan->state);
-    cudaFree(plan->chunk_coeff);
+    cudaFree(plan->slots);
     cudaFree(plan->wide_state);
     cudaFree(plan->power);
     cudaFree(plan->scratch);

@@ -168,6 +168,25 @@ def test_fm_narrow_matches_reference(ref, shape, axes, deemphasis):
         assert np.abs(g[m] - w[m]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("shape,axes", [((64, 8192), (1, 0, -1)), ((24, 5, 4096), (2, 0, 1)), ((7, 1001), (1, 0, -1)),
+                                        ((3, 2, 6150), (2, 0, 1))])
+@pytest.mark.parametrize("deemphasis", ["none", "75us"])
+def test_fm_narrow_many_tiles(ref, shape, axes, deemphasis):
+    """The one-pass kernel's decoupled look-back over hundreds of tiles per lane, several lanes, frame lengths that are
+    not a multiple of the tile or of the vector width, state carried over three cycles."""
+    config = {"mode": "narrow", "deemphasis": deemphasis, "sampleRate": 250e3}
+    cycles = [_fm_signal(shape, 50 + i, 250e3) for i in range(3)]
+    cycles[1].reshape(-1)[4099] = np.nan + 0j
+    cycles[2].reshape(-1)[0] = np.inf + 0j
+    want = _ref_fm(cycles, config, axes)
+    got = _our_fm(cycles, config, axes)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        assert np.array_equal(np.isnan(g), np.isnan(w))
+        m = ~np.isnan(w)
+        assert np.abs(g[m] - w[m]).max() <= 1e-5
+
+
 def test_fm_first_sample_is_zero_and_known_tone():
     """fm/module_tests.cc: out[0] of the very first sample is 0; a constant-frequency tone demodulates to a constant."""
     import cyberether_b200 as cb
