@@ -25,6 +25,8 @@
 
 namespace b200 {
 
+constexpr uint32_t kFirConstTapWords = 1024;     // tap tables up to 4 KB travel in the kernel parameters (constant bank)
+
 struct FirParams {
     const float2* x;        // [n_in] stream (frames concatenated)
     const float2* hist;     // [L-1] last inputs of the previous call (zeros initially)
@@ -44,10 +46,13 @@ struct FirParams {
     const float2* rot;      // [heads, frame_out]   exp(-j 2 pi c_h (m R) / M), F64-evaluated
     const float2* corr;     // [heads, frames]      exp(j (phase_h + inc_h frame)), F64-evaluated per call
     uint64_t frames;
+    // CONST_TAPS: the re-ordered tap table itself. Tap reads then go through the constant cache (LDC) instead of the
+    // shared-memory pipe, which the sliding-window loads already keep two thirds busy.
+    float taps_c[kFirConstTapWords];
 };
 
-template <int OB, bool REAL_TAPS>
-__global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
+template <int OB, bool REAL_TAPS, bool CONST_TAPS>
+__global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ FirParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* const planes = reinterpret_cast<float2*>(smem_raw);
     const uint32_t tap_words = p.heads * p.R * p.lp_pad * (REAL_TAPS ? 1 : 2);
@@ -55,8 +60,10 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
     float2* const out_s = reinterpret_cast<float2*>(taps_s + ((tap_words + 1) & ~1u));
 
     const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
-    for (uint32_t i = tid; i < tap_words; i += nthreads) {
-        taps_s[i] = p.taps[i];
+    if constexpr (!CONST_TAPS) {
+        for (uint32_t i = tid; i < tap_words; i += nthreads) {
+            taps_s[i] = p.taps[i];
+        }
     }
 
     const uint64_t tiles = (p.n_out + p.qt - 1) / p.qt;
@@ -162,6 +169,7 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 }
                 const float2* xq = xp;      // xq[-(s+1)] is the element tap (m0 + s + 1) slides in
                 const float* hq = hp;
+                uint32_t hc = (head * p.R + plane) * p.lp_pad * (REAL_TAPS ? 1 : 2);     // index into p.taps_c
                 // taps actually present in this plane: k = kp0 + m R < L  (the padded tail is skipped, not multiplied)
                 const uint32_t kp0 = plane == 0 ? 0 : p.R - plane;
                 const uint32_t lp_plane = p.lp - (kp0 >= p.lp_thr ? 1u : 0u);      // == ceil((L - kp0) / R), no division
@@ -169,14 +177,15 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                 auto tap_step = [&](const int s) {
                     // logical window element i lives in w[(i - s) mod OB]
                     if constexpr (REAL_TAPS) {
-                        const float h = hq[s];
+                        const float h = CONST_TAPS ? p.taps_c[hc + s] : hq[s];
                         const float2 hh = make_float2(h, h);
 #pragma unroll
                         for (int i = 0; i < OB; ++i) {
                             acc[i] = __ffma2_rn(w[(i - s + OB) % OB], hh, acc[i]);
                         }
                     } else {
-                        const float2 h = reinterpret_cast<const float2*>(hq)[s];
+                        const float2 h = CONST_TAPS ? make_float2(p.taps_c[hc + 2 * s], p.taps_c[hc + 2 * s + 1])
+                                                    : reinterpret_cast<const float2*>(hq)[s];
                         const float2 hr = make_float2(h.x, h.x), hi = make_float2(-h.y, h.y);
 #pragma unroll
                         for (int i = 0; i < OB; ++i) {
@@ -195,6 +204,7 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const FirParams p) {
                     }
                     xq -= OB;
                     hq += OB * (REAL_TAPS ? 1 : 2);
+                    hc += OB * (REAL_TAPS ? 1 : 2);
                 }
                 const uint32_t rem = lp_plane - full;       // CTA-uniform
 #pragma unroll
@@ -279,6 +289,8 @@ struct b200_fir_plan {
     b200_ctx* ctx;
     uint32_t L, R, heads;
     bool real_taps;
+    bool const_taps = false;
+    std::vector<float> taps_host;      // re-ordered table (also uploaded to taps_dev)
     int ob;
     uint32_t lp_pad, hpad, threads, qt, plane_pitch;
     size_t smem;
@@ -295,19 +307,23 @@ struct b200_fir_plan {
     uint64_t corr_frames = 0;
 };
 
-template <int OB>
-static int fir_launch(b200_fir_plan* pl, const FirParams& p, unsigned grid, cudaStream_t s) {
-    if (pl->real_taps) {
-        auto k = fir_decim_kernel<OB, true>;
-        B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl->smem)));
-        k<<<grid, pl->threads, pl->smem, s>>>(p);
-    } else {
-        auto k = fir_decim_kernel<OB, false>;
-        B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl->smem)));
-        k<<<grid, pl->threads, pl->smem, s>>>(p);
-    }
+template <int OB, bool REAL_TAPS, bool CONST_TAPS>
+static int fir_launch_variant(b200_fir_plan* pl, const FirParams& p, unsigned grid, cudaStream_t s) {
+    auto k = fir_decim_kernel<OB, REAL_TAPS, CONST_TAPS>;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl->smem)));
+    k<<<grid, pl->threads, pl->smem, s>>>(p);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
+}
+
+template <int OB>
+static int fir_launch(b200_fir_plan* pl, const FirParams& p, unsigned grid, cudaStream_t s) {
+    if (pl->const_taps) {
+        return pl->real_taps ? fir_launch_variant<OB, true, true>(pl, p, grid, s)
+                             : fir_launch_variant<OB, false, true>(pl, p, grid, s);
+    }
+    return pl->real_taps ? fir_launch_variant<OB, true, false>(pl, p, grid, s)
+                         : fir_launch_variant<OB, false, false>(pl, p, grid, s);
 }
 
 extern "C" {
@@ -439,6 +455,8 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
             }
         }
     }
+    pl->taps_host = host;
+    pl->const_taps = host.size() <= kFirConstTapWords && getenv("B200_FIR_SMEM_TAPS") == nullptr;
     void* dev = nullptr;
     if (b200_malloc(ctx, host.size() * sizeof(float), &dev) != B200_SUCCESS) {
         delete pl;
@@ -535,6 +553,9 @@ int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_
     p.hist = plan->hist[plan->cur];
     p.y = reinterpret_cast<float2*>(y);
     p.taps = plan->taps_dev;
+    if (plan->const_taps) {
+        std::copy(plan->taps_host.begin(), plan->taps_host.end(), p.taps_c);
+    }
     p.n_in = n_in;
     p.n_out = n_in / plan->R;
     p.L = plan->L;
