@@ -534,7 +534,8 @@ int b200_copy_strided(b200_ctx* ctx, const void* src, void* dst, int elem_bytes,
                       const uint64_t* src_stride, const uint64_t* dst_stride, b200_stream stream) {
     B200_REQUIRE(ctx && src && dst && shape && src_stride && dst_stride, "b200_copy_strided: null argument");
     B200_REQUIRE(rank >= 1 && rank <= 8, "b200_copy_strided: rank %d unsupported (1..8)", rank);
-    B200_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "b200_copy_strided: element size must be 4 (F32) or 8 (CF32)");
+    B200_REQUIRE(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8,
+                 "b200_copy_strided: element size must be 1, 2, 4 or 8 bytes");
     CopyPlan plan{};
     plan.rank = rank;
     uint64_t total = 1;
@@ -552,6 +553,12 @@ int b200_copy_strided(b200_ctx* ctx, const void* src, void* dst, int elem_bytes,
     if (elem_bytes == 8) {
         copy_strided_kernel<float2><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float2*>(src),
                                                                           static_cast<float2*>(dst), total, plan);
+    } else if (elem_bytes == 1) {
+        copy_strided_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(src),
+                                                                           static_cast<uint8_t*>(dst), total, plan);
+    } else if (elem_bytes == 2) {
+        copy_strided_kernel<uint16_t><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t*>(src),
+                                                                            static_cast<uint16_t*>(dst), total, plan);
     } else {
         copy_strided_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(src),
                                                                          static_cast<float*>(dst), total, plan);

@@ -604,6 +604,7 @@ class Cast(Module):
 
     def create_impl(self):
         self.input = self.inputs["buffer"].tensor
+        self._staging = None
         out_type = self.config["outputType"]
         self.bypass = self.input.dtype == out_type
         if self.bypass:
@@ -629,10 +630,27 @@ class Cast(Module):
         if err:
             return err
         ctx = Context.get(self.input.device)
+        src = self.input.data
+        if not src.is_contiguous():
+            # Taint::DISCONTIGUOUS: sliced / permuted views are gathered into a dense staging tensor first. A complex
+            # integer is one element of twice the scalar size (its trailing (re, im) axis is always dense).
+            pair = 2 if self.input.complex_int else 1
+            if self.input.complex_int and src.stride(-1) != 1:
+                return _error("[MODULE_CAST_B200] Complex-integer input must keep (re, im) adjacent.")
+            if self._staging is None:
+                self._staging = torch.empty(src.shape, dtype=src.dtype, device=src.device)
+            shape = list(self.input.shape)
+            strides = [src.stride(d) // pair for d in range(len(shape))]
+            result = _call("b200_copy_strided", ctx.handle, ctypes.c_void_p(src.data_ptr()),
+                           ctypes.c_void_p(self._staging.data_ptr()), src.element_size() * pair, len(shape),
+                           _u64_array(shape), _u64_array(strides), _u64_array(_contiguous_strides(shape)), stream)
+            if result != Result.SUCCESS:
+                return result
+            src = self._staging
         if self.input.dtype == "F32":
-            return _call("b200_cast_f32_cf32", ctx.handle, self.input.ptr(), self.output.ptr(), self.input.size,
-                         stream)
-        return _call("b200_cast_int", ctx.handle, self.input.ptr(), DTYPE_CODES[self.input.dtype],
+            return _call("b200_cast_f32_cf32", ctx.handle, ctypes.c_void_p(src.data_ptr()), self.output.ptr(),
+                         self.input.size, stream)
+        return _call("b200_cast_int", ctx.handle, ctypes.c_void_p(src.data_ptr()), DTYPE_CODES[self.input.dtype],
                      self.output.ptr(), self.input.size, stream)
 
 

@@ -130,7 +130,7 @@ int b200_range_coefficients(float min, float max, float* scale, float* offset);
 int b200_range_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, float scale,
                    float offset, b200_stream stream);
 
-/* Layout gather / scatter: strided element copy over `shape` (rank <= 8, strides in ELEMENTS, elem_bytes 4 or 8).
+/* Layout gather / scatter: strided element copy over `shape` (rank <= 8, strides in ELEMENTS, elem_bytes 1, 2, 4 or 8).
  * The role of the reference's `fft_layout` kernel, src/domains/dsp/fft/module_impl_native_cuda.cc:31-141: modules that
  * declare Module::Taint::DISCONTIGUOUS bring strided / non-innermost-axis views into the contiguous [batch, n]
  * layout of the fast kernels with it and scatter the result back. */

@@ -26,6 +26,7 @@
 #include "domains/core/multiply/module_impl.hh"
 #include "domains/core/range/module_impl.hh"
 #include "domains/core/reshape/module_impl.hh"
+#include "domains/dsp/agc/module_impl.hh"
 #include "domains/dsp/amplitude/module_impl.hh"
 #include "domains/dsp/fft/module_impl.hh"
 #include "domains/dsp/invert/module_impl.hh"
@@ -116,8 +117,31 @@ struct CastImplB200 : public CastImpl, public NativeCudaRuntimeContext, public S
             return Check(b200_cast_f32_cf32(B200Ctx(), DevicePtr<float>(input), DevicePtr<b200_cf32>(output),
                                             input.size(), stream), "CAST");
         }
-        JST_ERROR("[MODULE_CAST_B200] Only the CF32 bypass and F32 -> CF32 are implemented by this provider.");
-        return Result::ERROR;
+        // integer -> F32 and complex integer -> CF32 (module_impl_native_cpu.cc:163-330); dtype codes of b200dsp.h
+        int code = -1;
+        switch (input.dtype()) {
+            case DataType::I8: code = B200_DTYPE_I8; break;
+            case DataType::U8: code = B200_DTYPE_U8; break;
+            case DataType::I16: code = B200_DTYPE_I16; break;
+            case DataType::U16: code = B200_DTYPE_U16; break;
+            case DataType::I32: code = B200_DTYPE_I32; break;
+            case DataType::U32: code = B200_DTYPE_U32; break;
+            case DataType::CI8: code = B200_DTYPE_CI8; break;
+            case DataType::CU8: code = B200_DTYPE_CU8; break;
+            case DataType::CI16: code = B200_DTYPE_CI16; break;
+            case DataType::CU16: code = B200_DTYPE_CU16; break;
+            case DataType::CI32: code = B200_DTYPE_CI32; break;
+            case DataType::CU32: code = B200_DTYPE_CU32; break;
+            default: break;
+        }
+        const bool complexIn = code >= B200_DTYPE_CI8;
+        if (code < 0 || !input.contiguous() || outputDtype != (complexIn ? DataType::CF32 : DataType::F32)) {
+            JST_ERROR("[MODULE_CAST_B200] Unsupported conversion '{}' -> '{}' (contiguous inputs only).",
+                      input.dtype(), outputDtype);
+            return Result::ERROR;
+        }
+        return Check(b200_cast_int(B200Ctx(), DevicePtr<void>(input), code, DevicePtr<void>(output), input.size(),
+                                   stream), "CAST");
     }
 };
 JST_REGISTER_MODULE(CastImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
@@ -176,6 +200,43 @@ struct FftImplB200 : public FftImpl, public NativeCudaRuntimeContext, public Sch
     b200_fft_plan* plan = nullptr;
 };
 JST_REGISTER_MODULE(FftImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+// ---- agc ---------------------------------------------------------------------------------------------------
+struct AgcImplB200 : public AgcImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
+    Result create() final {
+        JST_CHECK(AgcImpl::create());
+        if (!input.contiguous() || sampleAxis + 1 != input.rank() ||
+            (input.dtype() != DataType::CF32 && input.dtype() != DataType::F32)) {
+            JST_ERROR("[MODULE_AGC_B200] This provider implements contiguous F32 / CF32 inputs with the sample axis innermost.");
+            return Result::ERROR;
+        }
+        return Result::SUCCESS;
+    }
+    Result computeSubmit(const cudaStream_t& stream) override {
+        const U64 samples = input.shape(sampleAxis);
+        uint64_t need = 0;
+        JST_CHECK(Check(b200_agc_scratch_bytes(laneCount, samples, tileSize, &need), "AGC"));
+        if (need > scratchBytes) {                       // tileSize may be reconfigured between cycles
+            b200_free(B200Ctx(), scratch);
+            scratch = nullptr;
+            scratchBytes = 0;
+            JST_CHECK(Check(b200_malloc(B200Ctx(), need, &scratch), "AGC"));
+            scratchBytes = need;
+        }
+        return Check(b200_agc(B200Ctx(), DevicePtr<void>(input), DevicePtr<void>(output),
+                              input.dtype() == DataType::CF32 ? 1 : 0, laneCount, samples, tileSize, reference, epsilon,
+                              minGain, maxGain, maxGainChange, scratch, stream), "AGC");
+    }
+    Result computeDeinitialize() override {
+        b200_free(B200Ctx(), scratch);
+        scratch = nullptr;
+        scratchBytes = 0;
+        return Result::SUCCESS;
+    }
+    void* scratch = nullptr;
+    uint64_t scratchBytes = 0;
+};
+JST_REGISTER_MODULE(AgcImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
 
 // ---- amplitude -------------------------------------------------------------------------------------------
 struct AmplitudeImplB200 : public AmplitudeImpl, public NativeCudaRuntimeContext, public Scheduler::Context {

@@ -91,7 +91,7 @@ static Tensor OutputOf(Flowgraph& fg, const char* block, const char* port) {
 }
 
 static bool RunChain(const DeviceType device, const char* provider, const std::vector<std::complex<float>>& x,
-                     const U64 rows, const U64 n, const bool scale, std::vector<float>& result) {
+                     const U64 rows, const U64 n, const bool scale, const bool agc, std::vector<float>& result) {
     Flowgraph fg;
     if (fg.create({}, nullptr, nullptr, nullptr) != Result::SUCCESS) return false;
     Parser::Map srcConfig;
@@ -109,6 +109,7 @@ static bool RunChain(const DeviceType device, const char* provider, const std::v
     }
     Parser::Map cfg;
     cfg["enableScale"] = std::string(scale ? "true" : "false");
+    cfg["enableAgc"] = std::string(agc ? "true" : "false");
     cfg["rangeMin"] = std::string("-120");
     cfg["rangeMax"] = std::string("0");
     TensorMap inputs;
@@ -162,10 +163,11 @@ int main() {
         }
     }
     int failures = 0;
-    for (const bool scale : {false, true}) {
+    for (const int variant : {0, 1, 3}) {                 // bit 0: enableScale, bit 1: enableAgc
+        const bool scale = variant & 1, agc = variant & 2;
         std::vector<float> cpu, gpu;
-        if (!RunChain(DeviceType::CPU, "generic", x, rows, n, scale, cpu) ||
-            !RunChain(DeviceType::CUDA, "b200", x, rows, n, scale, gpu)) {
+        if (!RunChain(DeviceType::CPU, "generic", x, rows, n, scale, agc, cpu) ||
+            !RunChain(DeviceType::CUDA, "b200", x, rows, n, scale, agc, gpu)) {
             return 2;
         }
         double worst = 0.0;
@@ -176,9 +178,9 @@ int main() {
             worst = std::max(worst, d);
             bad += d > (scale ? 2e-3 : 0.25);   // noise-floor bins: see DESIGN.md §2 (tests/ hold the tight bound)
         }
-        std::printf("spectrum_engine(enableScale=%d) reference-CPU vs b200 provider through the reference Flowgraph: "
-                    "max |diff| = %.3e, out-of-bound = %llu of %zu\n",
-                    scale ? 1 : 0, worst, static_cast<unsigned long long>(bad), cpu.size());
+        std::printf("spectrum_engine(enableScale=%d, enableAgc=%d) reference-CPU vs b200 provider through the reference "
+                    "Flowgraph: max |diff| = %.3e, out-of-bound = %llu of %zu\n",
+                    scale ? 1 : 0, agc ? 1 : 0, worst, static_cast<unsigned long long>(bad), cpu.size());
         failures += bad != 0;
     }
     std::printf(failures ? "SHIM FAIL\n" : "SHIM OK\n");

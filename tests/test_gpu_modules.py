@@ -405,3 +405,53 @@ def test_agc_rejects_bad_config_like_reference():
         ctx.set_config(**bad)
         assert ctx.run() == cb.Result.ERROR
         assert text in cb.last_error()
+
+
+def test_cast_non_contiguous_view_like_reference_test():
+    """core/cast/module_tests.cc:628-668 — a sliced + permuted I8 view (non-zero offset, not contiguous) -> F32."""
+    import torch
+    import cyberether_b200 as cb
+    storage = (np.arange(24, dtype=np.int64) - 12).astype(np.int8).reshape(2, 3, 4)
+    dev = torch.from_numpy(storage).cuda()
+    view = dev[1].permute(1, 0)                       # shape (4, 3), offset 12, strides (1, 4)
+    assert not view.is_contiguous() and view.storage_offset() != 0
+    t = cb.Tensor(view)
+    t.set_attribute("sampleAxis", 1)
+    link = cb.TensorLink()
+    link.produced("test", "buffer", t)
+    module = cb.build_module("cast", "cuda", "native", "b200")
+    assert module.create("cast", {"outputType": "F32"}, {"buffer": link}) == cb.Result.SUCCESS, cb.last_error()
+    runtime = cb.NativeCudaRuntime("test", "cuda")
+    assert runtime.create([module]) == cb.Result.SUCCESS
+    assert runtime.compute([], set(), set()) == cb.Result.SUCCESS, cb.last_error()
+    out = module.outputs["buffer"].tensor.numpy()
+    want = storage[1].T.astype(np.float32) / np.float32(128.0)
+    assert out.shape == (4, 3) and np.array_equal(out, want)
+    runtime.destroy()
+    module.destroy()
+
+
+@pytest.mark.parametrize("name,np_type,is_complex", CAST_CASES + [("F32", np.float32, False)])
+def test_cast_matching_dtype_is_a_bypass(name, np_type, is_complex):
+    """core/cast/module_tests.cc "preserves every matching dtype bypass": the output aliases the input."""
+    import cyberether_b200 as cb
+    x = np.ones((3, 2) if is_complex else (3,), np_type)
+    ctx = cb.TestContext("cast")
+    ctx.set_input("buffer", x, dtype=name if name != "F32" else None, sampleAxis=0)
+    ctx.set_config(outputType=name)
+    assert ctx.start() == cb.Result.SUCCESS, cb.last_error()
+    assert ctx.module.bypass
+    assert ctx.module.outputs["buffer"].tensor.data.data_ptr() == ctx.inputs["buffer"].data.data_ptr()
+    assert ctx.compute() == cb.Result.SUCCESS
+    ctx.stop()
+
+
+@pytest.mark.parametrize("spelling", ["", "cf32", "CF32 ", "NONE", "NOPE"])
+def test_cast_rejects_invalid_output_spelling(spelling):
+    """core/cast/module_tests.cc:670-686."""
+    import cyberether_b200 as cb
+    ctx = cb.TestContext("cast")
+    ctx.set_input("buffer", np.zeros((2, 2), np.int8), dtype="CI8", sampleAxis=0)
+    ctx.set_config(outputType=spelling)
+    assert ctx.run() == cb.Result.ERROR
+    assert "Invalid output type" in cb.last_error()

@@ -46,7 +46,7 @@ for nn in (256, 1024, 2048, 8192, 16384):
     rr = rows * n // nn
     xx = x.reshape(rr, nn); yy = y.reshape(rr, nn)
     pl = ctypes.c_void_p(); _native.check(lib.b200_fft_plan_c2c(ctx.handle, nn, rr, ctypes.byref(pl)))
-    report(f"fft c2c {nn} x {rr} (generic stockham)", timeit(lambda: _native.check(lib.b200_fft_exec(pl, xx.data_ptr(), yy.data_ptr(), 1, sp))), rr * nn, 16)
+    report(f"fft c2c {nn} x {rr} ({'radix-16 kernel' if nn <= 8192 else 'four-step plan'})", timeit(lambda: _native.check(lib.b200_fft_exec(pl, xx.data_ptr(), yy.data_ptr(), 1, sp))), rr * nn, 16)
     report(f"cuFFT {nn} x {rr} [baseline]", timeit(lambda: torch.fft.fft(xx)), rr * nn, 16)
 coeff = cb.amplitude_scaling_coeff(n)
 report("amplitude cf32", timeit(lambda: _native.check(lib.b200_amplitude_cf32(ctx.handle, y.data_ptr(), f.data_ptr(), rows * n, coeff, sp))), rows * n, 12)
@@ -71,18 +71,36 @@ report("fused chain 4096 x 16384", timeit(lambda: _native.check(lib.b200_chain_e
 # ---- FIR (BASELINE config 3: 2^26 CF32 samples as [8192, 8192] frames)
 frames, T = 8192, 8192
 xs = torch.view_as_complex(torch.randn(frames, T, 2, device=dev, generator=g))
-for taps, R in ((129, 8), (127, 1), (129, 1)):
+for taps, R in ((127, 8), (127, 16), (127, 4), (127, 1)):
     centers = (ctypes.c_double * 1)(0.0)
     host = np.zeros((1, taps), np.complex64)
     _native.check(lib.b200_filter_taps_host(8e6, 1e6, centers, 1, taps, host.ctypes.data_as(ctypes.c_void_p)))
     fp = ctypes.c_void_p(); _native.check(lib.b200_fir_plan_create(ctx.handle, host.ctypes.data_as(ctypes.c_void_p), taps, 1, R, ctypes.byref(fp)))
     yo = torch.empty(frames, 1, T // R, dtype=torch.complex64, device=dev)
     report(f"fir {taps} taps decimate {R}, 2^26 samples", timeit(lambda: _native.check(lib.b200_fir_exec(fp, xs.data_ptr(), yo.data_ptr(), frames, T, sp)), iters=10, warm=3), frames * T, 8 + 8 / R)
-# ---- FM narrow (2^24 samples)
-fr, fl = 2048, 8192
-xf = torch.view_as_complex(torch.randn(fr, fl, 2, device=dev, generator=g)); of = torch.empty(fr, fl, device=dev)
-for de in (0, 75):
-    mp_ = ctypes.c_void_p(); _native.check(lib.b200_fm_plan_create(ctx.handle, 1, 250e3, 0, de, ctypes.byref(mp_)))
-    report(f"fm narrow deemphasis={de}us, 2^24 samples", timeit(lambda: _native.check(lib.b200_fm_exec(mp_, xf.data_ptr(), of.data_ptr(), fr, fl, sp)), iters=10, warm=3), fr * fl, 12)
+# ---- integer ingest (cast module; fused into the chain)
+from cyberether_b200.jetstream import DTYPE_CODES
+for name, tdt, nb in (("CI8", torch.int8, 2), ("CI16", torch.int16, 4)):
+    xi = torch.randint(-100, 100, (rows, n, 2), device=dev, dtype=torch.int32).to(tdt)
+    report(f"cast {name} -> CF32", timeit(lambda: _native.check(lib.b200_cast_int(ctx.handle, xi.data_ptr(), DTYPE_CODES[name], y.data_ptr(), rows * n, sp))), rows * n, nb + 8)
+    report(f"fused chain 4096 x 16384, {name} input", timeit(lambda: _native.check(lib.b200_chain_exec_typed(cp, xi.data_ptr(), DTYPE_CODES[name], f.data_ptr(), rows, coeff, 1, sc, off, sp))), rows * n, nb + 4)
+# ---- agc (CF32, one tile per 4096-sample row, as spectrum_engine uses it; and 1024-sample tiles)
+need = ctypes.c_uint64()
+for tile in (4096, 1024):
+    _native.check(lib.b200_agc_scratch_bytes(rows, n, tile, ctypes.byref(need)))
+    scratch = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    report(f"agc cf32 [16384,4096], tile {tile}", timeit(lambda: _native.check(lib.b200_agc(ctx.handle, x.data_ptr(), y.data_ptr(), 1, rows, n, tile, 1.0, 1e-12, 0.01, 100.0, 4.0, scratch.data_ptr(), sp))), rows * n, 16)
+# ---- FM (2^26 samples as [8192, 1, 8192])
+fr, fl = 8192, 8192
+xf = xs.reshape(fr, 1, fl); of = torch.empty(fr, 1, fl, device=dev)
+for wide, de, label in ((0, 0, "narrow"), (0, 75, "narrow, de-emphasis 75us"), (1, 0, "wide (stereo)"), (1, 75, "wide (stereo), de-emphasis 75us")):
+    mp_ = ctypes.c_void_p(); _native.check(lib.b200_fm_plan_create(ctx.handle, 1, ctypes.c_float(250e3), wide, de, ctypes.byref(mp_)))
+    if wide:
+        frw = 64        # the stereo decoder is a chain of scans with serial parts: 2^19 samples; out = [.., 2] (L, R)
+        ofw = torch.empty(frw, 1, fl, 2, device=dev)
+        report(f"fm {label}, 2^19 samples", timeit(lambda: _native.check(lib.b200_fm_exec(mp_, xf.data_ptr(), ofw.data_ptr(), frw, fl, sp)), iters=5, warm=2), frw * fl, 16)
+    else:
+        report(f"fm {label}, 2^26 samples", timeit(lambda: _native.check(lib.b200_fm_exec(mp_, xf.data_ptr(), of.data_ptr(), fr, fl, sp)), iters=10, warm=3), fr * fl, 12)
+    lib.b200_fm_plan_destroy(mp_)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(dict(peak_gbs=PEAK, results=results), open("gpurun_out/bench_modules.json", "w"), indent=1)
