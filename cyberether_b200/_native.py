@@ -59,6 +59,8 @@ SIGNATURES = {
     "b200_chain_plan_create": (c_int, [c_vp, c_u64, c_u64, c_vp, P(c_vp)]),
     "b200_chain_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_vp]),
     "b200_chain_exec_typed": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_vp]),
+    "b200_chain_exec_agc": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_f64, c_f64, c_f64, c_f64,
+                                    c_vp]),
     "b200_chain_exec_host": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_u64]),
     "b200_chain_plan_destroy": (c_int, [c_vp]),
     "b200_chain_plan_variant": (ctypes.c_char_p, [c_vp]),

@@ -121,12 +121,14 @@ class SpectrumEngine(Block):
             return r
 
         # enableAgc puts an `agc` module (one RMS tile per spectrum) between fft and amplitude
-        # (block_impl.cc:186-200): that graph runs module by module; the fused kernel covers the default chain.
-        if self.config["fused"] and axis == tensor.rank - 1 and not self.config["enableAgc"]:
+        # (block_impl.cc:186-200). The fused kernel has that stage for 4096-point spectra; other lengths run the
+        # graph module by module.
+        if self.config["fused"] and axis == tensor.rank - 1 and (not self.config["enableAgc"] or size == 4096):
             r = self.module_create("spectral_chain", "spectral_chain",
                                    {"enableScale": bool(self.config["enableScale"]),
                                     "rangeMin": float(self.config["rangeMin"]),
-                                    "rangeMax": float(self.config["rangeMax"])},
+                                    "rangeMax": float(self.config["rangeMax"]),
+                                    "enableAgc": bool(self.config["enableAgc"])},
                                    {"buffer": complex_input, "window": self.module_get_output("invert", "signal")})
             if r != Result.SUCCESS:
                 return r

@@ -175,11 +175,11 @@ static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_
     return B200_SUCCESS;
 }
 
-// Fused complex-integer ingest (cast -> window -> fft -> amplitude -> range in one kernel), real window only.
-template <int MODE, int ITYPE>
+// Fused complex-integer ingest (cast -> window -> fft -> [agc] -> amplitude -> range in one kernel), real window only.
+template <int MODE, int ITYPE, bool AGC = false>
 static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
-    auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE>;
-    constexpr int smem = fft4096_int_smem_bytes(ITYPE);
+    auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE, AGC>;
+    constexpr int smem = ITYPE == IN_CF32 ? fft4096_smem_bytes(2) : fft4096_int_smem_bytes(ITYPE);
     static bool configured[64] = {};
     if (!configured[ctx->device & 63]) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -899,6 +899,48 @@ int b200_chain_exec_typed(b200_chain_plan* plan, const void* x, int in_dtype, fl
         B200_INT_DISPATCH(MODE_AMP)
     }
 #undef B200_INT_DISPATCH
+}
+
+int b200_chain_exec_agc(b200_chain_plan* plan, const void* x, int in_dtype, float* out, uint64_t batch, float amp_coeff,
+                        int enable_range, float scale, float offset, double agc_reference, double agc_epsilon,
+                        double agc_min_gain, double agc_max_gain, b200_stream stream) {
+    B200_REQUIRE(plan, "b200_chain_exec_agc: null plan");
+    B200_REQUIRE(std::isfinite(agc_reference) && agc_reference > 0.0, "[MODULE_AGC] Reference must be finite and positive.");
+    B200_REQUIRE(std::isfinite(agc_epsilon) && agc_epsilon > 0.0, "[MODULE_AGC] Epsilon must be finite and positive.");
+    B200_REQUIRE(std::isfinite(agc_min_gain) && agc_min_gain > 0.0, "[MODULE_AGC] Minimum gain must be finite and positive.");
+    B200_REQUIRE(std::isfinite(agc_max_gain) && agc_max_gain >= agc_min_gain,
+                 "[MODULE_AGC] Maximum gain must be finite and no less than minimum gain.");
+    B200_REQUIRE(!plan->composite && plan->n == kFft4096N && plan->win_re != nullptr,
+                 "b200_chain_exec_agc: the fused AGC path needs n = 4096 and a real window (run the modules otherwise)");
+    B200_REQUIRE(in_dtype == B200_DTYPE_CF32 || (in_dtype >= B200_DTYPE_CI8 && in_dtype <= B200_DTYPE_CU16),
+                 "b200_chain_exec_agc: input dtype code %d is not CF32 / CI8 / CU8 / CI16 / CU16", in_dtype);
+    if (batch == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(x && out, "b200_chain_exec_agc: null buffer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "b200_chain_exec_agc: input must be 16-byte aligned");
+    DeviceGuard guard(plan->ctx);
+    const cudaStream_t s = as_stream(stream);
+    FftParams p{};
+    chain_params(plan, static_cast<const float2*>(x), out, batch, amp_coeff, enable_range, scale, offset, &p);
+    p.agc_reference = agc_reference;
+    p.agc_epsilon = agc_epsilon;
+    p.agc_min = agc_min_gain;
+    p.agc_max = agc_max_gain;
+#define B200_AGC_DISPATCH(MODE)                                                                  \
+    switch (in_dtype) {                                                                          \
+        case B200_DTYPE_CF32: return launch_4096_int<MODE, IN_CF32, true>(plan->ctx, p, s);      \
+        case B200_DTYPE_CI8: return launch_4096_int<MODE, IN_CI8, true>(plan->ctx, p, s);        \
+        case B200_DTYPE_CU8: return launch_4096_int<MODE, IN_CU8, true>(plan->ctx, p, s);        \
+        case B200_DTYPE_CI16: return launch_4096_int<MODE, IN_CI16, true>(plan->ctx, p, s);      \
+        default: return launch_4096_int<MODE, IN_CU16, true>(plan->ctx, p, s);                   \
+    }
+    if (enable_range) {
+        B200_AGC_DISPATCH(MODE_AMP_RANGE)
+    } else {
+        B200_AGC_DISPATCH(MODE_AMP)
+    }
+#undef B200_AGC_DISPATCH
 }
 
 int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* out_host, uint64_t batch,

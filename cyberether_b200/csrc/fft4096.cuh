@@ -144,8 +144,12 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const TwiddleSet
     }
 }
 
-template <int MODE, int WIN, int CTAS, int ITYPE = IN_CF32>
+template <int MODE, int WIN, int CTAS, int ITYPE = IN_CF32, bool AGC = false>
 __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const FftParams p) {
+    // AGC: the mean power of the spectrum equals the power of the windowed row (Parseval: sum |X_k|^2 = N sum |x_n w_n|^2),
+    // which pass 1 has in registers: per-warp partial sums go to shared memory (double-buffered by row parity; barriers
+    // (A) and (C) of the row order them before the epilogue reads them).
+    __shared__ float agc_partial[2][kFft4096Threads / 32];
     constexpr bool kInt = ITYPE != IN_CF32;
     constexpr int kFft4096Stages = kInt ? kFft4096IntLandStages : fft4096_stages(CTAS);   // TMA ring depth
     constexpr int kLandBytes = kFft4096N * fft4096_in_bytes(ITYPE);                        // bytes of one input row
@@ -245,6 +249,20 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
             }
             v[a] = x;
         }
+        if constexpr (AGC) {
+            float power = 0.0f;
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+                power = fmaf(v[a].x, v[a].x, fmaf(v[a].y, v[a].y, power));
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                power += __shfl_xor_sync(0xffffffffu, power, off);
+            }
+            if ((t & 31) == 0) {
+                agc_partial[i & 1][t >> 5] = power;
+            }
+        }
         dft16(v);
         apply_twiddles(v, tw1);
 #pragma unroll
@@ -309,9 +327,20 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
             }
         } else {
             float* const out = reinterpret_cast<float*>(out_ptr);
+            float gain = 1.0f;
+            if constexpr (AGC) {
+                float mean_power = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kFft4096Threads / 32; ++w) {
+                    mean_power += agc_partial[i & 1][w];
+                }
+                // AgcImplNativeCpu: clamp(reference / sqrt(meanPower + epsilon), minGain, maxGain), F64
+                const double g = p.agc_reference / sqrt(static_cast<double>(mean_power) + p.agc_epsilon);
+                gain = static_cast<float>(g < p.agc_min ? p.agc_min : (p.agc_max < g ? p.agc_max : g));
+            }
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {
-                const float2 r = spectral_epilogue2<MODE>(v[dft16_pos(k)], v[dft16_pos(k + 1)], p);
+                const float2 r = spectral_epilogue2<MODE, AGC>(v[dft16_pos(k)], v[dft16_pos(k + 1)], p, gain);
                 stg_stream_f1(out + 256 * k, r.x);
                 stg_stream_f1(out + 256 * (k + 1), r.y);
             }

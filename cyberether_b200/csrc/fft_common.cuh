@@ -24,6 +24,9 @@ struct FftParams {
     // range with min == max (scale 0) is the constant 0.5: the host passes k1 = k0 = 0, zero_value = 0.5.
     float amp_scale, amp_coeff, k1, k0;
     float zero_value;       // MODE_AMP_RANGE result where |X|^2 == 0 (0, or 0.5 for a flat range)
+    // Fused AGC (spectrum_engine enableAgc: one RMS tile per spectrum, src/domains/dsp/spectrum_engine/block_impl.cc:186-200):
+    // every row is scaled by clamp(reference / sqrt(mean |X|^2 + epsilon), min, max) before the amplitude.
+    double agc_reference, agc_epsilon, agc_min, agc_max;
 };
 
 // ---- butterflies (forward sign) ------------------------------------------------------------
@@ -119,12 +122,15 @@ __device__ __forceinline__ float rcp_approx(const float x) {
 //   (include/jetstream/backend/devices/cpu/helpers.hh:61-74).
 //   MODE_AMP       : Y * amp_scale + amp_coeff, -inf where |X|^2 == 0
 //   MODE_AMP_RANGE : 1 / (1 + 2^(Y k1 + k0)) == 0.5 + 0.5 tanh(4 ((dB s + o) - 0.5)), 0 where |X|^2 == 0
-template <int MODE>
-__device__ __forceinline__ float2 spectral_epilogue2(const float2 X0, const float2 X1, const FftParams& p) {
+template <int MODE, bool AGC = false>
+__device__ __forceinline__ float2 spectral_epilogue2(const float2 X0, const float2 X1, const FftParams& p,
+                                                     const float gain = 1.0f) {
     const float p0 = fmaf(X0.x, X0.x, X0.y * X0.y);
     const float p1 = fmaf(X1.x, X1.x, X1.y * X1.y);
-    const int b0 = __float_as_int(sqrt_approx(p0));
-    const int b1 = __float_as_int(sqrt_approx(p1));
+    // AGC: |g X| = g |X| (the reference scales the components in F64 and rounds them to F32 first; the difference is
+    // one rounding of the magnitude)
+    const int b0 = __float_as_int(AGC ? sqrt_approx(p0) * gain : sqrt_approx(p0));
+    const int b1 = __float_as_int(AGC ? sqrt_approx(p1) * gain : sqrt_approx(p1));
     const float2 f = make_float2(__int_as_float((b0 & 0x007fffff) | 0x3f000000),
                                  __int_as_float((b1 & 0x007fffff) | 0x3f000000));
     // (float)(biased exponent field); the frexp bias (-126) is folded into the last polynomial constant.

@@ -1138,7 +1138,10 @@ class SpectralChain(Module):
     `buffer` may also be a complex-integer tensor (CI8 ... CU32): the `cast` module an SDR flowgraph puts in front of
     spectrum_engine is then folded into the kernel's load (b200_chain_exec_typed)."""
     TYPE = "spectral_chain"
-    DEFAULTS = {"enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0}
+    DEFAULTS = {"enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0,
+                # enableAgc: spectrum_engine's optional agc stage (one RMS tile per spectrum) inside the same kernel;
+                # the four numbers are the agc module's config (include/jetstream/domains/dsp/agc/module.hh:9-14)
+                "enableAgc": False, "agcReference": 1.0, "agcEpsilon": 1e-12, "agcMinGain": 0.01, "agcMaxGain": 100.0}
 
     def __init__(self):
         super().__init__()
@@ -1156,6 +1159,9 @@ class SpectralChain(Module):
             return _error("[MODULE_SPECTRAL_CHAIN_B200] Input signal axis metadata is invalid.")
         if axes.sample != t.rank - 1:
             return _error("[MODULE_SPECTRAL_CHAIN_B200] The sample axis must be the innermost axis.")
+        if self.config["enableAgc"] and t.shape[-1] != 4096:
+            return _error("[MODULE_SPECTRAL_CHAIN_B200] The fused AGC stage exists for 4096-point spectra only; "
+                          "wire fft -> agc -> amplitude for other lengths.")
         return Result.SUCCESS
 
     def define(self):
@@ -1180,7 +1186,8 @@ class SpectralChain(Module):
         return Result.SUCCESS
 
     def reconfigure_impl(self, candidate):
-        if bool(candidate["enableScale"]) != bool(self.config["enableScale"]):
+        if bool(candidate["enableScale"]) != bool(self.config["enableScale"]) or \
+                bool(candidate["enableAgc"]) != bool(self.config["enableAgc"]):
             return Result.RECREATE
         self.scale, self.offset = range_coefficients(float(candidate["rangeMin"]), float(candidate["rangeMax"]))
         return Result.SUCCESS
@@ -1205,9 +1212,15 @@ class SpectralChain(Module):
             result = self._create_plan()
             if result != Result.SUCCESS:
                 return result
+        c = self.config
+        if c["enableAgc"]:
+            return _call("b200_chain_exec_agc", self._plan_handle, self.input.ptr(), DTYPE_CODES[self.input.dtype],
+                         self.output.ptr(), self._batch, ctypes.c_float(self.amp_coeff), 1 if c["enableScale"] else 0,
+                         ctypes.c_float(self.scale), ctypes.c_float(self.offset), float(c["agcReference"]),
+                         float(c["agcEpsilon"]), float(c["agcMinGain"]), float(c["agcMaxGain"]), stream)
         return _call("b200_chain_exec_typed", self._plan_handle, self.input.ptr(), DTYPE_CODES[self.input.dtype],
                      self.output.ptr(), self._batch, ctypes.c_float(self.amp_coeff),
-                     1 if self.config["enableScale"] else 0, ctypes.c_float(self.scale), ctypes.c_float(self.offset),
+                     1 if c["enableScale"] else 0, ctypes.c_float(self.scale), ctypes.c_float(self.offset),
                      stream)
 
     def compute_deinitialize(self):

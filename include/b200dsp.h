@@ -194,6 +194,16 @@ int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint6
 int b200_chain_exec_typed(b200_chain_plan* plan, const void* x, int in_dtype, float* out, uint64_t batch,
                           float amp_coeff, int enable_range, float scale, float offset, b200_stream stream);
 
+/* spectrum_engine with enableAgc (src/domains/dsp/spectrum_engine/block_impl.cc:186-200: an `agc` module with one
+ * RMS tile per spectrum between fft and amplitude), still ONE kernel: the row's mean power comes from the windowed
+ * input by Parseval, gain = clamp(reference / sqrt(mean |X|^2 + epsilon), min_gain, max_gain) in F64 as
+ * AgcImplNativeCpu (module_impl_native_cpu.cc:112-124; the rate limit does not apply to a single tile).
+ * n = 4096 with a real window only (ERROR otherwise: wire fft -> agc -> amplitude -> range instead);
+ * in_dtype CF32 or CI8/CU8/CI16/CU16. */
+int b200_chain_exec_agc(b200_chain_plan* plan, const void* x, int in_dtype, float* out, uint64_t batch, float amp_coeff,
+                        int enable_range, float scale, float offset, double agc_reference, double agc_epsilon,
+                        double agc_min_gain, double agc_max_gain, b200_stream stream);
+
 /* Same computation for HOST-resident tensors (what the reference's TestContext hands a CUDA module:
  * host memory mapped onto the device, src/testing.cc:136, src/memory/buffer_cuda.cc:188). x_host and
  * out_host should be pinned (b200_host_alloc) for full PCIe rate. The batch is cut into chunks of

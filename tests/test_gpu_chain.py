@@ -99,13 +99,13 @@ def test_chain_flat_range(ref):
     assert np.array_equal(got, want) and np.all(got == 0.5)
 
 
-def _chain_module(buffer, window, dtype=None, enable_scale=True):
+def _chain_module(buffer, window, dtype=None, enable_scale=True, agc=False):
     import cyberether_b200 as cb
     ctx = cb.TestContext("spectral_chain")
     shape_rank = buffer.ndim - (1 if dtype and dtype.startswith("C") else 0)
     ctx.set_input("buffer", buffer, dtype=dtype, sampleAxis=shape_rank - 1, batchAxis=0 if shape_rank > 1 else None)
     ctx.set_input("window", window, sampleAxis=0)
-    ctx.set_config(enableScale=enable_scale, rangeMin=-120.0, rangeMax=0.0)
+    ctx.set_config(enableScale=enable_scale, rangeMin=-120.0, rangeMax=0.0, enableAgc=agc)
     assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
     return ctx.output("buffer")
 
@@ -155,28 +155,45 @@ def test_chain_integer_ingest_equals_cast_then_chain(ref, name, np_type, n, rows
 
 @pytest.mark.parametrize("enable_scale", [True, False])
 @pytest.mark.parametrize("fused", [True, False])
-def test_spectrum_engine_with_agc(ref, enable_scale, fused):
+@pytest.mark.parametrize("n,level", [(4096, 0.03), (4096, 30.0), (4096, 1e-4), (1024, 0.03)])
+def test_spectrum_engine_with_agc(ref, enable_scale, fused, n, level):
     """enableAgc: an `agc` module (one RMS tile per spectrum) between fft and amplitude (block_impl.cc:186-200).
-    The provider runs that graph module by module (the fused flag has no effect); same allowance as the chain plus
-    the dB image of the gain's last-bit differences."""
+    4096-point spectra run it inside the fused kernel (row power by Parseval), other lengths and fused=False module by
+    module. Levels: gain inside its clamp range, clamped at minGain (loud) and at maxGain (quiet)."""
     import cyberether_b200 as cb
     from cyberether_b200.blocks import SpectrumEngine
     from cyberether_b200.synthetic import spectral_rows
-    x = spectral_rows(7, 48) * np.float32(0.03)
+    x = spectral_rows(7, 48, n=n) * np.float32(level)
     block = SpectrumEngine(enableAgc=True, enableScale=enable_scale, fused=fused)
     inp = cb.Tensor.from_numpy(x, sampleAxis=1, batchAxis=0)
     assert block.create("spec", {"buffer": inp}) == cb.Result.SUCCESS, cb.last_error()
     for _ in range(2):
         assert block.compute() == cb.Result.SUCCESS, cb.last_error()
     got = block.output("buffer").numpy()
-    assert "agc" in block.modules and "spectral_chain" not in block.modules
+    assert ("spectral_chain" in block.modules) == (fused and n == 4096)
+    assert ("agc" in block.modules) != ("spectral_chain" in block.modules)
     block.destroy()
     want = ref.run_block("spectrum_engine", {"buffer": x}, {"enableAgc": True, "enableScale": enable_scale,
                                                            "rangeMin": -120.0, "rangeMax": 0.0}, "buffer")
-    spec = true_spectrum(x, _window(ref, 4096))
-    # the AGC gain is common to a row: it moves every bin by the same dB, the allowance is relative to the row peak
-    # exactly as without AGC
+    # the gain is common to a row: the allowance is computed on the spectrum the amplitude stage sees (g X)
+    w = _window(ref, n)
+    spec = true_spectrum(x, w)
+    mean_power = (np.abs(spec) ** 2).mean(axis=1, keepdims=True)
+    gain = np.clip(1.0 / np.sqrt(mean_power + 1e-12), 0.01, 100.0)
     if enable_scale:
-        assert_db_close(got, want, spec, scale=_range_slope(-120.0, 0.0), floor=3e-7)
+        assert_db_close(got, want, spec * gain, scale=_range_slope(-120.0, 0.0), floor=3e-7)
     else:
-        assert_db_close(got, want, spec)
+        assert_db_close(got, want, spec * gain)
+
+
+@pytest.mark.parametrize("name,np_type", [("CI8", np.int8), ("CU16", np.uint16)])
+def test_chain_integer_ingest_with_agc(ref, name, np_type):
+    """Integer ingest and the AGC stage in the same kernel: bit-identical to cast -> CF32 chain with AGC."""
+    from oracle import port
+    info = np.iinfo(np_type)
+    x = np.random.default_rng(11).integers(info.min // 4, info.max // 4, size=(33, 4096, 2), dtype=np_type)
+    w = _window(ref, 4096)
+    got = _chain_module(x, w, dtype=name, agc=True)
+    two_step = _chain_module(port.cast(x, complex_pairs=True), w, agc=True)
+    assert np.array_equal(got, two_step)
+    assert not np.array_equal(got, _chain_module(x, w, dtype=name, agc=False))

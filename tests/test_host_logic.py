@@ -104,11 +104,14 @@ def test_spectrum_engine_wiring_fused_and_unfused():
     sched = unfused.scheduler
     static = {m.name.split(":")[1] for m in sched.order if sched.is_static(m)}
     assert static == {"window", "invert", "reshape_window"}     # settle after cycle 1 (block_tests.cc:103-122)
-    with_agc = SpectrumEngine(enableAgc=True)                   # agc sits between fft and amplitude (block_impl.cc:186-200)
+    with_agc = SpectrumEngine(enableAgc=True, fused=False)      # agc sits between fft and amplitude (block_impl.cc:186-200)
     assert with_agc.create("s", {"buffer": x}) == cb.Result.SUCCESS
     names = list(with_agc.modules)
     assert names.index("fft") < names.index("agc") < names.index("amplitude") and "spectral_chain" not in names
     assert with_agc.modules["agc"].config["tileSize"] == 4096   # one RMS tile per spectrum
+    fused_agc = SpectrumEngine(enableAgc=True)                  # 4096-point spectra: the stage lives inside the fused kernel
+    assert fused_agc.create("s", {"buffer": x}) == cb.Result.SUCCESS
+    assert "agc" not in fused_agc.modules and fused_agc.modules["spectral_chain"].config["enableAgc"] is True
     assert SpectrumEngine().create("s", {"buffer": tensor((4, 8))}) == cb.Result.ERROR
 
 
