@@ -45,10 +45,11 @@ enum : int { IN_CF32 = 0, IN_CI8 = 1, IN_CU8 = 2, IN_CI16 = 3, IN_CU16 = 4 };
 __host__ __device__ constexpr int fft4096_in_bytes(const int itype) {
     return itype == IN_CF32 ? 8 : (itype <= IN_CU8 ? 2 : 4);
 }
-// Integer rows land in their own 3-deep ring (8 or 16 KiB per row) and the exchanges alternate between two buffers.
-constexpr int kFft4096IntLandStages = 3;
+// Integer rows land in their own ring (3 x 8 KiB for 8-bit, 2 x 16 KiB for 16-bit samples: 2 CTAs/SM need <= 113 KB
+// each) and the exchanges alternate between two buffers.
+__host__ __device__ constexpr int fft4096_int_land_stages(const int itype) { return fft4096_in_bytes(itype) == 2 ? 3 : 2; }
 __host__ __device__ constexpr int fft4096_int_smem_bytes(const int itype) {
-    return 2 * kFft4096StageBytes + kFft4096IntLandStages * kFft4096N * fft4096_in_bytes(itype) + 64;
+    return 2 * kFft4096StageBytes + fft4096_int_land_stages(itype) * kFft4096N * fft4096_in_bytes(itype) + 64;
 }
 template <int ITYPE>
 __device__ __forceinline__ float2 load_int_sample(const unsigned char* land, const uint32_t index) {
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
     // (A) and (C) of the row order them before the epilogue reads them).
     __shared__ float agc_partial[2][kFft4096Threads / 32];
     constexpr bool kInt = ITYPE != IN_CF32;
-    constexpr int kFft4096Stages = kInt ? kFft4096IntLandStages : fft4096_stages(CTAS);   // TMA ring depth
+    constexpr int kFft4096Stages = kInt ? fft4096_int_land_stages(ITYPE) : fft4096_stages(CTAS);   // TMA ring depth
     constexpr int kLandBytes = kFft4096N * fft4096_in_bytes(ITYPE);                        // bytes of one input row
     constexpr int kLandPitch = kInt ? kLandBytes : kFft4096StageBytes;
     constexpr int kLandBase = kInt ? 2 * kFft4096StageBytes : 0;
