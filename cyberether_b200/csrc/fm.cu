@@ -314,8 +314,11 @@ __device__ __forceinline__ float biquad_step(const float x, const Biquad& c, flo
 // JST_PI is a double literal, so the comparison and the subtraction happen in F64 and round back to F32.
 __device__ __forceinline__ float advance_phase(float phase, const float inc) {
     phase = __fadd_rn(phase, inc);
-    const double two_pi = 2.0 * 3.14159265358979323846;
-    if (static_cast<double>(phase) >= two_pi) {
+    // (double)phase >= 2 pi  <=>  phase >= the smallest F32 not below the F64 value of 2 pi (0x40C90FDB, 6.2831855f): the
+    // comparison stays in F32 and the F64 subtraction only runs on a wrap (every ~13 samples at 19 kHz / 250 kS/s) —
+    // the serial chain is what bounds the wideband decoder.
+    if (phase >= 6.2831854820251465f) {
+        const double two_pi = 2.0 * 3.14159265358979323846;
         phase = static_cast<float>(static_cast<double>(phase) - two_pi);
     }
     return phase;
@@ -327,8 +330,42 @@ __global__ void fm_wide_phase_kernel(float* __restrict__ phase, float* __restric
     if (blockIdx.x != 0 || threadIdx.x != 0) {
         return;
     }
+    // One thread, in-order issue: a branch per sample costs ~50 cycles per step. Four additions are chained without
+    // branches; when none of them reaches 2 pi (about two blocks out of three at 19 kHz / 250 kS/s) they are exactly the
+    // sequential values. Otherwise the values before the first wrap are kept, the wrap is evaluated as the reference
+    // does (F64 subtraction, rounded to F32) and the next block starts right after it.
+    const float kWrap = 6.2831854820251465f;       // smallest F32 >= the F64 value of 2 pi (see advance_phase)
+    const double two_pi = 2.0 * 3.14159265358979323846;
     float ph = *phase_state;
-    for (uint64_t n = 0; n < lane_len; ++n) {
+    uint64_t n = 0;
+    while (n + 4 <= lane_len) {
+        const float a1 = __fadd_rn(ph, inc), a2 = __fadd_rn(a1, inc), a3 = __fadd_rn(a2, inc), a4 = __fadd_rn(a3, inc);
+        if (!(a1 >= kWrap || a2 >= kWrap || a3 >= kWrap || a4 >= kWrap)) {
+            phase[n] = ph;
+            phase[n + 1] = a1;
+            phase[n + 2] = a2;
+            phase[n + 3] = a3;
+            ph = a4;
+            n += 4;
+            continue;
+        }
+        // first wrapped sum a_j (j = 1..4): samples n .. n+j-1 hold ph, a1 .. a_{j-1}; the next sample is wrap(a_j)
+        const int j = a1 >= kWrap ? 1 : (a2 >= kWrap ? 2 : (a3 >= kWrap ? 3 : 4));
+        phase[n] = ph;
+        if (j > 1) {
+            phase[n + 1] = a1;
+        }
+        if (j > 2) {
+            phase[n + 2] = a2;
+        }
+        if (j > 3) {
+            phase[n + 3] = a3;
+        }
+        const float over = j == 1 ? a1 : (j == 2 ? a2 : (j == 3 ? a3 : a4));
+        ph = static_cast<float>(static_cast<double>(over) - two_pi);
+        n += j;
+    }
+    for (; n < lane_len; ++n) {
         phase[n] = ph;
         ph = advance_phase(ph, inc);
     }
@@ -363,60 +400,105 @@ __global__ void scan_reduce_kernel(const System sys, float* __restrict__ chunk_r
 }
 
 // carry-in of chunk c overwrites its response slot; `power` is A^kWideChunk (row-major S x S, F32).
+// One warp per lane. The recurrence over chunks is sequential, but its inputs are not: the warp loads the responses
+// of 32 chunks at once (the next batch is requested before the current one is consumed), every lane then steps the
+// same recurrence — chunk k's response arrives by shuffle from lane k — and lane k keeps the carry-in of its own chunk.
+// (A single thread walking the chunks paid a full global-memory latency per chunk: 0.6-0.9 ms per 2048 chunks.)
 template <class System>
-__global__ void scan_carry_kernel(const System sys, float* __restrict__ chunk_resp, const int* __restrict__ chunk_count,
-                                  const float* __restrict__ power, float* __restrict__ lane_state,
-                                  const uint64_t lanes, const uint64_t chunks_per_lane) {
-    const uint64_t lane = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (lane >= lanes) {
-        return;
-    }
-    float st[System::S];
+__global__ void __launch_bounds__(32) scan_carry_kernel(const System sys, float* __restrict__ chunk_resp,
+                                                        const int* __restrict__ chunk_count,
+                                                        const float* __restrict__ power, float* __restrict__ lane_state,
+                                                        const uint64_t lanes, const uint64_t chunks_per_lane) {
+    constexpr int S = System::S;
+    const uint32_t lid = threadIdx.x;
+    float a[S * S];
 #pragma unroll
-    for (int i = 0; i < System::S; ++i) {
-        st[i] = lane_state[lane * System::S + i];
+    for (int i = 0; i < S * S; ++i) {
+        a[i] = power[i];
     }
-    for (uint64_t c = 0; c < chunks_per_lane; ++c) {
-        float* const slot = chunk_resp + (lane * chunks_per_lane + c) * System::S;
-        float resp[System::S], next[System::S];
+    for (uint64_t lane = blockIdx.x; lane < lanes; lane += gridDim.x) {
+        float* const base = chunk_resp + lane * chunks_per_lane * S;
+        const int* const counts = chunk_count + lane * chunks_per_lane;
+        float st[S];
 #pragma unroll
-        for (int i = 0; i < System::S; ++i) {
-            resp[i] = slot[i];
-            slot[i] = st[i];
+        for (int i = 0; i < S; ++i) {
+            st[i] = lane_state[lane * S + i];
         }
-        const int count = chunk_count[lane * chunks_per_lane + c];
-        if (count == kWideChunk) {
+        float resp_next[S];
+        int count_next = 0;
+        auto fetch = [&](const uint64_t c0) {
+            const uint64_t c = c0 + lid;
 #pragma unroll
-            for (int i = 0; i < System::S; ++i) {
-                float acc = resp[i];
+            for (int i = 0; i < S; ++i) {
+                resp_next[i] = c < chunks_per_lane ? base[c * S + i] : 0.0f;
+            }
+            count_next = c < chunks_per_lane ? counts[c] : 0;
+        };
+        fetch(0);
+        for (uint64_t c0 = 0; c0 < chunks_per_lane; c0 += 32) {
+            float resp_mine[S], carry_mine[S];
 #pragma unroll
-                for (int j = 0; j < System::S; ++j) {
-                    acc = fmaf(power[i * System::S + j], st[j], acc);
+            for (int i = 0; i < S; ++i) {
+                resp_mine[i] = resp_next[i];
+                carry_mine[i] = 0.0f;
+            }
+            const int count_mine = count_next;
+            if (c0 + 32 < chunks_per_lane) {
+                fetch(c0 + 32);                                  // in flight while this batch is stepped
+            }
+            const int batch = static_cast<int>(chunks_per_lane - c0 < 32 ? chunks_per_lane - c0 : 32);
+            for (int k = 0; k < batch; ++k) {
+                float resp[S], next[S];
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    resp[i] = __shfl_sync(0xffffffffu, resp_mine[i], k);
+                    if (static_cast<int>(lid) == k) {
+                        carry_mine[i] = st[i];                   // carry-in of chunk c0 + k
+                    }
                 }
-                next[i] = acc;
-            }
-        } else {
-            // homogeneous response by stepping `count` zero-input samples, then add the zero-state response
+                const int count = __shfl_sync(0xffffffffu, count_mine, k);
+                if (count == kWideChunk) {
 #pragma unroll
-            for (int i = 0; i < System::S; ++i) {
-                next[i] = st[i];
-            }
-            for (int k = 0; k < count; ++k) {
-                sys.step_homogeneous(next);
-            }
+                    for (int i = 0; i < S; ++i) {
+                        float acc = resp[i];
 #pragma unroll
-            for (int i = 0; i < System::S; ++i) {
-                next[i] += resp[i];
+                        for (int j = 0; j < S; ++j) {
+                            acc = fmaf(a[i * S + j], st[j], acc);
+                        }
+                        next[i] = acc;
+                    }
+                } else {
+                    // homogeneous response by stepping `count` zero-input samples, then add the zero-state response
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        next[i] = st[i];
+                    }
+                    for (int q = 0; q < count; ++q) {
+                        sys.step_homogeneous(next);
+                    }
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        next[i] += resp[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    st[i] = next[i];
+                }
+            }
+            if (static_cast<int>(lid) < batch) {
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    base[(c0 + lid) * S + i] = carry_mine[i];
+                }
             }
         }
+        if (lid == 0) {
 #pragma unroll
-        for (int i = 0; i < System::S; ++i) {
-            st[i] = next[i];
+            for (int i = 0; i < S; ++i) {
+                lane_state[lane * S + i] = st[i];
+            }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < System::S; ++i) {
-        lane_state[lane * System::S + i] = st[i];
     }
 }
 
@@ -628,8 +710,8 @@ static int run_scan(const System& sys, float* chunk_resp, int* chunk_count, cons
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((total + 63) / 64, cap));
     scan_reduce_kernel<System><<<grid, 64, 0, s>>>(sys, chunk_resp, chunk_count, lanes, lane_len, chunks_per_lane);
     B200_LAUNCH_CHECK();
-    scan_carry_kernel<System><<<static_cast<unsigned>((lanes + 31) / 32), 32, 0, s>>>(sys, chunk_resp, chunk_count, power,
-                                                                                      lane_state, lanes, chunks_per_lane);
+    scan_carry_kernel<System><<<static_cast<unsigned>(std::min<uint64_t>(lanes, cap)), 32, 0, s>>>(
+        sys, chunk_resp, chunk_count, power, lane_state, lanes, chunks_per_lane);
     B200_LAUNCH_CHECK();
     scan_replay_kernel<System><<<grid, 64, 0, s>>>(sys, chunk_resp, lanes, lane_len, chunks_per_lane);
     B200_LAUNCH_CHECK();

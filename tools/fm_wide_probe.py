@@ -1,0 +1,18 @@
+"""Ad-hoc: one wideband (stereo) FM exec of 2^19 samples, for launch lists (ncu --metrics gpu__time_duration.sum)."""
+import ctypes, sys, os
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cyberether_b200 import _native
+from cyberether_b200.jetstream import Context
+lib = _native.load(); dev = torch.device("cuda:0"); ctx = Context.get(dev)
+sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+frames, lanes, fl = 64, 1, 8192
+x = torch.view_as_complex(torch.randn(frames, lanes, fl, 2, device=dev))
+out = torch.empty(frames, lanes, fl, 2, dtype=torch.float32, device=dev)
+plan = ctypes.c_void_p()
+_native.check(lib.b200_fm_plan_create(ctx.handle, lanes, ctypes.c_float(250e3), 1, 75, ctypes.byref(plan)))
+for _ in range(2): _native.check(lib.b200_fm_exec(plan, x.data_ptr(), out.data_ptr(), frames, fl, sp))
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); _native.check(lib.b200_fm_exec(plan, x.data_ptr(), out.data_ptr(), frames, fl, sp)); e1.record(); torch.cuda.synchronize()
+print(f"fm wide 2^19 samples: {e0.elapsed_time(e1):.3f} ms")
