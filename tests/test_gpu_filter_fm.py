@@ -245,3 +245,35 @@ def test_filter_multi_head_channelizer_with_resampling(ref):
         assert g.shape == w.shape == (6, 3, 256)
         err = np.abs(g - w).max() / np.abs(w).max()
         assert err <= 1e-5, (c, err)
+
+
+@pytest.mark.parametrize("deemphasis", ["none", "75us"])
+def test_fm_narrow_large_split_property(deemphasis):
+    """Size-independent property at 2^23 samples (4096 tiles per lane in the look-back scan): demodulating a stream in
+    one call equals demodulating it in two calls with the state carried in the plan — bit for bit without de-emphasis,
+    to 2e-6 with it (the carry reaches a tile through differently grouped map compositions)."""
+    import torch
+    import cyberether_b200 as cb
+    from cyberether_b200.blocks import FmBlock
+    frames, fl = 1024, 8192
+    x = _fm_signal((frames, fl), 77, 250e3)
+
+    def run(parts):
+        inp = cb.Tensor.from_numpy(parts[0], sampleAxis=1, batchAxis=0)
+        block = FmBlock(mode="narrow", deemphasis=deemphasis, sampleRate=250e3)
+        assert block.create("fm", {"signal": inp}) == cb.Result.SUCCESS, cb.last_error()
+        outs = []
+        for part in parts:
+            inp.data.copy_(torch.from_numpy(part))
+            assert block.compute() == cb.Result.SUCCESS, cb.last_error()
+            outs.append(block.output("signal").numpy().copy())
+        block.destroy()
+        return np.concatenate(outs, axis=0)
+
+    whole = run([x])
+    halves = run([x[:512], x[512:]])
+    assert whole.shape == halves.shape == (frames, fl)
+    if deemphasis == "none":
+        assert np.array_equal(whole, halves)
+    else:
+        assert np.abs(whole - halves).max() <= 2e-6
