@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200_fir_plan_set_translation": (c_int, [c_vp, c_u64, P(ctypes.c_int64)]),
     "b200_fir_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_vp]),
     "b200_fir_reset": (c_int, [c_vp, c_vp]),
+    "b200_fir_set_history": (c_int, [c_vp, c_vp, c_u64, c_u64, c_vp]),
     "b200_fir_plan_destroy": (c_int, [c_vp]),
     "b200_fm_plan_create": (c_int, [c_vp, c_u64, c_f32, c_int, c_int, P(c_vp)]),
     "b200_fm_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_vp]),

@@ -537,6 +537,39 @@ int b200_fir_reset(b200_fir_plan* plan, b200_stream stream) {
     return B200_SUCCESS;
 }
 
+// Time sharding across GPUs: a rank that continues a stream another rank (or an earlier call elsewhere)
+// started loads the last taps-1 input samples before its slab — the halo — as the plan's history. `count` < taps-1 pads
+// the front with zeros (a stream shorter than the filter); a translating plan also takes the number of FRAMES that
+// precede the slab so that its phase_correction phasor continues where the previous shard's would be.
+int b200_fir_set_history(b200_fir_plan* plan, const b200_cf32* tail_dev, uint64_t count, uint64_t frames_before,
+                         b200_stream stream) {
+    B200_REQUIRE(plan, "b200_fir_set_history: null plan");
+    const uint64_t hist_len = plan->L - 1;
+    B200_REQUIRE(count <= hist_len, "b200_fir_set_history: %llu samples given, the history holds taps - 1 = %llu",
+                 static_cast<unsigned long long>(count), static_cast<unsigned long long>(hist_len));
+    B200_REQUIRE(count == 0 || tail_dev, "b200_fir_set_history: null buffer");
+    DeviceGuard guard(plan->ctx);
+    const cudaStream_t s = as_stream(stream);
+    float2* const hist = plan->hist[plan->cur];
+    if (hist_len > count) {
+        B200_CUDA_CHECK(cudaMemsetAsync(hist, 0, (hist_len - count) * sizeof(float2), s));
+    }
+    if (count > 0) {
+        B200_CUDA_CHECK(cudaMemcpyAsync(hist + (hist_len - count), tail_dev, count * sizeof(float2),
+                                        cudaMemcpyDeviceToDevice, s));
+    }
+    if (plan->translate) {
+        // phase after `frames_before` frames: remainder(inc * frames, 2 pi) per head, as fir_phase_advance_kernel from 0
+        B200_CUDA_CHECK(cudaMemsetAsync(plan->phases_dev, 0, plan->heads * sizeof(double), s));
+        if (frames_before > 0) {
+            fir_phase_advance_kernel<<<static_cast<unsigned>((plan->heads + 63) / 64), 64, 0, s>>>(
+                plan->phases_dev, plan->increments_dev, plan->heads, frames_before);
+            B200_LAUNCH_CHECK();
+        }
+    }
+    return B200_SUCCESS;
+}
+
 int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_t frames, uint64_t frame_len,
                   b200_stream stream) {
     B200_REQUIRE(plan, "b200_fir_exec: null plan");

@@ -57,6 +57,40 @@ def scatter_rows(whole, total_rows: int, row_shape, dtype, device, src: int = 0)
     return recv[: end - begin]
 
 
+def exchange_fir_halo(local_frames: torch.Tensor, taps: int, previous_cycle_tail=None) -> torch.Tensor:
+    """Time sharding of the `filter` path: the frames of a stream are cut into contiguous slabs, one per
+    rank (`shard_bounds` over the frame axis), and a FIR with `taps` coefficients needs the `taps - 1` input samples
+    that precede its slab. One neighbour exchange per cycle: rank r sends the tail of its slab to rank r + 1; rank 0
+    takes `previous_cycle_tail` (the tail the LAST rank kept from the previous cycle, None / zeros at stream start).
+    Returns the halo [taps - 1] for this rank (zero-padded in front when the neighbour's slab is shorter than that) and
+    leaves this rank's own tail in `.own_tail` of the result for the caller to keep (only the last rank's matters)."""
+    need = taps - 1
+    flat = local_frames.reshape(-1)
+    own_tail = flat[-need:].clone() if need > 0 else flat[:0].clone()
+    if own_tail.numel() < need:
+        own_tail = torch.cat([torch.zeros(need - own_tail.numel(), dtype=flat.dtype, device=flat.device), own_tail])
+    if previous_cycle_tail is None:
+        previous_cycle_tail = torch.zeros(need, dtype=flat.dtype, device=flat.device)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or need == 0:
+        halo = previous_cycle_tail.clone()
+        halo.own_tail = own_tail
+        return halo
+    world, rank = dist.get_world_size(), dist.get_rank()
+    halo = torch.empty(need, dtype=flat.dtype, device=flat.device)
+    real_view = lambda t: torch.view_as_real(t) if t.is_complex() else t      # gloo has no complex send/recv
+    ops = []
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, real_view(own_tail), rank + 1))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, real_view(halo), rank - 1))
+    for req in dist.batch_isend_irecv(ops) if ops else []:
+        req.wait()
+    if rank == 0:
+        halo.copy_(previous_cycle_tail)
+    halo.own_tail = own_tail
+    return halo
+
+
 def gather_rows(local: torch.Tensor, total_rows: int, dst: int = 0):
     """Graph-boundary gather: concatenates every rank's [rows_r, n] slab on `dst` in rank order (None elsewhere).
     Slabs may differ by one row, so they are padded to the largest slab for the collective."""

@@ -242,6 +242,12 @@ int b200_fir_plan_set_translation(b200_fir_plan* plan, uint64_t frame_len, const
 int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_t frames, uint64_t frame_len,
                   b200_stream stream);
 int b200_fir_reset(b200_fir_plan* plan, b200_stream stream);
+/* Time sharding (one stream cut into slabs for several GPUs): load the halo — the last `count` <= taps-1
+ * input samples that precede this plan's slab (device pointer) — as the carried state that overlap_add's tail is in the
+ * reference (src/domains/dsp/overlap_add/module_impl_native_cpu.cc:155-198). `frames_before` = frames of the stream
+ * before the slab (only used by translating plans: phase_correction continues from there). */
+int b200_fir_set_history(b200_fir_plan* plan, const b200_cf32* tail_dev, uint64_t count, uint64_t frames_before,
+                         b200_stream stream);
 int b200_fir_plan_destroy(b200_fir_plan* plan);
 
 /* ---- fm ---------------------------------------------------------------------------------------- */

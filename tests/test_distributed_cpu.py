@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cyberether_b200.sharding import all_shards, gather_rows, max_over_ranks, scatter_rows, shard_bounds
+from cyberether_b200.sharding import (all_shards, exchange_fir_halo, gather_rows, max_over_ranks, scatter_rows,
+                                      shard_bounds)
 
 
 def test_shards_partition_the_batch_exactly():
@@ -41,6 +42,15 @@ def _worker(rank, world, port, total_rows, n, results):
         whole_in = torch.arange(total_rows, dtype=torch.float32)[:, None].repeat(1, n) if rank == 0 else None
         mine = scatter_rows(whole_in, total_rows, (n,), torch.float32, "cpu", src=0)
         assert mine.shape == (end - begin, n) and torch.equal(mine, local)
+        # FIR time sharding: each rank must receive the taps-1 samples that precede its slab of the stream
+        stream = torch.arange(total_rows * n, dtype=torch.float32).reshape(total_rows, n)
+        stream = torch.complex(stream, -stream)
+        taps = 7
+        halo = exchange_fir_halo(stream[begin:end], taps)
+        flat = stream.reshape(-1)
+        expect = flat[begin * n - (taps - 1):begin * n] if begin > 0 else torch.zeros(taps - 1, dtype=flat.dtype)
+        assert torch.equal(halo, expect)
+        assert torch.equal(halo.own_tail, flat[end * n - (taps - 1):end * n])
         slowest = max_over_ranks(10.0 + rank)                 # rank 1 is slower: everyone must see 11.0
         whole = gather_rows(local, total_rows, dst=0)
         dist.barrier()

@@ -277,3 +277,45 @@ def test_fm_narrow_large_split_property(deemphasis):
         assert np.array_equal(whole, halves)
     else:
         assert np.abs(whole - halves).max() <= 2e-6
+
+
+@pytest.mark.parametrize("config", [dict(sampleRate=8e6, bandwidth=1e6, taps=129),
+                                    dict(sampleRate=1e6, bandwidth=100e3, taps=101, heads=3,
+                                         center=(-250e3, 0.0, 125e3))])
+def test_filter_time_sharding_with_halo(config):
+    """Time sharding: the second half of a stream filtered by a FRESH plan whose history is the halo —
+    the last taps-1 samples of the first half, what `sharding.exchange_fir_halo` delivers to the next rank — equals the
+    second half of the whole-stream result bit for bit, including translating multi-head plans (frames_before)."""
+    import torch
+    import cyberether_b200 as cb
+    from cyberether_b200.blocks import Filter
+    from cyberether_b200.sharding import exchange_fir_halo
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((8, 2000) if "heads" in config else (64, 8192), 21)
+    split = x.shape[0] // 2
+
+    def block_for(part):
+        inp = cb.Tensor.from_numpy(part, sampleAxis=1, batchAxis=0)
+        block = Filter(**config)
+        assert block.create("f", {"signal": inp}) == cb.Result.SUCCESS, cb.last_error()
+        return block, inp
+
+    whole_block, _ = block_for(x)
+    assert whole_block.compute() == cb.Result.SUCCESS, cb.last_error()
+    whole = whole_block.output("buffer").numpy().copy()
+    whole_block.destroy()
+
+    first_block, first_in = block_for(x[:split])
+    assert first_block.compute() == cb.Result.SUCCESS
+    first = first_block.output("buffer").numpy().copy()
+    halo = exchange_fir_halo(first_in.data, config["taps"]).own_tail       # what rank 0 would send to rank 1
+    first_block.destroy()
+
+    second_block, _ = block_for(x[split:])
+    assert second_block.modules["fir"].set_history(halo, frames_before=split) == cb.Result.SUCCESS, cb.last_error()
+    assert second_block.compute() == cb.Result.SUCCESS
+    second = second_block.output("buffer").numpy().copy()
+    second_block.destroy()
+
+    assert np.array_equal(first, whole[:split])
+    assert np.array_equal(second, whole[split:])
