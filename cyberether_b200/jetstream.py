@@ -1395,21 +1395,26 @@ class FirFilter(Module):
             result = self._create_plan()
             if result != Result.SUCCESS:
                 return result
+        pending = getattr(self, "_pending_history", None)
+        if pending is not None:
+            tail, frames_before = pending
+            self._pending_history = None
+            result = _call("b200_fir_set_history", self._plan_handle, ctypes.c_void_p(tail.data_ptr()), tail.numel(),
+                           frames_before, stream)
+            if result != Result.SUCCESS:
+                return result
         return _call("b200_fir_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), self._frames,
                      self._frame_len, stream)
 
-    def set_history(self, tail: torch.Tensor, frames_before: int = 0, stream=None) -> Result:
-        """Time sharding (sharding.exchange_fir_halo): load the last `taps - 1` input samples that precede this
-        module's slab of the stream (CF32 device tensor, possibly shorter) as the carried filter state."""
-        if self._plan_handle is None:
-            result = self._create_plan()
-            if result != Result.SUCCESS:
-                return result
+    def set_history(self, tail: torch.Tensor, frames_before: int = 0) -> Result:
+        """Time sharding (sharding.exchange_fir_halo): the last `taps - 1` input samples that precede this module's
+        slab of the stream (CF32 device tensor, possibly shorter) become the carried filter state of the NEXT compute
+        cycle (the plan itself is created on the first cycle, once the static taps have settled)."""
         tail = tail.contiguous()
         if tail.dtype != torch.complex64 or tail.device.type != "cuda":
             return _error("[MODULE_FIR_FILTER_B200] The halo must be a CF32 CUDA tensor.")
-        return _call("b200_fir_set_history", self._plan_handle, ctypes.c_void_p(tail.data_ptr()), tail.numel(),
-                     int(frames_before), stream if stream is not None else current_stream_ptr(tail.device))
+        self._pending_history = (tail, int(frames_before))
+        return Result.SUCCESS
 
     def compute_deinitialize(self):
         if self._plan_handle is not None:

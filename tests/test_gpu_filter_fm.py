@@ -318,4 +318,9 @@ def test_filter_time_sharding_with_halo(config):
     second_block.destroy()
 
     assert np.array_equal(first, whole[:split])
-    assert np.array_equal(second, whole[split:])
+    if "heads" in config:
+        # the frame phasor of a translating head is exp(j (phase0 + inc frame)): starting from remainder(inc * split)
+        # instead of 0 changes the F64 angle by a multiple of 2 pi up to rounding
+        assert np.abs(second - whole[split:]).max() <= 1e-6 * np.abs(whole).max()
+    else:
+        assert np.array_equal(second, whole[split:])
