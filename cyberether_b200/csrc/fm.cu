@@ -372,6 +372,69 @@ __global__ void fm_wide_phase_kernel(float* __restrict__ phase, float* __restric
     *phase_state = ph;
 }
 
+// Same recurrence, stores batched: lane 0 of the warp fills a shared-memory batch with the block-of-four logic, the warp
+// flushes it with coalesced stores; values that overshoot a batch move to the front of the next one. Bit-identical to
+// fm_wide_phase_kernel (tools/microbench3.cu compares them); selected with B200_FM_NCO_BATCHED=1 until it is measured
+// faster on hardware.
+__global__ void __launch_bounds__(32) fm_wide_phase_batched_kernel(float* __restrict__ phase, float* __restrict__ phase_state,
+                                                                  const uint64_t lane_len, const float inc) {
+    constexpr uint32_t kBatch = 2048;
+    __shared__ float buf[kBatch + 4];
+    const float kWrap = 6.2831854820251465f;
+    const double two_pi = 2.0 * 3.14159265358979323846;
+    float ph = *phase_state;
+    uint32_t carried = 0;                                  // values already in buf[0 .. carried) for this batch
+    for (uint64_t base = 0; base < lane_len; base += kBatch) {
+        const uint32_t want = lane_len - base < kBatch ? static_cast<uint32_t>(lane_len - base) : kBatch;
+        uint32_t n = carried;
+        if (threadIdx.x == 0) {
+            while (n < want) {
+                const float a1 = __fadd_rn(ph, inc), a2 = __fadd_rn(a1, inc), a3 = __fadd_rn(a2, inc),
+                            a4 = __fadd_rn(a3, inc);
+                buf[n] = ph;
+                if (!(a1 >= kWrap || a2 >= kWrap || a3 >= kWrap || a4 >= kWrap)) {
+                    buf[n + 1] = a1;
+                    buf[n + 2] = a2;
+                    buf[n + 3] = a3;
+                    ph = a4;
+                    n += 4;
+                    continue;
+                }
+                const int j = a1 >= kWrap ? 1 : (a2 >= kWrap ? 2 : (a3 >= kWrap ? 3 : 4));
+                if (j > 1) {
+                    buf[n + 1] = a1;
+                }
+                if (j > 2) {
+                    buf[n + 2] = a2;
+                }
+                if (j > 3) {
+                    buf[n + 3] = a3;
+                }
+                const float over = j == 1 ? a1 : (j == 2 ? a2 : (j == 3 ? a3 : a4));
+                ph = static_cast<float>(static_cast<double>(over) - two_pi);
+                n += j;
+            }
+        }
+        n = __shfl_sync(0xffffffffu, n, 0);
+        __syncwarp();
+        for (uint32_t i = threadIdx.x; i < want; i += 32) {
+            phase[base + i] = buf[i];
+        }
+        __syncwarp();
+        carried = n - want;                                // 0..3 values belong to the next batch
+        if (threadIdx.x == 0) {
+            if (base + want >= lane_len) {
+                *phase_state = carried ? buf[want] : ph;   // the state is the value of sample `lane_len`
+            } else {
+                for (uint32_t i = 0; i < carried; ++i) {
+                    buf[i] = buf[want + i];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Generic blocked scan over S-state systems. System must provide:
 //   static constexpr int S;  __device__ void step(float* state, uint64_t n, lane, bool replay)  — one sample, reference op order;
 //   returns false when the sample is skipped (non-finite discriminator).
@@ -921,7 +984,12 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
             B200_SUCCESS) {
             return B200_ERROR;
         }
-        fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
+        static const bool nco_batched = getenv("B200_FM_NCO_BATCHED") != nullptr;
+        if (nco_batched) {
+            fm_wide_phase_batched_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
+        } else {
+            fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
+        }
         B200_LAUNCH_CHECK();
         const unsigned ucap = static_cast<unsigned>(cap);
         PilotSystem pilot{sum, phase, diff, at, plan->wc.pilot_alpha};
