@@ -66,6 +66,43 @@ def main():
                 s.compute()
                 out[f"fm_{de}_in{i}"] = c
                 out[f"fm_{de}_out{i}"] = s.output("fm", "signal")
+    # cast: every integer / complex-integer conversion (extremes included)
+    rng = np.random.default_rng(123)
+    for name, np_type, is_complex in (("I8", np.int8, False), ("U8", np.uint8, False), ("I16", np.int16, False),
+                                      ("U16", np.uint16, False), ("I32", np.int32, False), ("U32", np.uint32, False),
+                                      ("CI8", np.int8, True), ("CU8", np.uint8, True), ("CI16", np.int16, True),
+                                      ("CU16", np.uint16, True), ("CI32", np.int32, True), ("CU32", np.uint32, True)):
+        info = np.iinfo(np_type)
+        v = rng.integers(info.min, info.max, size=(2, 24, 2) if is_complex else (2, 24), endpoint=True, dtype=np_type)
+        v.flat[0], v.flat[-1] = info.min, info.max
+        out[f"cast_{name}_in"] = v
+        out[f"cast_{name}_out"] = ref.run_block("cast", {"buffer": v}, {"outputType": "CF32" if is_complex else "F32"},
+                                                "buffer", dtypes={"buffer": name})
+    # agc block (its parameters are F32 in the block): level jump, two tile sizes, F32 and CF32
+    env = np.exp(rng.uniform(-5, 5, size=(3, 1))) * (1 + 7 * (np.arange(700) > 350))
+    for kind in ("f32", "cf32"):
+        a = rng.standard_normal((3, 700)) * env
+        a = a.astype(np.float32) if kind == "f32" else (a + 1j * rng.standard_normal((3, 700)) * env).astype(np.complex64)
+        out[f"agc_{kind}_in"] = a
+        for tile in (128, 700):
+            out[f"agc_{kind}_tile{tile}"] = ref.run_block("agc", {"signal": a}, {"tileSize": tile}, "signal")
+    # SDR-style flowgraph: cast(CI8 / CI16) -> spectrum_engine, with and without AGC
+    for name, np_type in (("CI8", np.int8), ("CI16", np.int16)):
+        info = np.iinfo(np_type)
+        t = np.arange(4096)
+        sig = 0.4 * np.exp(2j * np.pi * 300.25 * t / 4096)[None, :] + 0.02 * (rng.standard_normal((3, 4096)) +
+                                                                            1j * rng.standard_normal((3, 4096)))
+        q = np.clip(np.rint(np.stack([sig.real, sig.imag], axis=-1) * info.max), info.min, info.max).astype(np_type)
+        out[f"sdr_{name}_in"] = q
+        for agc in (False, True):
+            with ref.Session() as s:
+                s.add_source("src", q, sample_axis=1, batch_axis=0, dtype=name)
+                s.add_block("c", "cast", {"outputType": "CF32"}, {"buffer": "src.signal"})
+                s.add_block("se", "spectrum_engine", {"enableScale": True, "enableAgc": agc, "rangeMin": -120.0,
+                                                      "rangeMax": 0.0}, {"buffer": "c.buffer"})
+                s.compute()
+                s.compute()
+                out[f"sdr_{name}_agc{int(agc)}"] = s.output("se", "buffer")
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(HERE, "reference_vectors.npz")), "bytes")
 

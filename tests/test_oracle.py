@@ -155,3 +155,29 @@ def test_port_agc_matches_reference(ref, complex_input, shape, tile):
                    max_gain_change=f32(4.0))
     assert got.dtype == want.dtype
     assert np.array_equal(got, want)
+
+
+# ---- golden vectors of the widened path (cast, agc, SDR-style integer chain) ---------------------------------------
+
+@pytest.mark.parametrize("name", ["I8", "U8", "I16", "U16", "I32", "U32", "CI8", "CU8", "CI16", "CU16", "CI32", "CU32"])
+def test_golden_cast_bit_exact(gold, name):
+    got = port.cast(gold[f"cast_{name}_in"], complex_pairs=name.startswith("C"))
+    assert np.array_equal(got, gold[f"cast_{name}_out"])
+
+
+@pytest.mark.parametrize("kind", ["f32", "cf32"])
+@pytest.mark.parametrize("tile", [128, 700])
+def test_golden_agc_bit_exact(gold, kind, tile):
+    f32 = lambda v: float(np.float32(v))           # the agc BLOCK widens F32 parameters (block.hh:9-14)
+    got = port.agc(gold[f"agc_{kind}_in"], tile_size=tile, reference=f32(1.0), epsilon=f32(1e-12), min_gain=f32(0.01),
+                   max_gain=f32(100.0), max_gain_change=f32(4.0))
+    assert np.array_equal(got, gold[f"agc_{kind}_tile{tile}"])
+
+
+@pytest.mark.parametrize("name", ["CI8", "CI16"])
+def test_golden_sdr_chain(gold, name):
+    """cast -> spectrum_engine on integer captures: the port (cast restatement + chain restatement) against the
+    reference flowgraph's output, same bound as the CF32 chain golden."""
+    x = port.cast(gold[f"sdr_{name}_in"], complex_pairs=True)
+    got = port.spectrum_engine(x, enable_scale=True)
+    assert np.abs(got - gold[f"sdr_{name}_agc0"]).max() <= 2e-3
