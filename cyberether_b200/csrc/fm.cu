@@ -372,66 +372,47 @@ __global__ void fm_wide_phase_kernel(float* __restrict__ phase, float* __restric
     *phase_state = ph;
 }
 
-// Same recurrence, stores batched: lane 0 of the warp fills a shared-memory batch with the block-of-four logic, the warp
-// flushes it with coalesced stores; values that overshoot a batch move to the front of the next one. Bit-identical to
-// fm_wide_phase_kernel (tools/microbench3.cu compares them); selected with B200_FM_NCO_BATCHED=1 until it is measured
-// faster on hardware.
+// Same recurrence without branches and without F64: for every F32 a in [2 pi, 2 pi + 1) the reference's wrap
+// (float)((double)a - 2 pi) equals fadd(fsub(a, T), C) with T = 6.2831855f (the F32 just above 2 pi) and
+// C = (float)(T - 2 pi) = 1.7484555e-07f — a - T is exact and the rounding of the sum never sits near a tie (checked
+// exhaustively over all 2^21 values). A step is then FADD, two FADDs and a select (16 cycles of dependent latency
+// instead of ~39 with branches). Lane 0 fills a shared-memory batch, the warp flushes it with coalesced stores.
+// Selected with B200_FM_NCO_BATCHED=1 until it has been timed on hardware (tools/microbench3.cu).
+__device__ __forceinline__ float nco_step(const float ph, const float inc) {
+    const float a = __fadd_rn(ph, inc);
+    const float wrapped = __fadd_rn(__fsub_rn(a, 6.2831854820251465f), 1.7484555314695172e-07f);
+    return a >= 6.2831854820251465f ? wrapped : a;
+}
+
 __global__ void __launch_bounds__(32) fm_wide_phase_batched_kernel(float* __restrict__ phase, float* __restrict__ phase_state,
                                                                   const uint64_t lane_len, const float inc) {
     constexpr uint32_t kBatch = 2048;
-    __shared__ float buf[kBatch + 4];
-    const float kWrap = 6.2831854820251465f;
-    const double two_pi = 2.0 * 3.14159265358979323846;
+    __shared__ float buf[kBatch];
     float ph = *phase_state;
-    uint32_t carried = 0;                                  // values already in buf[0 .. carried) for this batch
     for (uint64_t base = 0; base < lane_len; base += kBatch) {
         const uint32_t want = lane_len - base < kBatch ? static_cast<uint32_t>(lane_len - base) : kBatch;
-        uint32_t n = carried;
         if (threadIdx.x == 0) {
-            while (n < want) {
-                const float a1 = __fadd_rn(ph, inc), a2 = __fadd_rn(a1, inc), a3 = __fadd_rn(a2, inc),
-                            a4 = __fadd_rn(a3, inc);
-                buf[n] = ph;
-                if (!(a1 >= kWrap || a2 >= kWrap || a3 >= kWrap || a4 >= kWrap)) {
-                    buf[n + 1] = a1;
-                    buf[n + 2] = a2;
-                    buf[n + 3] = a3;
-                    ph = a4;
-                    n += 4;
-                    continue;
+            uint32_t i = 0;
+            for (; i + 8 <= want; i += 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    buf[i + k] = ph;
+                    ph = nco_step(ph, inc);
                 }
-                const int j = a1 >= kWrap ? 1 : (a2 >= kWrap ? 2 : (a3 >= kWrap ? 3 : 4));
-                if (j > 1) {
-                    buf[n + 1] = a1;
-                }
-                if (j > 2) {
-                    buf[n + 2] = a2;
-                }
-                if (j > 3) {
-                    buf[n + 3] = a3;
-                }
-                const float over = j == 1 ? a1 : (j == 2 ? a2 : (j == 3 ? a3 : a4));
-                ph = static_cast<float>(static_cast<double>(over) - two_pi);
-                n += j;
+            }
+            for (; i < want; ++i) {
+                buf[i] = ph;
+                ph = nco_step(ph, inc);
             }
         }
-        n = __shfl_sync(0xffffffffu, n, 0);
         __syncwarp();
         for (uint32_t i = threadIdx.x; i < want; i += 32) {
             phase[base + i] = buf[i];
         }
         __syncwarp();
-        carried = n - want;                                // 0..3 values belong to the next batch
-        if (threadIdx.x == 0) {
-            if (base + want >= lane_len) {
-                *phase_state = carried ? buf[want] : ph;   // the state is the value of sample `lane_len`
-            } else {
-                for (uint32_t i = 0; i < carried; ++i) {
-                    buf[i] = buf[want + i];
-                }
-            }
-        }
-        __syncwarp();
+    }
+    if (threadIdx.x == 0) {
+        *phase_state = ph;
     }
 }
 

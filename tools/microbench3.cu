@@ -68,39 +68,32 @@ __global__ void phase_kernel(float* __restrict__ phase, float* __restrict__ stat
     *state = ph + (VARIANT == 1 ? sink * 1e-30f : 0.f);
 }
 
-// Variant 3: exact batched version (candidate for the product): the serial thread fills a shared-memory batch, the warp
-// flushes it with coalesced stores; values that overshoot a batch move to the front of the next one.
+// Variant 3 (the product's B200_FM_NCO_BATCHED kernel): branch-free F32-only step — (float)((double)a - 2 pi) equals
+// fadd(fsub(a, T), C) for every F32 a in [2 pi, 2 pi + 1) — lane 0 fills a shared-memory batch, the warp flushes it.
+__device__ __forceinline__ float nco_step(const float ph, const float inc) {
+    const float a = __fadd_rn(ph, inc);
+    const float wrapped = __fadd_rn(__fsub_rn(a, 6.2831854820251465f), 1.7484555314695172e-07f);
+    return a >= 6.2831854820251465f ? wrapped : a;
+}
 __global__ void phase_kernel_batched(float* __restrict__ phase, float* __restrict__ state, const uint32_t len, const float inc) {
     constexpr uint32_t kBatch = 2048;
-    __shared__ float buf[kBatch + 4];
+    __shared__ float buf[kBatch];
     float ph = *state;
-    uint32_t carried = 0;                                  // values already in buf[0 .. carried) for this batch
     for (uint32_t base = 0; base < len; base += kBatch) {
         const uint32_t want = len - base < kBatch ? len - base : kBatch;
-        uint32_t n = carried;
         if (threadIdx.x == 0) {
-            while (n < want) {
-                float a[4]; int j;
-                block4(ph, inc, a, j);
-                buf[n] = a[0];
-                if (j > 1) buf[n + 1] = a[1];
-                if (j > 2) buf[n + 2] = a[2];
-                if (j > 3) buf[n + 3] = a[3];
-                n += j;
+            uint32_t i = 0;
+            for (; i + 8 <= want; i += 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { buf[i + k] = ph; ph = nco_step(ph, inc); }
             }
+            for (; i < want; ++i) { buf[i] = ph; ph = nco_step(ph, inc); }
         }
-        n = __shfl_sync(0xffffffffu, n, 0);
         __syncwarp();
         for (uint32_t i = threadIdx.x; i < want; i += 32) phase[base + i] = buf[i];
         __syncwarp();
-        carried = n - want;                                // 0..3
-        if (base + want >= len) {                          // last batch: the state is the value of sample `len`
-            if (threadIdx.x == 0) *state = carried ? buf[want] : ph;
-        } else if (threadIdx.x == 0) {
-            for (uint32_t i = 0; i < carried; ++i) buf[i] = buf[want + i];
-        }
-        __syncwarp();
     }
+    if (threadIdx.x == 0) *state = ph;
 }
 
 template <int V>
@@ -140,7 +133,7 @@ int main() {
     float* h0 = new float[odd]; float* h1 = new float[odd];
     cudaMemcpy(h0, phase, odd * 4, cudaMemcpyDeviceToHost); cudaMemcpy(h1, phase2, odd * 4, cudaMemcpyDeviceToHost);
     uint32_t diff = 0; for (uint32_t i = 0; i + 4 < odd; ++i) diff += h0[i] != h1[i];   // (variant 0 leaves its <4 tail unwritten)
-    std::printf("%-44s %8.3f ms  %6.1f ns/sample  mismatches %u\n", "exact batched candidate", ms, ms * 1e6 / odd, diff);
+    std::printf("%-44s %8.3f ms  %6.1f ns/sample  mismatches %u\n", "branch-free F32 step, batched stores", ms, ms * 1e6 / odd, diff);
     (void)s0; (void)s1;
     return 0;
 }
