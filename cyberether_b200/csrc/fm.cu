@@ -312,79 +312,20 @@ __device__ __forceinline__ float biquad_step(const float x, const Biquad& c, flo
 
 // state.pilotPhase += inc; if (state.pilotPhase >= 2.0f * JST_PI) state.pilotPhase -= 2.0f * JST_PI;
 // JST_PI is a double literal, so the comparison and the subtraction happen in F64 and round back to F32.
-__device__ __forceinline__ float advance_phase(float phase, const float inc) {
-    phase = __fadd_rn(phase, inc);
-    // (double)phase >= 2 pi  <=>  phase >= the smallest F32 not below the F64 value of 2 pi (0x40C90FDB, 6.2831855f): the
-    // comparison stays in F32 and the F64 subtraction only runs on a wrap (every ~13 samples at 19 kHz / 250 kS/s) —
-    // the serial chain is what bounds the wideband decoder.
-    if (phase >= 6.2831854820251465f) {
-        const double two_pi = 2.0 * 3.14159265358979323846;
-        phase = static_cast<float>(static_cast<double>(phase) - two_pi);
-    }
-    return phase;
-}
-
-// The NCO phase is input independent and identical for every lane: one thread evaluates the F32 recurrence.
-__global__ void fm_wide_phase_kernel(float* __restrict__ phase, float* __restrict__ phase_state, const uint64_t lane_len,
-                                     const float inc) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) {
-        return;
-    }
-    // One thread, in-order issue: a branch per sample costs ~50 cycles per step. Four additions are chained without
-    // branches; when none of them reaches 2 pi (about two blocks out of three at 19 kHz / 250 kS/s) they are exactly the
-    // sequential values. Otherwise the values before the first wrap are kept, the wrap is evaluated as the reference
-    // does (F64 subtraction, rounded to F32) and the next block starts right after it.
-    const float kWrap = 6.2831854820251465f;       // smallest F32 >= the F64 value of 2 pi (see advance_phase)
-    const double two_pi = 2.0 * 3.14159265358979323846;
-    float ph = *phase_state;
-    uint64_t n = 0;
-    while (n + 4 <= lane_len) {
-        const float a1 = __fadd_rn(ph, inc), a2 = __fadd_rn(a1, inc), a3 = __fadd_rn(a2, inc), a4 = __fadd_rn(a3, inc);
-        if (!(a1 >= kWrap || a2 >= kWrap || a3 >= kWrap || a4 >= kWrap)) {
-            phase[n] = ph;
-            phase[n + 1] = a1;
-            phase[n + 2] = a2;
-            phase[n + 3] = a3;
-            ph = a4;
-            n += 4;
-            continue;
-        }
-        // first wrapped sum a_j (j = 1..4): samples n .. n+j-1 hold ph, a1 .. a_{j-1}; the next sample is wrap(a_j)
-        const int j = a1 >= kWrap ? 1 : (a2 >= kWrap ? 2 : (a3 >= kWrap ? 3 : 4));
-        phase[n] = ph;
-        if (j > 1) {
-            phase[n + 1] = a1;
-        }
-        if (j > 2) {
-            phase[n + 2] = a2;
-        }
-        if (j > 3) {
-            phase[n + 3] = a3;
-        }
-        const float over = j == 1 ? a1 : (j == 2 ? a2 : (j == 3 ? a3 : a4));
-        ph = static_cast<float>(static_cast<double>(over) - two_pi);
-        n += j;
-    }
-    for (; n < lane_len; ++n) {
-        phase[n] = ph;
-        ph = advance_phase(ph, inc);
-    }
-    *phase_state = ph;
-}
-
-// Same recurrence without branches and without F64: for every F32 a in [2 pi, 2 pi + 1) the reference's wrap
-// (float)((double)a - 2 pi) equals fadd(fsub(a, T), C) with T = 6.2831855f (the F32 just above 2 pi) and
-// C = (float)(T - 2 pi) = 1.7484555e-07f — a - T is exact and the rounding of the sum never sits near a tie (checked
-// exhaustively over all 2^21 values). A step is then FADD, two FADDs and a select (16 cycles of dependent latency
-// instead of ~39 with branches). Lane 0 fills a shared-memory batch, the warp flushes it with coalesced stores.
-// Selected with B200_FM_NCO_BATCHED=1 until it has been timed on hardware (tools/microbench3.cu).
+// The NCO phase is input independent and identical for every lane, and its F32 recurrence cannot be jumped ahead: one
+// thread steps it. The step has no branches and no F64: for every F32 a in [2 pi, 2 pi + 1) the reference's wrap
+// (float)((double)a - 2 pi) equals fadd(fsub(a, T), C) with T = 6.2831855f (the smallest F32 >= the F64 value of 2 pi;
+// (double)a >= 2 pi <=> a >= T) and C = (float)(T - 2 pi) = 1.7484555e-07f — a - T is exact and the rounding of the sum
+// never sits near a tie (checked exhaustively over all 2^21 values). Lane 0 fills a shared-memory batch, the warp flushes
+// it with coalesced stores. tools/microbench3.cu: 12.2 ns/sample against 25.9 for a branchy loop with one global store
+// per sample (the stores alone were 11 ns of that).
 __device__ __forceinline__ float nco_step(const float ph, const float inc) {
     const float a = __fadd_rn(ph, inc);
     const float wrapped = __fadd_rn(__fsub_rn(a, 6.2831854820251465f), 1.7484555314695172e-07f);
     return a >= 6.2831854820251465f ? wrapped : a;
 }
 
-__global__ void __launch_bounds__(32) fm_wide_phase_batched_kernel(float* __restrict__ phase, float* __restrict__ phase_state,
+__global__ void __launch_bounds__(32) fm_wide_phase_kernel(float* __restrict__ phase, float* __restrict__ phase_state,
                                                                   const uint64_t lane_len, const float inc) {
     constexpr uint32_t kBatch = 2048;
     __shared__ float buf[kBatch];
@@ -965,12 +906,7 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
             B200_SUCCESS) {
             return B200_ERROR;
         }
-        static const bool nco_batched = getenv("B200_FM_NCO_BATCHED") != nullptr;
-        if (nco_batched) {
-            fm_wide_phase_batched_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
-        } else {
-            fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
-        }
+        fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
         B200_LAUNCH_CHECK();
         const unsigned ucap = static_cast<unsigned>(cap);
         PilotSystem pilot{sum, phase, diff, at, plan->wc.pilot_alpha};

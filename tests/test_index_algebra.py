@@ -195,3 +195,21 @@ def test_fft_radix_kernel_padded_stockham_scheme():
             ns *= r
         want = np.fft.fft(x.reshape(rows, n), axis=1).reshape(-1)
         assert np.abs(out - want).max() < 1e-9 * n, log2n
+
+
+def test_fm_nco_wrap_identity_exhaustive():
+    """fm.cu:nco_step replaces the reference's F64 wrap `(float)((double)a - 2 pi)` (taken when (double)a >= 2 pi,
+    src/domains/dsp/fm/module_impl_native_cpu.cc NCO update) by fadd(fsub(a, T), C) and the test by a >= T, T = the F32
+    just above 2 pi. Both are checked for EVERY F32 a in [T, T + 1) and around the threshold."""
+    import numpy as np
+    two_pi = 2.0 * 3.14159265358979323846
+    t = np.float32(6.2831854820251465)
+    c = np.float32(1.7484555314695172e-07)
+    assert float(t) >= two_pi > float(np.nextafter(t, np.float32(0)))          # (double)a >= 2 pi  <=>  a >= T
+    assert c == np.float32(float(t) - two_pi)
+    lo = np.array([t], np.float32).view(np.uint32)[0]
+    hi = np.array([t + np.float32(1.0)], np.float32).view(np.uint32)[0]
+    a = np.arange(lo, hi, dtype=np.uint32).view(np.float32)
+    reference = (a.astype(np.float64) - two_pi).astype(np.float32)
+    ours = ((a - t).astype(np.float32) + c).astype(np.float32)
+    assert len(a) == 1 << 21 and np.array_equal(reference, ours)
