@@ -38,23 +38,28 @@ def max_over_ranks(value: float, device=None) -> float:
 def scatter_rows(whole, total_rows: int, row_shape, dtype, device, src: int = 0) -> torch.Tensor:
     """Graph-boundary scatter: `src` holds the whole [total_rows, ...] batch (None elsewhere); every rank receives
     its contiguous slab (`shard_bounds`). The counterpart of `gather_rows`; one collective per graph input, none
-    inside the data path."""
+    inside the data path. Complex tensors travel as (re, im) pairs (NCCL and gloo have no complex types)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return whole
     world, rank = dist.get_world_size(), dist.get_rank()
     bounds = all_shards(total_rows, world)
     largest = max(e - b for b, e in bounds)
-    recv = torch.empty((largest,) + tuple(row_shape), dtype=dtype, device=device)
+    is_complex = dtype.is_complex
+    wire_dtype = torch.float32 if dtype == torch.complex64 else (torch.float64 if dtype == torch.complex128 else dtype)
+    wire_shape = (largest,) + tuple(row_shape) + ((2,) if is_complex else ())
+    recv = torch.empty(wire_shape, dtype=wire_dtype, device=device)
     parts = None
     if rank == src:
+        source = torch.view_as_real(whole) if is_complex else whole
         parts = []
         for b, e in bounds:
             part = torch.zeros_like(recv)
-            part[: e - b] = whole[b:e]
+            part[: e - b] = source[b:e]
             parts.append(part)
     dist.scatter(recv, parts, src=src)
     begin, end = bounds[rank]
-    return recv[: end - begin]
+    mine = recv[: end - begin]
+    return torch.view_as_complex(mine.contiguous()) if is_complex else mine
 
 
 def exchange_fir_halo(local_frames: torch.Tensor, taps: int, previous_cycle_tail=None) -> torch.Tensor:
@@ -93,18 +98,22 @@ def exchange_fir_halo(local_frames: torch.Tensor, taps: int, previous_cycle_tail
 
 def gather_rows(local: torch.Tensor, total_rows: int, dst: int = 0):
     """Graph-boundary gather: concatenates every rank's [rows_r, n] slab on `dst` in rank order (None elsewhere).
-    Slabs may differ by one row, so they are padded to the largest slab for the collective."""
+    Slabs may differ by one row, so they are padded to the largest slab for the collective; complex tensors travel
+    as (re, im) pairs."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
     bounds = all_shards(total_rows, world)
     largest = max(e - b for b, e in bounds)
-    padded = local
-    if local.shape[0] < largest:
-        padded = torch.zeros((largest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        padded[: local.shape[0]] = local
+    is_complex = local.is_complex()
+    wire = torch.view_as_real(local.contiguous()) if is_complex else local
+    padded = wire
+    if wire.shape[0] < largest:
+        padded = torch.zeros((largest,) + tuple(wire.shape[1:]), dtype=wire.dtype, device=wire.device)
+        padded[: wire.shape[0]] = wire
     parts = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-    dist.gather(padded, parts, dst=dst)
+    dist.gather(padded.contiguous(), parts, dst=dst)
     if rank != dst:
         return None
-    return torch.cat([p[: e - b] for p, (b, e) in zip(parts, bounds)], dim=0)
+    whole = torch.cat([p[: e - b] for p, (b, e) in zip(parts, bounds)], dim=0)
+    return torch.view_as_complex(whole.contiguous()) if is_complex else whole

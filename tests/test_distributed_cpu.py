@@ -51,6 +51,12 @@ def _worker(rank, world, port, total_rows, n, results):
         expect = flat[begin * n - (taps - 1):begin * n] if begin > 0 else torch.zeros(taps - 1, dtype=flat.dtype)
         assert torch.equal(halo, expect)
         assert torch.equal(halo.own_tail, flat[end * n - (taps - 1):end * n])
+        # complex slabs travel as (re, im) pairs through the boundary collectives
+        cwhole = stream if rank == 0 else None
+        cmine = scatter_rows(cwhole, total_rows, (n,), torch.complex64, "cpu", src=0)
+        assert cmine.dtype == torch.complex64 and torch.equal(cmine, stream[begin:end])
+        cback = gather_rows(cmine, total_rows, dst=0)
+        assert (cback is None) if rank else torch.equal(cback, stream)
         slowest = max_over_ranks(10.0 + rank)                 # rank 1 is slower: everyone must see 11.0
         whole = gather_rows(local, total_rows, dst=0)
         dist.barrier()
