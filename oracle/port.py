@@ -353,3 +353,105 @@ class FmNarrow:
             self.prev[lane] = stream[-1]
             self.has_prev[lane] = True
         return out
+
+
+class FmWide:
+    """FmImplNativeCpu::computeSubmit wide (stereo) path, src/domains/dsp/fm/module_impl_native_cpu.cc:112-165, with the
+    coefficients of FmImpl::updateCoefficients (module_impl.cc:108-155) and applyBiquad / applyAudioLowPass
+    (module_impl.cc:157-174). Sequential per sample and lane, F32 operation by operation (python loop: small cases
+    only). Input [frames, lanes, frame_len]; output [frames, lanes, frame_len, 2] = (left, right). A sample with a
+    non-finite discriminator output only advances the pilot NCO (:96-105)."""
+
+    def __init__(self, sample_rate: float, deemphasis: str = "none", lanes: int = 1):
+        sr = F32(sample_rate)
+        srd = float(sr)
+        kf = F32(75e3) / sr
+        self.ref = F32(1.0 / (2.0 * JST_PI * float(kf)))
+        # `2.0f * JST_PI * 19e3f / sampleRate`: JST_PI is a double literal -> evaluated left to right in F64, then F32
+        self.inc = F32(((2.0 * JST_PI) * float(F32(19e3))) / srd)
+        self.pilot_alpha = F32(1.0 - np.exp(-2.0 * JST_PI * 200.0 / srd))
+        self.deemph = deemphasis != "none"
+        tau = 50e-6 if deemphasis == "50us" else 75e-6
+        self.deemph_alpha = F32(1.0 - np.exp(-1.0 / (srd * tau))) if self.deemph else F32(1.0)
+        w = 2.0 * JST_PI * 19e3 / srd
+        na = np.sin(w) / (2.0 * 20.0)
+        a0 = 1.0 + na
+        b0 = F32(1.0 / a0)
+        b1 = F32(-2.0 * np.cos(w) / a0)
+        self.notch = (b0, b1, b0, b1, F32((1.0 - na) / a0))              # b0 b1 b2 a1 a2
+        self.lowpass = []
+        w = 2.0 * JST_PI * 15e3 / srd
+        for q in (0.51763809, 0.70710678, 1.93185165):
+            al = np.sin(w) / (2.0 * q)
+            a0 = 1.0 + al
+            lb0 = F32((1.0 - np.cos(w)) * 0.5 / a0)
+            self.lowpass.append((lb0, F32((1.0 - np.cos(w)) / a0), lb0, F32(-2.0 * np.cos(w) / a0),
+                                 F32((1.0 - al) / a0)))
+        z = lambda: [F32(0.0), F32(0.0)]
+        self.lanes = [dict(prev=np.complex64(0), has_prev=False, phase=F32(0.0), cos_stage=F32(0.0), sin_stage=F32(0.0),
+                           pcos=F32(0.0), psin=F32(0.0), sum_notch=z(), diff_notch=z(),
+                           sum_lp=[z(), z(), z()], diff_lp=[z(), z(), z()], left=F32(0.0), right=F32(0.0))
+                      for _ in range(lanes)]
+
+    @staticmethod
+    def _biquad(x, c, st):
+        b0, b1, b2, a1, a2 = c
+        y = F32(F32(b0 * x) + st[0])
+        st[0] = F32(F32(F32(b1 * x) - F32(a1 * y)) + st[1])
+        st[1] = F32(F32(b2 * x) - F32(a2 * y))
+        return y
+
+    def _lowpass(self, x, states):
+        for c, st in zip(self.lowpass, states):
+            x = self._biquad(x, c, st)
+        return x
+
+    def _advance(self, s):
+        s["phase"] = F32(s["phase"] + self.inc)
+        if float(s["phase"]) >= 2.0 * JST_PI:
+            s["phase"] = F32(float(s["phase"]) - 2.0 * JST_PI)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        frames, lanes, n = x.shape
+        out = np.empty(x.shape + (2,), np.float32)
+        two = F32(2.0)
+        with np.errstate(invalid="ignore", over="ignore"):
+            for lane in range(lanes):
+                s = self.lanes[lane]
+                for f in range(frames):
+                    for i in range(n):
+                        cur = x[f, lane, i]
+                        prev = s["prev"]
+                        if not s["has_prev"]:
+                            d = F32(0.0)
+                        else:
+                            pr, pi, cr, ci = F32(prev.real), F32(prev.imag), F32(cur.real), F32(cur.imag)
+                            if not (np.isfinite(pr) and np.isfinite(pi) and np.isfinite(cr) and np.isfinite(ci)):
+                                d = F32(np.nan)
+                            else:
+                                re = F32(F32(pr * cr) + F32(pi * ci))
+                                im = F32(F32(pr * ci) - F32(pi * cr))
+                                d = F32(F32(np.arctan2(im, re)) * self.ref)
+                        s["prev"], s["has_prev"] = cur, True
+                        if not np.isfinite(d):
+                            out[f, lane, i] = np.nan
+                            self._advance(s)
+                            continue
+                        pc, ps = F32(np.cos(s["phase"])), F32(np.sin(s["phase"]))
+                        s["cos_stage"] = F32(s["cos_stage"] + F32(self.pilot_alpha * F32(F32(d * pc) - s["cos_stage"])))
+                        s["sin_stage"] = F32(s["sin_stage"] + F32(self.pilot_alpha * F32(F32(d * ps) - s["sin_stage"])))
+                        s["pcos"] = F32(s["pcos"] + F32(self.pilot_alpha * F32(s["cos_stage"] - s["pcos"])))
+                        s["psin"] = F32(s["psin"] + F32(self.pilot_alpha * F32(s["sin_stage"] - s["psin"])))
+                        total = self._lowpass(self._biquad(d, self.notch, s["sum_notch"]), s["sum_lp"])
+                        offset = F32(np.arctan2(s["pcos"], s["psin"]))
+                        carrier = F32(np.sin(F32(two * F32(s["phase"] + offset))))
+                        diff = self._lowpass(self._biquad(F32(F32(two * d) * carrier), self.notch, s["diff_notch"]),
+                                             s["diff_lp"])
+                        left, right = F32(total + diff), F32(total - diff)
+                        if self.deemph:
+                            s["left"] = F32(s["left"] + F32(self.deemph_alpha * F32(left - s["left"])))
+                            s["right"] = F32(s["right"] + F32(self.deemph_alpha * F32(right - s["right"])))
+                            left, right = s["left"], s["right"]
+                        out[f, lane, i, 0], out[f, lane, i, 1] = left, right
+                        self._advance(s)
+        return out
