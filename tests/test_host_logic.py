@@ -162,3 +162,61 @@ def test_scheduler_detects_cycles_and_duplicates():
     assert m.create("w", {"size": 8}, {}) == cb.Result.SUCCESS
     assert s.add(m) == cb.Result.SUCCESS
     assert s.add(m) == cb.Result.ERROR
+
+
+def test_cast_validation_and_dtypes():
+    """core/cast/module_tests.cc: supported pairs, bypass on matching dtype, invalid spellings, unsupported pairs."""
+    for name, np_type, is_complex, out in (("I8", np.int8, False, "F32"), ("U16", np.uint16, False, "F32"),
+                                           ("CI8", np.int8, True, "CF32"), ("CU32", np.uint32, True, "CF32")):
+        x = cb.Tensor.from_numpy(np.zeros((3, 5, 2) if is_complex else (3, 5), np_type), device="cpu", dtype=name,
+                                 sampleAxis=1)
+        assert x.dtype == name and x.shape == (3, 5) and x.rank == 2 and x.size == 15
+        m = build_module("cast")
+        assert m.create("c", {"outputType": out}, {"buffer": link(x)}) == cb.Result.SUCCESS, cb.last_error()
+        o = m.outputs["buffer"].tensor
+        assert o.dtype == out and o.shape == (3, 5) and o.attribute("sampleAxis") == 1 and not m.bypass
+        m = build_module("cast")
+        assert m.create("c", {"outputType": name}, {"buffer": link(x)}) == cb.Result.SUCCESS
+        assert m.bypass and m.outputs["buffer"].tensor.data is x.data            # alias, not a copy
+    ci8 = cb.Tensor.from_numpy(np.zeros((4, 2), np.int8), device="cpu", dtype="CI8", sampleAxis=0)
+    for spelling in ("", "cf32", "CF32 ", "NONE", "NOPE"):
+        m = build_module("cast")
+        assert m.create("c", {"outputType": spelling}, {"buffer": link(ci8)}) == cb.Result.ERROR
+        assert "Invalid output type" in cb.last_error()
+    m = build_module("cast")
+    assert m.create("c", {"outputType": "F32"}, {"buffer": link(ci8)}) == cb.Result.ERROR      # complex int -> real
+    assert "Unsupported conversion" in cb.last_error()
+    with pytest.raises(TypeError):
+        cb.Tensor.from_numpy(np.zeros((4, 3), np.int8), device="cpu", dtype="CI8")               # needs a trailing (re, im)
+
+
+def test_agc_validation_like_reference():
+    """dsp/agc/module_impl.cc:7-45."""
+    x = tensor((4, 64), sampleAxis=1, batchAxis=0)
+    for bad, text in ((dict(tileSize=0), "Tile size"), (dict(reference=-1.0), "Reference"), (dict(epsilon=0.0), "Epsilon"),
+                      (dict(minGain=0.0), "Minimum gain"), (dict(minGain=2.0, maxGain=1.0), "Maximum gain"),
+                      (dict(maxGainChange=0.99), "gain change")):
+        m = build_module("agc")
+        assert m.create("a", bad, {"signal": link(x)}) == cb.Result.ERROR
+        assert text in cb.last_error()
+    m = build_module("agc")
+    assert m.create("a", None, {"signal": link(tensor((4, 64)))}) == cb.Result.ERROR     # no signal axes
+    m = build_module("agc")
+    assert m.create("a", {"tileSize": 16}, {"signal": link(x)}) == cb.Result.SUCCESS
+    assert m.outputs["signal"].tensor.shape == (4, 64) and m.taint == Taint.STATELESS
+
+
+def test_spectral_chain_accepts_integer_input_and_limits_fused_agc():
+    win = tensor((4096,), sampleAxis=0)
+    ci16 = cb.Tensor.from_numpy(np.zeros((3, 4096, 2), np.int16), device="cpu", dtype="CI16", sampleAxis=1, batchAxis=0)
+    m = build_module("spectral_chain")
+    assert m.create("s", {"enableAgc": True}, {"buffer": link(ci16), "window": link(win)}) == cb.Result.SUCCESS
+    assert m.outputs["buffer"].tensor.dtype == "F32" and m.outputs["buffer"].tensor.shape == (3, 4096)
+    small = tensor((3, 1024), sampleAxis=1, batchAxis=0)
+    m = build_module("spectral_chain")
+    assert m.create("s", {"enableAgc": True}, {"buffer": link(small), "window": link(tensor((1024,), sampleAxis=0))}) \
+        == cb.Result.ERROR
+    assert "4096-point" in cb.last_error()
+    real = tensor((3, 4096), dtype=np.float32, sampleAxis=1, batchAxis=0)
+    m = build_module("spectral_chain")
+    assert m.create("s", None, {"buffer": link(real), "window": link(win)}) == cb.Result.ERROR
