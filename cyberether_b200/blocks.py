@@ -55,6 +55,7 @@ class Block:
     # -- lifecycle
     def create(self, name: str, inputs: Dict[str, Tensor], scheduler: Optional[SynchronousScheduler] = None) -> Result:
         self.name = name
+        self._owns_scheduler = scheduler is None
         self.scheduler = scheduler or SynchronousScheduler(self.device)
         self.inputs = {}
         for port, tensor in inputs.items():
@@ -76,12 +77,16 @@ class Block:
         return self.outputs[port].tensor
 
     def destroy(self) -> Result:
-        for module in list(self.modules.values()):
-            if self.scheduler is not None:
-                self.scheduler.modules.pop(module.name, None)
+        # Block::destroy (src/block.cc): every module leaves the scheduler — which rebuilds its order and runtime, so
+        # the other blocks of a SHARED scheduler keep running — and is then destroyed; the runtime itself is torn
+        # down only by the block that created the scheduler.
+        for module in reversed(list(self.modules.values())):
+            if self.scheduler is not None and module.name in self.scheduler.modules:
+                self.scheduler.remove(module)
             module.destroy()
-        if self.scheduler is not None and self.scheduler.runtime is not None:
+        if self.scheduler is not None and getattr(self, "_owns_scheduler", True) and self.scheduler.runtime is not None:
             self.scheduler.runtime.destroy()
+            self.scheduler.runtime = None
         self.modules = {}
         return Result.SUCCESS
 

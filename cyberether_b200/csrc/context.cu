@@ -115,6 +115,9 @@ int b200_malloc(b200_ctx* ctx, uint64_t bytes, void** ptr) {
         *ptr = nullptr;
         return fail("b200_malloc: cudaMemset failed: %s", cudaGetErrorString(e));
     }
+    // The zero-fill ran on the legacy stream, which non-blocking streams (the runtime's, PyTorch's) do not order
+    // against: settle it here, allocation is not on the per-cycle path.
+    B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
     return B200_SUCCESS;
 }
 

@@ -138,8 +138,8 @@ __global__ void multiply_same_f32_kernel(const float4* __restrict__ a, const flo
 // src/domains/core/multiply_constant/module_impl_native_cpu.cc:82-100 (CF32 * F32 scalar scales
 // both parts; std::complex<float> * float).
 __global__ void multiply_constant_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                         const uint64_t count, const float constant) {
-    const uint64_t vecs = count / 4;
+                                         const uint64_t count, const float constant, const bool vec) {
+    const uint64_t vecs = vec ? count / 4 : 0;      // misaligned (offset view) buffers take the scalar loop
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* out4 = reinterpret_cast<float4*>(out);
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -157,8 +157,8 @@ __global__ void multiply_constant_kernel(const float* __restrict__ in, float* __
 // ---- amplitude ----------------------------------------------------------------------------
 // src/domains/dsp/amplitude/module_impl_native_cpu.cc:73-99
 __global__ void amplitude_cf32_kernel(const float2* __restrict__ in, float* __restrict__ out,
-                                      const uint64_t count, const float coeff) {
-    const uint64_t quads = count / 4;
+                                      const uint64_t count, const float coeff, const bool vec) {
+    const uint64_t quads = vec ? count / 4 : 0;
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* out4 = reinterpret_cast<float4*>(out);
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -178,8 +178,8 @@ __global__ void amplitude_cf32_kernel(const float2* __restrict__ in, float* __re
 }
 
 __global__ void amplitude_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                     const uint64_t count, const float coeff) {
-    const uint64_t quads = count / 4;
+                                     const uint64_t count, const float coeff, const bool vec) {
+    const uint64_t quads = vec ? count / 4 : 0;
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* out4 = reinterpret_cast<float4*>(out);
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -197,8 +197,8 @@ __global__ void amplitude_f32_kernel(const float* __restrict__ in, float* __rest
 // ---- range --------------------------------------------------------------------------------
 // src/domains/core/range/module_impl_native_cpu.cc:67-82
 __global__ void range_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const uint64_t count,
-                                 const float scale, const float offset) {
-    const uint64_t quads = count / 4;
+                                 const float scale, const float offset, const bool vec) {
+    const uint64_t quads = vec ? count / 4 : 0;
     const float4* in4 = reinterpret_cast<const float4*>(in);
     float4* out4 = reinterpret_cast<float4*>(out);
     const uint64_t tid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -460,10 +460,9 @@ int b200_multiply_constant_f32(b200_ctx* ctx, const float* in, float* out, uint6
     if (count == 0) {
         return B200_SUCCESS;
     }
-    B200_REQUIRE(aligned16(in) && aligned16(out), "b200_multiply_constant: buffers must be 16-byte aligned");
     DeviceGuard guard(ctx);
-    multiply_constant_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(in, out, count,
-                                                                                                    constant);
+    multiply_constant_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(
+        in, out, count, constant, aligned16(in) && aligned16(out));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -474,10 +473,9 @@ int b200_amplitude_cf32(b200_ctx* ctx, const b200_cf32* in, float* out, uint64_t
     if (count == 0) {
         return B200_SUCCESS;
     }
-    B200_REQUIRE(aligned16(in) && aligned16(out), "b200_amplitude_cf32: buffers must be 16-byte aligned");
     DeviceGuard guard(ctx);
     amplitude_cf32_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float2*>(in), out, count, coeff);
+        reinterpret_cast<const float2*>(in), out, count, coeff, aligned16(in) && aligned16(out));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -488,10 +486,9 @@ int b200_amplitude_f32(b200_ctx* ctx, const float* in, float* out, uint64_t coun
     if (count == 0) {
         return B200_SUCCESS;
     }
-    B200_REQUIRE(aligned16(in) && aligned16(out), "b200_amplitude_f32: buffers must be 16-byte aligned");
     DeviceGuard guard(ctx);
-    amplitude_f32_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(in, out, count,
-                                                                                                coeff);
+    amplitude_f32_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(
+        in, out, count, coeff, aligned16(in) && aligned16(out));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -502,10 +499,9 @@ int b200_range_f32(b200_ctx* ctx, const float* in, float* out, uint64_t count, f
     if (count == 0) {
         return B200_SUCCESS;
     }
-    B200_REQUIRE(aligned16(in) && aligned16(out), "b200_range_f32: buffers must be 16-byte aligned");
     DeviceGuard guard(ctx);
-    range_f32_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(in, out, count, scale,
-                                                                                            offset);
+    range_f32_kernel<<<stream_grid(ctx, count / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(
+        in, out, count, scale, offset, aligned16(in) && aligned16(out));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

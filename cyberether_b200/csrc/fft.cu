@@ -573,6 +573,7 @@ int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan**
             return B200_ERROR;
         }
     }
+    cudaStreamSynchronize(cudaStreamLegacy);   // uploads / zero-fills above ran on the legacy stream: settle them before a non-blocking stream executes
     *plan = pl;
     return B200_SUCCESS;
 }
@@ -713,6 +714,7 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
             return B200_ERROR;
         }
         pl->variant = "composite<multiply,fft(four-step|bluestein),amplitude,range>";
+        cudaStreamSynchronize(cudaStreamLegacy);   // uploads / zero-fills above ran on the legacy stream: settle them before a non-blocking stream executes
         *plan = pl;
         return B200_SUCCESS;
     }
@@ -760,6 +762,7 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
     pl->variant = n == kFft4096N ? "fft4096_kernel<tma,radix16x3>"
                                  : (n >= 16 && n <= 8192 ? "fft_radix_kernel<tma,radix16 stockham>"
                                                          : "fft_generic_kernel<stockham4>");
+    cudaStreamSynchronize(cudaStreamLegacy);   // uploads / zero-fills above ran on the legacy stream: settle them before a non-blocking stream executes
     *plan = pl;
     return B200_SUCCESS;
 }

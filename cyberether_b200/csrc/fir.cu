@@ -477,6 +477,7 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
     pl->hist[0] = static_cast<float2*>(h0);
     pl->hist[1] = static_cast<float2*>(h1);
     pl->cur = 0;
+    cudaStreamSynchronize(cudaStreamLegacy);   // uploads / zero-fills above ran on the legacy stream: settle them before a non-blocking stream executes
     *plan = pl;
     return B200_SUCCESS;
 }
@@ -521,6 +522,7 @@ int b200_fir_plan_set_translation(b200_fir_plan* plan, uint64_t frame_len, const
     B200_CUDA_CHECK(cudaMemcpy(plan->rot_dev, rot.data(), rot.size() * sizeof(float2), cudaMemcpyHostToDevice));
     B200_CUDA_CHECK(cudaMemcpy(plan->increments_dev, inc.data(), inc.size() * sizeof(double), cudaMemcpyHostToDevice));
     B200_CUDA_CHECK(cudaMemset(plan->phases_dev, 0, plan->heads * sizeof(double)));
+    B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
     plan->translate = true;
     plan->frame_len = frame_len;
     return B200_SUCCESS;

@@ -850,6 +850,7 @@ int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wi
         pl->power = static_cast<float*>(dev);
         pl->wide_state = static_cast<float*>(wst);
     }
+    cudaStreamSynchronize(cudaStreamLegacy);   // uploads / zero-fills above ran on the legacy stream: settle them before a non-blocking stream executes
     *plan = pl;
     return B200_SUCCESS;
 }

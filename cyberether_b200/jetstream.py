@@ -487,12 +487,21 @@ class Window(Module):
         return _call("b200_window_blackman_cf32", ctx.handle, self.output.ptr(), self.output.size, stream)
 
 
+def _empty_input_axis(tensor: "Tensor") -> int:
+    """Sample axis of an EMPTY input (validate() returns early on those, docs/blocks-and-modules.md:182-186)."""
+    axes = resolve_signal_axes(tensor)
+    if axes is not None and axes.sample is not None:
+        return axes.sample
+    return max(tensor.rank - 1, 0)
+
+
 @register_module
 class Invert(Module):
     """`invert` — src/domains/dsp/invert/module_impl.cc + native_cpu.cc:78-103."""
     TYPE = "invert"
 
     def validate(self):
+        self._axis = None
         link = self.inputs.get("signal")
         if link is None or not link.resolved() or link.tensor.size == 0:
             return Result.SUCCESS
@@ -512,6 +521,8 @@ class Invert(Module):
 
     def create_impl(self):
         self.input = self.inputs["signal"].tensor
+        if self._axis is None:      # empty input: validate() resolved nothing (it must tolerate empty tensors)
+            self._axis = _empty_input_axis(self.input)
         self._layout = _Layout(self.input.data, None)
         self._layout.perm = list(range(self.input.rank))
         self._layout.shape_p = list(self.input.shape)
@@ -529,6 +540,8 @@ class Invert(Module):
         return Result.SUCCESS
 
     def compute_submit(self, stream):
+        if self.input.size == 0:
+            return Result.SUCCESS
         err = _require_cuda(self, self.input, self.output)
         if err:
             return err
@@ -935,6 +948,7 @@ class Agc(Module):
             return _error("[MODULE_AGC] Maximum gain must be finite and no less than minimum gain.")
         if not math.isfinite(float(c["maxGainChange"])) or float(c["maxGainChange"]) < 1.0:
             return _error("[MODULE_AGC] Maximum gain change must be finite and at least one.")
+        self._axis = None
         link = self.inputs.get("signal")
         if link is None or not link.resolved() or link.tensor.size == 0:
             return Result.SUCCESS
@@ -955,8 +969,10 @@ class Agc(Module):
     def create_impl(self):
         self.input = self.inputs["signal"].tensor
         t = self.input
-        self._samples = t.shape[self._axis]
-        self._lanes = t.size // self._samples
+        if self._axis is None:
+            self._axis = _empty_input_axis(t)
+        self._samples = t.shape[self._axis] if t.rank else 0
+        self._lanes = t.size // self._samples if self._samples else 0
         self.output = Tensor.create(t.device, t.dtype, t.shape)
         self.output.propagate_attributes(t)
         self.outputs["signal"] = TensorLink()
@@ -971,6 +987,8 @@ class Agc(Module):
         return Result.SUCCESS
 
     def compute_submit(self, stream):
+        if self.input.size == 0:
+            return Result.SUCCESS
         err = _require_cuda(self, self.input, self.output)
         if err:
             return err
@@ -1315,14 +1333,19 @@ def filter_resample_plan(sample_rate: float, bandwidth: float, taps: int, signal
 class FirFilter(Module):
     """`fir_filter` — B200-only fused module: the per-cycle module chain of the `filter` block
     (src/domains/dsp/filter/block_impl.cc:350-582) as one streaming time-domain (decimating) FIR kernel.
-    Inputs: `signal` CF32 [T] or [B, T] (batch = consecutive frames), `coeffs` CF32 [heads, taps] (settled).
-    Output `buffer`: [B, heads, T / R] with channelAxis = old sample axis, sampleAxis = +1."""
+    Inputs: `signal` CF32 [T] or [B, T], `coeffs` CF32 [heads, taps] (settled).
+    Output `buffer`: [B, heads, T / R] with channelAxis = old sample axis, sampleAxis = +1.
+    With batchAxis = 0 the B rows are consecutive frames of ONE stream (overlap_add carries frame k's tail into frame
+    k+1, src/domains/dsp/overlap_add/module_impl_native_cpu.cc:155-174); WITHOUT a batchAxis they are B independent
+    lanes, each carrying its own tail across cycles (:176-198) — one plan (history) per lane."""
     TYPE = "fir_filter"
     DEFAULTS = {"decimation": 1, "centerBins": None}
+    MAX_LANES = 256
 
     def __init__(self):
         super().__init__()
         self._plan_handle = None
+        self._lane_plans: List[ctypes.c_void_p] = []
 
     def validate(self):
         link = self.inputs.get("signal")
@@ -1341,6 +1364,9 @@ class FirFilter(Module):
         r = int(self.config["decimation"])
         if r < 1 or t.shape[-1] % r != 0:
             return _error("[MODULE_FIR_FILTER_B200] Frame length must be a multiple of the decimation.")
+        if t.rank == 2 and axes.batch is None and t.shape[0] > self.MAX_LANES:
+            return _error(f"[MODULE_FIR_FILTER_B200] At most {self.MAX_LANES} independent lanes (rows without a batchAxis).")
+        self._lane_mode = t.rank == 2 and axes.batch is None
         return Result.SUCCESS
 
     def define(self):
@@ -1357,7 +1383,9 @@ class FirFilter(Module):
         self._r = int(self.config["decimation"])
         t = self.input
         self._frame_len = t.shape[-1]
-        self._frames = t.size // self._frame_len
+        rows = t.size // self._frame_len
+        self._lanes = rows if getattr(self, "_lane_mode", False) else 1
+        self._frames = 1 if self._lanes > 1 else rows
         out_shape = tuple(t.shape[:-1]) + (self._heads, self._frame_len // self._r)
         self.output = Tensor.create(t.device, "CF32", out_shape)
         self.output.propagate_attributes(t)
@@ -1378,16 +1406,22 @@ class FirFilter(Module):
         ctx = Context.get(self.input.device)
         torch.cuda.current_stream(self.input.device).synchronize()   # coefficients are settled static output
         host = np.ascontiguousarray(self.coeffs.numpy())
-        handle = ctypes.c_void_p()
-        result = _call("b200_fir_plan_create", ctx.handle, host.ctypes.data_as(ctypes.c_void_p), self._taps,
-                       self._heads, self._r, ctypes.byref(handle))
-        if result != Result.SUCCESS:
-            return result
-        self._plan_handle = handle
         bins = self.config.get("centerBins")
-        if bins is not None and any(int(b) != 0 for b in bins):
-            arr = (ctypes.c_int64 * self._heads)(*[int(b) for b in bins])
-            return _call("b200_fir_plan_set_translation", self._plan_handle, self._frame_len, arr)
+        translate = bins is not None and any(int(b) != 0 for b in bins)
+        self._lane_plans = []
+        for _ in range(self._lanes):
+            handle = ctypes.c_void_p()
+            result = _call("b200_fir_plan_create", ctx.handle, host.ctypes.data_as(ctypes.c_void_p), self._taps,
+                           self._heads, self._r, ctypes.byref(handle))
+            if result != Result.SUCCESS:
+                return result
+            self._lane_plans.append(handle)
+            if translate:
+                arr = (ctypes.c_int64 * self._heads)(*[int(b) for b in bins])
+                result = _call("b200_fir_plan_set_translation", handle, self._frame_len, arr)
+                if result != Result.SUCCESS:
+                    return result
+        self._plan_handle = self._lane_plans[0]
         return Result.SUCCESS
 
     def compute_submit(self, stream):
@@ -1403,8 +1437,17 @@ class FirFilter(Module):
                            frames_before, stream)
             if result != Result.SUCCESS:
                 return result
-        return _call("b200_fir_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), self._frames,
-                     self._frame_len, stream)
+        if self._lanes == 1:
+            return _call("b200_fir_exec", self._plan_handle, self.input.ptr(), self.output.ptr(), self._frames,
+                         self._frame_len, stream)
+        x0, y0 = self.input.ptr().value, self.output.ptr().value
+        out_row = self._heads * (self._frame_len // self._r) * 8
+        for lane, handle in enumerate(self._lane_plans):
+            result = _call("b200_fir_exec", handle, ctypes.c_void_p(x0 + lane * self._frame_len * 8),
+                           ctypes.c_void_p(y0 + lane * out_row), 1, self._frame_len, stream)
+            if result != Result.SUCCESS:
+                return result
+        return Result.SUCCESS
 
     def set_history(self, tail: torch.Tensor, frames_before: int = 0) -> Result:
         """Time sharding (sharding.exchange_fir_halo): the last `taps - 1` input samples that precede this module's
@@ -1417,9 +1460,10 @@ class FirFilter(Module):
         return Result.SUCCESS
 
     def compute_deinitialize(self):
-        if self._plan_handle is not None:
-            _call("b200_fir_plan_destroy", self._plan_handle)
-            self._plan_handle = None
+        for handle in self._lane_plans:
+            _call("b200_fir_plan_destroy", handle)
+        self._lane_plans = []
+        self._plan_handle = None
         return Result.SUCCESS
 
     def destroy(self):
@@ -1450,6 +1494,7 @@ class Fm(Module):
             return _error("[MODULE_FM] Sample rate must not exceed 20 MHz.")
         if c["mode"] == "wide" and sr < 200e3:
             return _error("[MODULE_FM] Wideband mode requires a sample rate of at least 200 kHz.")
+        self._axes = None
         link = self.inputs.get("signal")
         if link is None or not link.resolved() or link.tensor.size == 0:
             return Result.SUCCESS
@@ -1475,9 +1520,11 @@ class Fm(Module):
         if not self.input.contiguous():
             return _error("[MODULE_FM_B200] Strided inputs are not supported by this provider yet.")
         t = self.input
-        self._frame_len = t.shape[-1]
+        if self._axes is None:      # empty input
+            self._axes = resolve_signal_axes(t) or SignalAxes()
+        self._frame_len = t.shape[-1] if t.rank else 0
         self._frames = t.shape[0] if (self._axes.batch == 0 and t.rank >= 2) else 1
-        self._lanes = t.size // (self._frame_len * self._frames)
+        self._lanes = t.size // (self._frame_len * self._frames) if t.size else 0
         wide = self.config["mode"] == "wide"
         self.output = Tensor.create(t.device, "F32", tuple(t.shape) + ((2,) if wide else ()))
         self.output.propagate_attributes(t)
@@ -1489,7 +1536,7 @@ class Fm(Module):
         return Result.SUCCESS
 
     def compute_initialize(self):
-        if self.input.device.type != "cuda":
+        if self.input.device.type != "cuda" or self.input.size == 0:
             return Result.SUCCESS
         ctx = Context.get(self.input.device)
         handle = ctypes.c_void_p()
@@ -1501,6 +1548,8 @@ class Fm(Module):
         return result
 
     def compute_submit(self, stream):
+        if self.input.size == 0:
+            return Result.SUCCESS
         err = _require_cuda(self, self.input, self.output)
         if err:
             return err

@@ -67,13 +67,15 @@ def exchange_fir_halo(local_frames: torch.Tensor, taps: int, previous_cycle_tail
     rank (`shard_bounds` over the frame axis), and a FIR with `taps` coefficients needs the `taps - 1` input samples
     that precede its slab. One neighbour exchange per cycle: rank r sends the tail of its slab to rank r + 1; rank 0
     takes `previous_cycle_tail` (the tail the LAST rank kept from the previous cycle, None / zeros at stream start).
-    Returns the halo [taps - 1] for this rank (zero-padded in front when the neighbour's slab is shorter than that) and
-    leaves this rank's own tail in `.own_tail` of the result for the caller to keep (only the last rank's matters)."""
+    Returns the halo [taps - 1] for this rank and leaves this rank's own tail in `.own_tail` of the result for the
+    caller to keep (only the last rank's matters). A slab shorter than taps - 1 samples would need samples from TWO
+    ranks back (a chain dependency): that is rejected, not zero-padded — cut the stream into longer slabs."""
     need = taps - 1
     flat = local_frames.reshape(-1)
+    if flat.numel() < need:
+        raise ValueError(f"exchange_fir_halo: a slab of {flat.numel()} samples is shorter than the {need}-sample halo "
+                         f"a {taps}-tap filter needs; use fewer ranks or longer frames")
     own_tail = flat[-need:].clone() if need > 0 else flat[:0].clone()
-    if own_tail.numel() < need:
-        own_tail = torch.cat([torch.zeros(need - own_tail.numel(), dtype=flat.dtype, device=flat.device), own_tail])
     if previous_cycle_tail is None:
         previous_cycle_tail = torch.zeros(need, dtype=flat.dtype, device=flat.device)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or need == 0:

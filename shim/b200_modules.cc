@@ -12,7 +12,9 @@
 //                    computeDeinitialize}                              include/jetstream/runtime_context_native_cuda.hh:13-39
 //   selection        blockCreate(name, type, config, inputs, DeviceType::CUDA, RuntimeType::NATIVE, "b200")
 //                    or `device: cuda / runtime: native / provider: b200` in a flowgraph YAML
+#include <cmath>
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include <jetstream/backend/base.hh>
@@ -23,54 +25,26 @@
 #include <jetstream/scheduler_context.hh>
 
 #include "domains/core/cast/module_impl.hh"
+#include "domains/core/expand_dims/module_impl.hh"
 #include "domains/core/multiply/module_impl.hh"
+#include "domains/core/multiply_constant/module_impl.hh"
 #include "domains/core/range/module_impl.hh"
 #include "domains/core/reshape/module_impl.hh"
 #include "domains/dsp/agc/module_impl.hh"
 #include "domains/dsp/amplitude/module_impl.hh"
 #include "domains/dsp/fft/module_impl.hh"
+#include "domains/dsp/filter_taps/module_impl.hh"
+#include "domains/dsp/fm/module_impl.hh"
 #include "domains/dsp/invert/module_impl.hh"
 #include "domains/dsp/window/module_impl.hh"
 
-#include "b200dsp.h"
+#include "b200_provider.hh"
 
 namespace Jetstream::Modules {
 
-namespace {
-
-// One b200_ctx for the device the reference's CUDA backend singleton selected.
-b200_ctx* B200Ctx() {
-    static b200_ctx* ctx = [] {
-        b200_ctx* created = nullptr;
-        int device = 0;
-        cudaGetDevice(&device);
-        if (b200_ctx_create(device, &created) != B200_SUCCESS) {
-            JST_ERROR("[B200] {}", b200_last_error());
-        }
-        return created;
-    }();
-    return ctx;
-}
-
-Result Check(const int code, const char* module) {
-    if (code == B200_SUCCESS) {
-        return Result::SUCCESS;
-    }
-    JST_ERROR("[MODULE_{}_B200] {}", module, b200_last_error());
-    return static_cast<Result>(code);
-}
-
-template<typename T>
-T* DevicePtr(Tensor& tensor) {
-    return reinterpret_cast<T*>(static_cast<std::uint8_t*>(tensor.buffer().data()) + tensor.offsetBytes());
-}
-template<typename T>
-const T* DevicePtr(const Tensor& tensor) {
-    return reinterpret_cast<const T*>(static_cast<const std::uint8_t*>(tensor.buffer().data()) +
-                                      tensor.offsetBytes());
-}
-
-}  // namespace
+using B200::Check;
+using B200::DevicePtr;
+static inline b200_ctx* B200Ctx() { return B200::Ctx(); }
 
 // ---- window ---------------------------------------------------------------------------------------
 struct WindowImplB200 : public WindowImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
@@ -118,22 +92,7 @@ struct CastImplB200 : public CastImpl, public NativeCudaRuntimeContext, public S
                                             input.size(), stream), "CAST");
         }
         // integer -> F32 and complex integer -> CF32 (module_impl_native_cpu.cc:163-330); dtype codes of b200dsp.h
-        int code = -1;
-        switch (input.dtype()) {
-            case DataType::I8: code = B200_DTYPE_I8; break;
-            case DataType::U8: code = B200_DTYPE_U8; break;
-            case DataType::I16: code = B200_DTYPE_I16; break;
-            case DataType::U16: code = B200_DTYPE_U16; break;
-            case DataType::I32: code = B200_DTYPE_I32; break;
-            case DataType::U32: code = B200_DTYPE_U32; break;
-            case DataType::CI8: code = B200_DTYPE_CI8; break;
-            case DataType::CU8: code = B200_DTYPE_CU8; break;
-            case DataType::CI16: code = B200_DTYPE_CI16; break;
-            case DataType::CU16: code = B200_DTYPE_CU16; break;
-            case DataType::CI32: code = B200_DTYPE_CI32; break;
-            case DataType::CU32: code = B200_DTYPE_CU32; break;
-            default: break;
-        }
+        const int code = B200::IntegerDtypeCode(input.dtype());
         const bool complexIn = code >= B200_DTYPE_CI8;
         if (code < 0 || !input.contiguous() || outputDtype != (complexIn ? DataType::CF32 : DataType::F32)) {
             JST_ERROR("[MODULE_CAST_B200] Unsupported conversion '{}' -> '{}' (contiguous inputs only).",
@@ -267,5 +226,336 @@ struct RangeImplB200 : public RangeImpl, public NativeCudaRuntimeContext, public
     }
 };
 JST_REGISTER_MODULE(RangeImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+// ---- expand_dims (view) / multiply_constant ----------------------------------------------------------------
+struct ExpandDimsImplB200 : public ExpandDimsImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
+    Result computeSubmit(const cudaStream_t&) override { return Result::SUCCESS; }
+};
+JST_REGISTER_MODULE(ExpandDimsImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+struct MultiplyConstantImplB200 : public MultiplyConstantImpl, public NativeCudaRuntimeContext,
+                                  public Scheduler::Context {
+    Result computeSubmit(const cudaStream_t& stream) override {
+        if (!input.contiguous()) {
+            JST_ERROR("[MODULE_MULTIPLY_CONSTANT_B200] Strided inputs are not supported by this provider.");
+            return Result::ERROR;
+        }
+        if (input.dtype() == DataType::CF32) {
+            return Check(b200_multiply_constant_cf32(B200Ctx(), DevicePtr<b200_cf32>(input),
+                                                     DevicePtr<b200_cf32>(output), input.size(), constant, stream),
+                         "MULTIPLY_CONSTANT");
+        }
+        if (input.dtype() == DataType::F32) {
+            return Check(b200_multiply_constant_f32(B200Ctx(), DevicePtr<float>(input), DevicePtr<float>(output),
+                                                    input.size(), constant, stream), "MULTIPLY_CONSTANT");
+        }
+        JST_ERROR("[MODULE_MULTIPLY_CONSTANT_B200] Unsupported data type '{}'.", input.dtype());
+        return Result::ERROR;
+    }
+};
+JST_REGISTER_MODULE(MultiplyConstantImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+// ---- filter_taps (STATIC_OUTPUT: F64 on the host with the reference's formula, uploaded once) -----------------
+struct FilterTapsImplB200 : public FilterTapsImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
+    Result computeSubmit(const cudaStream_t& stream) override {
+        const U64 heads = center.size();
+        host.assign(heads * taps, b200_cf32{0.0f, 0.0f});
+        JST_CHECK(Check(b200_filter_taps_host(sampleRate, bandwidth, center.data(), heads, taps, host.data()),
+                        "FILTER_TAPS"));
+        return Check(b200_memcpy(B200Ctx(), DevicePtr<void>(coeffs), host.data(), host.size() * sizeof(b200_cf32), 0,
+                                 stream), "FILTER_TAPS");
+    }
+    std::vector<b200_cf32> host;     // outlives the asynchronous upload
+};
+JST_REGISTER_MODULE(FilterTapsImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+// ---- fm -------------------------------------------------------------------------------------------------------
+// validate / create (coefficients, output shape, axes) are the reference's FmImpl; the per-lane state the reference
+// keeps in host vectors (previousSample, narrowDeemphasisState, stereoState) lives in the b200_fm_plan instead.
+struct FmImplB200 : public FmImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
+    Result create() final {
+        JST_CHECK(FmImpl::create());
+        const Index rank = input.rank();
+        if (input.dtype() != DataType::CF32 || !input.contiguous() || *signalAxes.sample + 1 != rank ||
+            (signalAxes.batch && *signalAxes.batch != 0)) {
+            JST_ERROR("[MODULE_FM_B200] This provider implements contiguous CF32 inputs with the sample axis innermost "
+                      "and the batch axis (if any) outermost.");
+            return Result::ERROR;
+        }
+        frameLength = input.shape(rank - 1);
+        frames = signalAxes.batch ? input.shape(0) : 1;
+        return Result::SUCCESS;
+    }
+    Result computeInitialize() override {
+        const int deemphasisUs = deemphasis == "50us" ? 50 : (deemphasis == "75us" ? 75 : 0);
+        return Check(b200_fm_plan_create(B200Ctx(), laneCount, sampleRate, wideBand ? 1 : 0, deemphasisUs, &plan), "FM");
+    }
+    Result computeSubmit(const cudaStream_t& stream) override {
+        return Check(b200_fm_exec(plan, DevicePtr<b200_cf32>(input), DevicePtr<float>(output), frames, frameLength,
+                                  stream), "FM");
+    }
+    Result computeDeinitialize() override {
+        const auto result = plan ? Check(b200_fm_plan_destroy(plan), "FM") : Result::SUCCESS;
+        plan = nullptr;
+        return result;
+    }
+    b200_fm_plan* plan = nullptr;
+    U64 frames = 1, frameLength = 0;
+};
+JST_REGISTER_MODULE(FmImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+// ---- spectral_chain: the per-cycle part of spectrum_engine as ONE kernel ----------------------------------------
+// Inputs: `buffer` (CF32 or complex integer, sample axis innermost) and `window` (CF32, n taps: the settled
+// window -> invert [-> reshape] output). Output `buffer`: F32, the input's shape and attributes.
+struct SpectralChainImplB200 : public Module::Impl, public DynamicConfig<SpectralChain>,
+                               public NativeCudaRuntimeContext, public Scheduler::Context {
+    Result validate() override {
+        const auto& config = *candidate();
+        if (!inputs().contains("buffer")) {
+            return Result::SUCCESS;
+        }
+        const Tensor& tensor = inputs().at("buffer").tensor;
+        if (!tensor.validShape() || tensor.size() == 0) {
+            return Result::SUCCESS;
+        }
+        if (tensor.dtype() != DataType::CF32 && B200::IntegerDtypeCode(tensor.dtype()) < B200_DTYPE_CI8) {
+            JST_ERROR("[MODULE_SPECTRAL_CHAIN_B200] Input must have data type CF32 or a complex integer type.");
+            return Result::ERROR;
+        }
+        SignalAxes axes;
+        if (ResolveSignalAxes(tensor, axes) != Result::SUCCESS || !axes.sample) {
+            JST_ERROR("[MODULE_SPECTRAL_CHAIN_B200] Input signal axis metadata is invalid.");
+            return Result::ERROR;
+        }
+        if (*axes.sample + 1 != tensor.rank() || !tensor.contiguous()) {
+            JST_ERROR("[MODULE_SPECTRAL_CHAIN_B200] The sample axis must be the innermost axis of a contiguous tensor.");
+            return Result::ERROR;
+        }
+        if (config.enableAgc && tensor.shape(tensor.rank() - 1) != 4096) {
+            JST_ERROR("[MODULE_SPECTRAL_CHAIN_B200] The fused AGC stage exists for 4096-point spectra only; wire "
+                      "fft -> agc -> amplitude for other lengths.");
+            return Result::ERROR;
+        }
+        if (enableScale != config.enableScale || enableAgc != config.enableAgc) {
+            return Result::RECREATE;
+        }
+        return Result::SUCCESS;
+    }
+    Result define() override {
+        JST_CHECK(defineTaint(Module::Taint::STATELESS));
+        JST_CHECK(defineInterfaceInput("buffer"));
+        JST_CHECK(defineInterfaceInput("window"));
+        return defineInterfaceOutput("buffer");
+    }
+    Result create() override {
+        input = inputs().at("buffer").tensor;
+        window = inputs().at("window").tensor;
+        n = input.shape(input.rank() - 1);
+        batch = input.size() / n;
+        if (window.dtype() != DataType::CF32 || window.size() != n || !window.contiguous()) {
+            JST_ERROR("[MODULE_SPECTRAL_CHAIN_B200] Window must be a contiguous CF32 tensor with one tap per sample.");
+            return Result::ERROR;
+        }
+        dtypeCode = input.dtype() == DataType::CF32 ? B200_DTYPE_CF32 : B200::IntegerDtypeCode(input.dtype());
+        JST_CHECK(Check(b200_amplitude_scaling_coeff(n, &amplitudeCoeff), "SPECTRAL_CHAIN"));
+        JST_CHECK(Check(b200_range_coefficients(rangeMin, rangeMax, &scalingCoeff, &offsetCoeff), "SPECTRAL_CHAIN"));
+        JST_CHECK(output.create(input.device(), DataType::F32, input.shape()));
+        JST_CHECK(output.propagateAttributes(input));
+        outputs()["buffer"].produced(name(), "buffer", output);
+        return Result::SUCCESS;
+    }
+    Result reconfigure() override {     // range limits change in place, like RangeImpl::reconfigure
+        const auto& config = *candidate();
+        if (config.enableScale != enableScale || config.enableAgc != enableAgc) {
+            return Result::RECREATE;
+        }
+        rangeMin = config.rangeMin;
+        rangeMax = config.rangeMax;
+        agcReference = config.agcReference;
+        agcEpsilon = config.agcEpsilon;
+        agcMinGain = config.agcMinGain;
+        agcMaxGain = config.agcMaxGain;
+        return Check(b200_range_coefficients(rangeMin, rangeMax, &scalingCoeff, &offsetCoeff), "SPECTRAL_CHAIN");
+    }
+    Result computeSubmit(const cudaStream_t& stream) override {
+        if (!plan) {
+            // The window is a STATIC_OUTPUT tensor produced earlier in this first cycle on this stream: wait for it
+            // once, then the plan captures it (real part only when the imaginary part is identically zero).
+            if (cudaStreamSynchronize(stream) != cudaSuccess) {
+                JST_ERROR("[MODULE_SPECTRAL_CHAIN_B200] Can't synchronize the stream before capturing the window.");
+                return Result::ERROR;
+            }
+            JST_CHECK(Check(b200_chain_plan_create(B200Ctx(), n, batch, DevicePtr<b200_cf32>(window), &plan),
+                            "SPECTRAL_CHAIN"));
+        }
+        if (enableAgc) {
+            return Check(b200_chain_exec_agc(plan, DevicePtr<void>(input), dtypeCode, DevicePtr<float>(output), batch,
+                                             amplitudeCoeff, enableScale ? 1 : 0, scalingCoeff, offsetCoeff,
+                                             agcReference, agcEpsilon, agcMinGain, agcMaxGain, stream), "SPECTRAL_CHAIN");
+        }
+        return Check(b200_chain_exec_typed(plan, DevicePtr<void>(input), dtypeCode, DevicePtr<float>(output), batch,
+                                           amplitudeCoeff, enableScale ? 1 : 0, scalingCoeff, offsetCoeff, stream),
+                     "SPECTRAL_CHAIN");
+    }
+    Result computeDeinitialize() override {
+        const auto result = plan ? Check(b200_chain_plan_destroy(plan), "SPECTRAL_CHAIN") : Result::SUCCESS;
+        plan = nullptr;
+        return result;
+    }
+    Tensor input, window, output;
+    U64 n = 0, batch = 0;
+    int dtypeCode = B200_DTYPE_CF32;
+    float amplitudeCoeff = 0.0f, scalingCoeff = 0.0f, offsetCoeff = 0.0f;
+    b200_chain_plan* plan = nullptr;
+};
+JST_REGISTER_MODULE(SpectralChainImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+// ---- fir_filter: the per-cycle part of the filter block as ONE streaming (decimating, multi-head) FIR kernel ----
+// Inputs: `signal` CF32 [T] or [B, T] (sample axis innermost), `coeffs` CF32 [heads, taps] (settled filter_taps
+// output). Output `buffer`: [.., heads, T / R], channelAxis = the old sample axis, sampleAxis = +1 — what the
+// reference block publishes (src/domains/dsp/filter/block_impl.cc:250-262,571-577).
+// With a batch axis the B rows are consecutive frames of ONE stream (overlap_add carries frame k's tail into frame
+// k+1, overlap_add/module_impl_native_cpu.cc:155-174); without one they are independent lanes, each with its own
+// tail across cycles (:176-198) — one plan per lane here.
+struct FirFilterImplB200 : public Module::Impl, public DynamicConfig<FirFilter>, public NativeCudaRuntimeContext,
+                           public Scheduler::Context {
+    static constexpr U64 kMaxLanes = 256;
+
+    Result validate() override {
+        const auto& config = *candidate();
+        validatedAxes = {};
+        if (config.decimation == 0) {
+            JST_ERROR("[MODULE_FIR_FILTER_B200] Decimation must be at least 1.");
+            return Result::ERROR;
+        }
+        if (!inputs().contains("signal")) {
+            return Result::SUCCESS;
+        }
+        const Tensor& tensor = inputs().at("signal").tensor;
+        if (!tensor.validShape() || tensor.size() == 0) {
+            return Result::SUCCESS;
+        }
+        if (tensor.dtype() != DataType::CF32) {
+            JST_ERROR("[MODULE_FIR_FILTER_B200] Signal input must be CF32.");
+            return Result::ERROR;
+        }
+        if (ResolveSignalAxes(tensor, validatedAxes) != Result::SUCCESS || !validatedAxes.sample) {
+            JST_ERROR("[BLOCK_FILTER] Signal axis metadata is invalid.");
+            return Result::ERROR;
+        }
+        if (validatedAxes.channel) {
+            JST_ERROR("[BLOCK_FILTER] Signal already has channelAxis. Generated filter channels cannot be nested.");
+            return Result::ERROR;
+        }
+        const Index rank = tensor.rank();
+        const bool layoutOk = tensor.contiguous() && *validatedAxes.sample + 1 == rank &&
+                              (rank == 1 || (rank == 2 && (!validatedAxes.batch || *validatedAxes.batch == 0)));
+        if (!layoutOk) {
+            JST_ERROR("[MODULE_FIR_FILTER_B200] Supported layouts: contiguous [T] or [rows, T] with the sample axis "
+                      "innermost.");
+            return Result::ERROR;
+        }
+        if (tensor.shape(rank - 1) % config.decimation != 0) {
+            JST_ERROR("[MODULE_FIR_FILTER_B200] Frame length must be a multiple of the decimation.");
+            return Result::ERROR;
+        }
+        if (rank == 2 && !validatedAxes.batch && tensor.shape(0) > kMaxLanes) {
+            JST_ERROR("[MODULE_FIR_FILTER_B200] At most {} independent lanes (rows without a batchAxis).", kMaxLanes);
+            return Result::ERROR;
+        }
+        if (config.decimation != decimation || config.centerBins != centerBins) {
+            return Result::RECREATE;
+        }
+        return Result::SUCCESS;
+    }
+    Result define() override {
+        JST_CHECK(defineInterfaceInput("signal"));
+        JST_CHECK(defineInterfaceInput("coeffs"));
+        return defineInterfaceOutput("buffer");
+    }
+    Result create() override {
+        input = inputs().at("signal").tensor;
+        coeffs = inputs().at("coeffs").tensor;
+        if (coeffs.dtype() != DataType::CF32 || coeffs.rank() != 2 || !coeffs.contiguous()) {
+            JST_ERROR("[MODULE_FIR_FILTER_B200] Coefficients must be a contiguous CF32 [heads, taps] tensor.");
+            return Result::ERROR;
+        }
+        heads = coeffs.shape(0);
+        taps = coeffs.shape(1);
+        const Index rank = input.rank();
+        const Index sampleAxis = rank - 1;
+        frameLength = input.shape(sampleAxis);
+        const U64 rows = input.size() / frameLength;
+        lanes = (rank == 2 && !validatedAxes.batch) ? rows : 1;
+        frames = lanes > 1 ? 1 : rows;
+        Shape outputShape = input.shape();
+        outputShape[sampleAxis] = heads;
+        outputShape.push_back(frameLength / decimation);
+        JST_CHECK(output.create(input.device(), DataType::CF32, outputShape));
+        JST_CHECK(output.propagateAttributes(input));
+        SignalAxes outputAxes;
+        outputAxes.sample = sampleAxis + 1;
+        outputAxes.channel = sampleAxis;
+        if (validatedAxes.batch) {
+            outputAxes.batch = *validatedAxes.batch >= sampleAxis ? *validatedAxes.batch + 1 : *validatedAxes.batch;
+        }
+        JST_CHECK(SetSignalAxes(output, outputAxes));
+        outputs()["buffer"].produced(name(), "buffer", output);
+        return Result::SUCCESS;
+    }
+    Result createPlans(const cudaStream_t& stream) {
+        // The taps are a STATIC_OUTPUT tensor uploaded earlier in this first cycle on this stream.
+        std::vector<b200_cf32> host(heads * taps);
+        JST_CHECK(Check(b200_memcpy(B200Ctx(), host.data(), DevicePtr<void>(coeffs), host.size() * sizeof(b200_cf32), 1,
+                                    stream), "FIR_FILTER"));
+        JST_CHECK(Check(b200_stream_synchronize(B200Ctx(), stream), "FIR_FILTER"));
+        bool translate = false;
+        std::vector<int64_t> bins(heads, 0);
+        for (U64 head = 0; head < heads && head < centerBins.size(); ++head) {
+            bins[head] = static_cast<int64_t>(std::llround(centerBins[head]));
+            translate = translate || bins[head] != 0;
+        }
+        plans.assign(lanes, nullptr);
+        for (auto& plan : plans) {
+            JST_CHECK(Check(b200_fir_plan_create(B200Ctx(), host.data(), taps, heads, decimation, &plan), "FIR_FILTER"));
+            if (translate) {
+                JST_CHECK(Check(b200_fir_plan_set_translation(plan, frameLength, bins.data()), "FIR_FILTER"));
+            }
+        }
+        return Result::SUCCESS;
+    }
+    Result computeSubmit(const cudaStream_t& stream) override {
+        if (plans.empty()) {
+            const auto result = createPlans(stream);
+            if (result != Result::SUCCESS) {
+                computeDeinitialize();
+                return result;
+            }
+        }
+        const auto* x = DevicePtr<b200_cf32>(input);
+        auto* y = DevicePtr<b200_cf32>(output);
+        const U64 outputRow = heads * (frameLength / decimation);
+        for (U64 lane = 0; lane < lanes; ++lane) {
+            JST_CHECK(Check(b200_fir_exec(plans[lane], x + lane * frameLength, y + lane * outputRow, frames, frameLength,
+                                          stream), "FIR_FILTER"));
+        }
+        return Result::SUCCESS;
+    }
+    Result computeDeinitialize() override {
+        Result result = Result::SUCCESS;
+        for (auto* plan : plans) {
+            if (plan && b200_fir_plan_destroy(plan) != B200_SUCCESS) {
+                result = Result::ERROR;
+            }
+        }
+        plans.clear();
+        return result;
+    }
+    Tensor input, coeffs, output;
+    SignalAxes validatedAxes;
+    U64 heads = 0, taps = 0, frameLength = 0, frames = 0, lanes = 1;
+    std::vector<b200_fir_plan*> plans;
+};
+JST_REGISTER_MODULE(FirFilterImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
 
 }  // namespace Jetstream::Modules

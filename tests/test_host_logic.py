@@ -220,3 +220,60 @@ def test_spectral_chain_accepts_integer_input_and_limits_fused_agc():
     real = tensor((3, 4096), dtype=np.float32, sampleAxis=1, batchAxis=0)
     m = build_module("spectral_chain")
     assert m.create("s", None, {"buffer": link(real), "window": link(win)}) == cb.Result.ERROR
+
+
+# ---- round 2: ADVICE r01 fixes ------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("mtype,port,config", [("invert", "signal", None), ("agc", "signal", None),
+                                                ("fm", "signal", {"mode": "narrow"})])
+def test_empty_inputs_return_a_result_not_an_exception(mtype, port, config):
+    """validate() must tolerate empty inputs (docs/blocks-and-modules.md:182-186); create on a size-0 tensor then
+    has to return a Result (it raised AttributeError before) and compute is a no-op."""
+    m = build_module(mtype)
+    x = tensor((0, 64), sampleAxis=1, batchAxis=0)
+    assert m.create("m", config, {port: link(x)}) == cb.Result.SUCCESS, cb.last_error()
+    assert m.outputs["signal"].tensor.shape[:2] == (0, 64)
+    assert m.compute_submit(None) == cb.Result.SUCCESS
+
+
+def test_fir_filter_rows_without_batch_axis_are_lanes():
+    """[B, T] with sampleAxis only: B independent lanes (overlap_add/module_impl_native_cpu.cc:176-198), one carried
+    history per lane; with batchAxis = 0 the rows are consecutive frames of one stream."""
+    coeffs = tensor((2, 33), sampleAxis=1, channelAxis=0)
+    m = build_module("fir_filter")
+    assert m.create("f", {"decimation": 4}, {"signal": link(tensor((6, 256), sampleAxis=1)),
+                                             "coeffs": link(coeffs)}) == cb.Result.SUCCESS, cb.last_error()
+    assert (m._lanes, m._frames) == (6, 1)
+    out = m.outputs["buffer"].tensor
+    assert out.shape == (6, 2, 64) and not out.has_attribute("batchAxis")
+    assert out.attribute("channelAxis") == 1 and out.attribute("sampleAxis") == 2
+    m = build_module("fir_filter")
+    assert m.create("f", {"decimation": 4}, {"signal": link(tensor((6, 256), sampleAxis=1, batchAxis=0)),
+                                             "coeffs": link(coeffs)}) == cb.Result.SUCCESS
+    assert (m._lanes, m._frames) == (1, 6)
+    m = build_module("fir_filter")
+    assert m.create("f", None, {"signal": link(tensor((300, 64), sampleAxis=1)),
+                                "coeffs": link(coeffs)}) == cb.Result.ERROR
+    assert "independent lanes" in cb.last_error()
+
+
+def test_block_destroy_on_a_shared_scheduler_keeps_the_other_block_running():
+    from cyberether_b200.jetstream import SynchronousScheduler
+    sched = SynchronousScheduler("cpu")
+    a, b = FmBlock(), FmBlock()
+    x = tensor((4, 128), sampleAxis=1, batchAxis=0)
+    assert a.create("a", {"signal": x}, scheduler=sched) == cb.Result.SUCCESS
+    assert b.create("b", {"signal": x}, scheduler=sched) == cb.Result.SUCCESS
+    assert [m.name for m in sched.order] == ["a:fm", "b:fm"]
+    assert a.destroy() == cb.Result.SUCCESS
+    assert [m.name for m in sched.order] == ["b:fm"] and set(sched.modules) == {"b:fm"}
+    assert sched.runtime is not None and [m.name for m in sched.runtime.modules] == ["b:fm"]
+
+
+def test_fir_halo_rejects_slabs_shorter_than_the_halo():
+    import torch
+    from cyberether_b200.sharding import exchange_fir_halo
+    with pytest.raises(ValueError, match="shorter than"):
+        exchange_fir_halo(torch.zeros(1, 64, dtype=torch.complex64), taps=129)
+    halo = exchange_fir_halo(torch.arange(256, dtype=torch.float32).reshape(2, 128), taps=129)
+    assert halo.shape == (128,) and torch.equal(halo.own_tail, torch.arange(128, 256, dtype=torch.float32))
