@@ -61,6 +61,13 @@ SIGNATURES = {
     "b200_chain_exec_typed": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_vp]),
     "b200_chain_exec_agc": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_f64, c_f64, c_f64, c_f64,
                                     c_vp]),
+    "b200_chain_exec_colsum": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_vp, c_vp]),
+    "b200_lineplot_scratch_bytes": (c_int, [c_u64, c_u64, c_u64, P(c_u64)]),
+    "b200_lineplot_init": (c_int, [c_vp, c_vp, c_vp, c_u64, c_vp]),
+    "b200_lineplot_update": (c_int, [c_vp, c_vp, c_u64, c_u64, c_u64, c_u64, c_u64, c_f32, c_u64, c_vp, c_vp, c_vp, c_vp]),
+    "b200_lineplot_update_from_colsum": (c_int, [c_vp, c_vp, c_u64, c_u64, c_f32, c_u64, c_vp, c_vp, c_vp]),
+    "b200_waterfall_update": (c_int, [c_vp, c_vp, c_u64, c_u64, c_u64, c_u64, c_vp, c_u64, c_u64, c_vp]),
+    "b200_waterfall_advance": (c_int, [P(c_u64), c_u64, c_u64]),
     "b200_chain_exec_host": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_u64]),
     "b200_chain_plan_destroy": (c_int, [c_vp]),
     "b200_chain_plan_variant": (ctypes.c_char_p, [c_vp]),

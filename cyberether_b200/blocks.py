@@ -98,7 +98,10 @@ class Block:
 class SpectrumEngine(Block):
     """`spectrum_engine` — include/jetstream/domains/dsp/spectrum_engine/block.hh:8-16."""
     TYPE = "spectrum_engine"
-    DEFAULTS = {"enableAgc": False, "enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0, "fused": True}
+    # publishColumnSums (b200 only): the fused kernel also emits sum-over-batch of every output column for a downstream
+    # `lineplot` on this provider (jetstream.SpectralChain.COLUMN_SUMS_ATTRIBUTE)
+    DEFAULTS = {"enableAgc": False, "enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0, "fused": True,
+                "publishColumnSums": False}
 
     def create_impl(self) -> Result:
         port = self.inputs.get("buffer")
@@ -133,7 +136,8 @@ class SpectrumEngine(Block):
                                    {"enableScale": bool(self.config["enableScale"]),
                                     "rangeMin": float(self.config["rangeMin"]),
                                     "rangeMax": float(self.config["rangeMax"]),
-                                    "enableAgc": bool(self.config["enableAgc"])},
+                                    "enableAgc": bool(self.config["enableAgc"]),
+                                    "publishColumnSums": bool(self.config["publishColumnSums"])},
                                    {"buffer": complex_input, "window": self.module_get_output("invert", "signal")})
             if r != Result.SUCCESS:
                 return r
@@ -262,3 +266,38 @@ class FmBlock(Block):
         if result != Result.SUCCESS:
             return result
         return self.module_expose_output("signal", "fm", "signal")
+
+
+class LineplotBlock(Block):
+    """`lineplot` block — src/domains/visualization/lineplot/block_impl.cc: one `lineplot` module (compute half)."""
+    TYPE = "lineplot"
+    DEFAULTS = {"averaging": 1, "decimation": 1, "numberOfVerticalLines": 11, "numberOfHorizontalLines": 5,
+                "thickness": 1.0}
+
+    def create_impl(self) -> Result:
+        port = self.inputs.get("signal")
+        if port is None or not port.resolved():
+            return Result.INCOMPLETE
+        return self.module_create("lineplot", "lineplot", dict(self.config), {"signal": port})
+
+    def signal_points(self):
+        return self.modules["lineplot"].signal_points()
+
+
+class WaterfallBlock(Block):
+    """`waterfall` block — src/domains/visualization/waterfall/block_impl.cc: one `waterfall` module (compute half)."""
+    TYPE = "waterfall"
+    DEFAULTS = {"height": 512, "interpolate": True}
+
+    def create_impl(self) -> Result:
+        port = self.inputs.get("signal")
+        if port is None or not port.resolved():
+            return Result.INCOMPLETE
+        return self.module_create("waterfall", "waterfall", dict(self.config), {"signal": port})
+
+    def frequency_bins(self):
+        return self.modules["waterfall"].frequency_bins()
+
+    @property
+    def write_index(self) -> int:
+        return self.modules["waterfall"].write_index

@@ -176,9 +176,9 @@ static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_
 }
 
 // Fused complex-integer ingest (cast -> window -> fft -> [agc] -> amplitude -> range in one kernel), real window only.
-template <int MODE, int ITYPE, bool AGC = false>
-static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
-    auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE, AGC>;
+template <int MODE, int ITYPE, bool AGC = false, bool COLSUM = false>
+static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream, unsigned* grid_out = nullptr) {
+    auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE, AGC, COLSUM>;
     constexpr int smem = ITYPE == IN_CF32 ? fft4096_smem_bytes(2) : fft4096_int_smem_bytes(ITYPE);
     static bool configured[64] = {};
     if (!configured[ctx->device & 63]) {
@@ -187,6 +187,9 @@ static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t
     }
     const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
     const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
+    if (grid_out) {
+        *grid_out = grid;
+    }
     kernel<<<grid, kFft4096Threads, smem, stream>>>(p);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
@@ -444,6 +447,14 @@ __global__ void pointwise_rowbcast_mul_kernel(float2* __restrict__ data, const f
 
 }  // namespace b200
 
+namespace b200 {
+// viz.cu: row-split column sums of a [batches, columns] F32 matrix (the lineplot consumer's batch sum)
+int colsum_partials(b200_ctx* ctx, const float* in, uint64_t batches, uint64_t columns, uint64_t batch_stride,
+                    uint64_t col_stride, float* partial, uint64_t* splits_out, cudaStream_t s);
+int colsum_reduce(const float* partial, uint64_t splits, uint64_t n, float* out, cudaStream_t s);
+uint64_t colsum_max_splits(uint64_t batches);
+}  // namespace b200
+
 struct b200_chain_plan {
     b200_ctx* ctx;
     uint64_t n;
@@ -457,6 +468,8 @@ struct b200_chain_plan {
     float2* scratch = nullptr;
     float2* cast_scratch = nullptr;   // typed input without a fused path: cast -> CF32 here, then the CF32 chain
     uint64_t cast_rows = 0;
+    float* colsum_partial = nullptr;  // b200_chain_exec_colsum: per-CTA (fused) or per-split (fallback) partial sums
+    uint64_t colsum_bytes = 0;
     // Host-buffer pipeline (b200_chain_exec_host): kHostSlots device staging slots, three streams.
     static constexpr int kHostSlots = 3;
     uint64_t host_chunk_rows = 0;
@@ -946,6 +959,64 @@ int b200_chain_exec_agc(b200_chain_plan* plan, const void* x, int in_dtype, floa
 #undef B200_AGC_DISPATCH
 }
 
+// spectrum_engine -> lineplot in one pass: the chain output AND its column sums (sum over the batch of every output
+// column = what LineplotImplNativeCpu::computeSubmit accumulates first, lineplot/module_impl_native_cpu.cc:93-98).
+// n = 4096 with a real window: the kernel's epilogue keeps the running sums of its rows in registers (COLSUM variant of
+// fft4096_kernel, +8 FADD2 per thread-row, no extra pass over the 1 GiB output); everything else: the normal chain
+// followed by the row-split column-sum kernel of viz.cu.
+int b200_chain_exec_colsum(b200_chain_plan* plan, const void* x, int in_dtype, float* out, uint64_t batch, float amp_coeff,
+                           int enable_range, float scale, float offset, float* colsum, b200_stream stream) {
+    B200_REQUIRE(plan && colsum, "b200_chain_exec_colsum: null argument");
+    B200_REQUIRE(in_dtype == B200_DTYPE_CF32 || (in_dtype >= B200_DTYPE_CI8 && in_dtype <= B200_DTYPE_CU32),
+                 "b200_chain_exec_colsum: input dtype code %d is not CF32 or a complex integer type", in_dtype);
+    DeviceGuard guard(plan->ctx);
+    const cudaStream_t s = as_stream(stream);
+    const uint64_t n = plan->n;
+    if (batch == 0) {
+        B200_CUDA_CHECK(cudaMemsetAsync(colsum, 0, n * sizeof(float), s));
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(x && out, "b200_chain_exec_colsum: null buffer");
+    const bool fused = !plan->composite && n == kFft4096N && plan->win_re != nullptr &&
+                       (in_dtype == B200_DTYPE_CF32 || in_dtype <= B200_DTYPE_CU16) &&
+                       (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && !fft4096_use_generic();
+    const uint64_t fused_bytes = static_cast<uint64_t>(plan->ctx->sms) * 2 * kFft4096N * sizeof(float);
+    const uint64_t need = fused ? fused_bytes : colsum_max_splits(batch) * n * sizeof(float) + 16;
+    if (plan->colsum_bytes < need) {
+        cudaFree(plan->colsum_partial);
+        plan->colsum_partial = nullptr;
+        plan->colsum_bytes = 0;
+        B200_CUDA_CHECK(cudaMalloc(&plan->colsum_partial, need));
+        plan->colsum_bytes = need;
+    }
+    if (!fused) {
+        int rc = b200_chain_exec_typed(plan, x, in_dtype, out, batch, amp_coeff, enable_range, scale, offset, stream);
+        uint64_t splits = 0;
+        rc = rc == B200_SUCCESS ? colsum_partials(plan->ctx, out, batch, n, n, 1, plan->colsum_partial, &splits, s) : rc;
+        return rc == B200_SUCCESS ? colsum_reduce(plan->colsum_partial, splits, n, colsum, s) : rc;
+    }
+    FftParams p{};
+    chain_params(plan, static_cast<const float2*>(x), out, batch, amp_coeff, enable_range, scale, offset, &p);
+    p.colsum_partial = plan->colsum_partial;
+    unsigned grid = 0;
+    int rc = B200_SUCCESS;
+#define B200_COLSUM_DISPATCH(MODE)                                                                                 \
+    switch (in_dtype) {                                                                                            \
+        case B200_DTYPE_CF32: rc = launch_4096_int<MODE, IN_CF32, false, true>(plan->ctx, p, s, &grid); break;     \
+        case B200_DTYPE_CI8: rc = launch_4096_int<MODE, IN_CI8, false, true>(plan->ctx, p, s, &grid); break;       \
+        case B200_DTYPE_CU8: rc = launch_4096_int<MODE, IN_CU8, false, true>(plan->ctx, p, s, &grid); break;       \
+        case B200_DTYPE_CI16: rc = launch_4096_int<MODE, IN_CI16, false, true>(plan->ctx, p, s, &grid); break;     \
+        default: rc = launch_4096_int<MODE, IN_CU16, false, true>(plan->ctx, p, s, &grid); break;                  \
+    }
+    if (enable_range) {
+        B200_COLSUM_DISPATCH(MODE_AMP_RANGE)
+    } else {
+        B200_COLSUM_DISPATCH(MODE_AMP)
+    }
+#undef B200_COLSUM_DISPATCH
+    return rc == B200_SUCCESS ? colsum_reduce(plan->colsum_partial, grid, n, colsum, s) : rc;
+}
+
 int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* out_host, uint64_t batch,
                          float amp_coeff, int enable_range, float scale, float offset, uint64_t chunk_rows) {
     B200_REQUIRE(plan, "b200_chain_exec_host: null plan");
@@ -1028,6 +1099,7 @@ int b200_chain_plan_destroy(b200_chain_plan* plan) {
     cudaFree(plan->win_c);
     cudaFree(plan->scratch);
     cudaFree(plan->cast_scratch);
+    cudaFree(plan->colsum_partial);
     b200_fft_plan_destroy(plan->fft);
     for (int i = 0; i < b200_chain_plan::kHostSlots; ++i) {
         cudaFree(plan->stage_in[i]);

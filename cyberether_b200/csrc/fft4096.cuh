@@ -145,8 +145,9 @@ __device__ __forceinline__ void apply_twiddles(float2 (&v)[16], const TwiddleSet
     }
 }
 
-template <int MODE, int WIN, int CTAS, int ITYPE = IN_CF32, bool AGC = false>
+template <int MODE, int WIN, int CTAS, int ITYPE = IN_CF32, bool AGC = false, bool COLSUM = false>
 __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const FftParams p) {
+    static_assert(!COLSUM || MODE != MODE_C2C, "column sums exist for the amplitude outputs only");
     // AGC: the mean power of the spectrum equals the power of the windowed row (Parseval: sum |X_k|^2 = N sum |x_n w_n|^2),
     // which pass 1 has in registers: per-warp partial sums go to shared memory (double-buffered by row parity; barriers
     // (A) and (C) of the row order them before the epilogue reads them).
@@ -219,6 +220,12 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
     unsigned char* out_ptr = static_cast<unsigned char*>(p.out) +
                              (first * kFft4096N + t) * (MODE == MODE_C2C ? 8 : 4);
     const uint64_t out_step = stride * kFft4096N * (MODE == MODE_C2C ? 8 : 4);
+    // COLSUM: running sums of this CTA's outputs, column t + 256 k in colsum[k / 2].{x, y} (rows in CTA order)
+    float2 colsum[COLSUM ? 8 : 1];
+#pragma unroll
+    for (int k = 0; k < (COLSUM ? 8 : 1); ++k) {
+        colsum[k] = make_float2(0.f, 0.f);
+    }
 
     for (uint32_t i = 0; i < my_rows; ++i) {
         // CF32: the row's landing buffer is also its exchange buffer. Integer input: a separate landing ring, the
@@ -344,6 +351,9 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
                 const float2 r = spectral_epilogue2<MODE, AGC>(v[dft16_pos(k)], v[dft16_pos(k + 1)], p, gain);
                 stg_stream_f1(out + 256 * k, r.x);
                 stg_stream_f1(out + 256 * (k + 1), r.y);
+                if constexpr (COLSUM) {
+                    colsum[k / 2] = __fadd2_rn(colsum[k / 2], r);
+                }
             }
         }
         out_ptr += out_step;
@@ -353,6 +363,14 @@ __global__ void __launch_bounds__(kFft4096Threads, CTAS) fft4096_kernel(const Ff
         if (++stage == kFft4096Stages) {
             stage = 0;
             parity ^= 1;
+        }
+    }
+    if constexpr (COLSUM) {
+        float* const dst = p.colsum_partial + static_cast<uint64_t>(blockIdx.x) * kFft4096N + t;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            dst[256 * k] = colsum[k / 2].x;
+            dst[256 * (k + 1)] = colsum[k / 2].y;
         }
     }
 }

@@ -27,6 +27,10 @@ struct FftParams {
     // Fused AGC (spectrum_engine enableAgc: one RMS tile per spectrum, src/domains/dsp/spectrum_engine/block_impl.cc:186-200):
     // every row is scaled by clamp(reference / sqrt(mean |X|^2 + epsilon), min, max) before the amplitude.
     double agc_reference, agc_epsilon, agc_min, agc_max;
+    // Fused column sums (the lineplot consumer's batch sum, lineplot/module_impl_native_cpu.cc:93-98): every CTA adds
+    // the epilogue results of its rows in registers and writes one [n] partial at the end; colsum_partial is
+    // [gridDim.x, n], reduced in CTA order afterwards (deterministic for a given grid).
+    float* colsum_partial;
 };
 
 // ---- butterflies (forward sign) ------------------------------------------------------------

@@ -1159,11 +1159,17 @@ class SpectralChain(Module):
     DEFAULTS = {"enableScale": False, "rangeMin": -120.0, "rangeMax": 0.0,
                 # enableAgc: spectrum_engine's optional agc stage (one RMS tile per spectrum) inside the same kernel;
                 # the four numbers are the agc module's config (include/jetstream/domains/dsp/agc/module.hh:9-14)
-                "enableAgc": False, "agcReference": 1.0, "agcEpsilon": 1e-12, "agcMinGain": 0.01, "agcMaxGain": 100.0}
+                "enableAgc": False, "agcReference": 1.0, "agcEpsilon": 1e-12, "agcMinGain": 0.01, "agcMaxGain": 100.0,
+                # publishColumnSums: the kernel's epilogue also accumulates sum-over-batch of every output column and
+                # the output tensor carries them as attribute "b200.columnSums" (Tensor [n] F32): a downstream `lineplot`
+                # on this provider then skips its pass over the [batch, n] spectra (b200_chain_exec_colsum).
+                "publishColumnSums": False}
+    COLUMN_SUMS_ATTRIBUTE = "b200.columnSums"
 
     def __init__(self):
         super().__init__()
         self._plan_handle = None
+        self.colsum = None
 
     def validate(self):
         link = self.inputs.get("buffer")
@@ -1199,13 +1205,18 @@ class SpectralChain(Module):
         self.scale, self.offset = range_coefficients(float(self.config["rangeMin"]), float(self.config["rangeMax"]))
         self.output = Tensor.create(self.input.device, "F32", self.input.shape)
         self.output.propagate_attributes(self.input)
+        self.colsum = None
+        if self.config["publishColumnSums"] and not self.config["enableAgc"]:
+            self.colsum = Tensor.create(self.input.device, "F32", (self._n,))
+            self.output.set_attribute(self.COLUMN_SUMS_ATTRIBUTE, self.colsum)
         self.outputs["buffer"] = TensorLink()
         self.outputs["buffer"].produced(self.name, "buffer", self.output)
         return Result.SUCCESS
 
     def reconfigure_impl(self, candidate):
         if bool(candidate["enableScale"]) != bool(self.config["enableScale"]) or \
-                bool(candidate["enableAgc"]) != bool(self.config["enableAgc"]):
+                bool(candidate["enableAgc"]) != bool(self.config["enableAgc"]) or \
+                bool(candidate["publishColumnSums"]) != bool(self.config["publishColumnSums"]):
             return Result.RECREATE
         self.scale, self.offset = range_coefficients(float(candidate["rangeMin"]), float(candidate["rangeMax"]))
         return Result.SUCCESS
@@ -1236,6 +1247,11 @@ class SpectralChain(Module):
                          self.output.ptr(), self._batch, ctypes.c_float(self.amp_coeff), 1 if c["enableScale"] else 0,
                          ctypes.c_float(self.scale), ctypes.c_float(self.offset), float(c["agcReference"]),
                          float(c["agcEpsilon"]), float(c["agcMinGain"]), float(c["agcMaxGain"]), stream)
+        if self.colsum is not None:
+            return _call("b200_chain_exec_colsum", self._plan_handle, self.input.ptr(), DTYPE_CODES[self.input.dtype],
+                         self.output.ptr(), self._batch, ctypes.c_float(self.amp_coeff),
+                         1 if c["enableScale"] else 0, ctypes.c_float(self.scale), ctypes.c_float(self.offset),
+                         self.colsum.ptr(), stream)
         return _call("b200_chain_exec_typed", self._plan_handle, self.input.ptr(), DTYPE_CODES[self.input.dtype],
                      self.output.ptr(), self._batch, ctypes.c_float(self.amp_coeff),
                      1 if c["enableScale"] else 0, ctypes.c_float(self.scale), ctypes.c_float(self.offset),
@@ -1568,6 +1584,194 @@ class Fm(Module):
 
     def destroy(self):
         return self.compute_deinitialize()
+
+
+def _element_layout(tensor: Tensor, tag: str):
+    """Geometry shared by lineplot and waterfall (lineplot/module_impl.cc:95-187, waterfall/module_impl.cc:30-83): the
+    element axis is sampleAxis or channelAxis (not both), every other dimension must be the batch axis.
+    Returns (extent, batches, element_stride, batch_stride) in elements, or a Result on error."""
+    axes = SignalAxes()
+    for name in ("sample", "batch", "channel"):
+        key = name + "Axis"
+        if tensor.has_attribute(key):
+            value = tensor.attribute(key)
+            if not isinstance(value, int) or isinstance(value, bool) or value < 0 or value >= tensor.rank:
+                return _error(f"[{tag}] Input must contain valid signal axis metadata.")
+            setattr(axes, name, value)
+    present = [v for v in (axes.sample, axes.batch, axes.channel) if v is not None]
+    if len(set(present)) != len(present):
+        return _error(f"[{tag}] Input must contain valid signal axis metadata.")
+    if axes.sample is not None and axes.channel is not None:
+        return _error(f"[{tag}] Input cannot contain both sampleAxis and channelAxis.")
+    element = axes.sample if axes.sample is not None else axes.channel
+    if element is None and tensor.rank == 1:
+        element = 0
+    if element is None:
+        return _error(f"[{tag}] Input must contain sampleAxis or channelAxis.")
+    for axis in range(tensor.rank):
+        if axis != element and axis != axes.batch:
+            return _error(f"[{tag}] Unsupported auxiliary input axis {axis}. Every dimension must be the element axis "
+                          "or batchAxis.")
+    strides = tensor.data.stride()
+    return (tensor.shape[element], tensor.shape[axes.batch] if axes.batch is not None else 1, strides[element],
+            strides[axes.batch] if axes.batch is not None else 0)
+
+
+@register_module
+class Lineplot(Module):
+    """`lineplot` compute — src/domains/visualization/lineplot/module_impl.cc:17-187 (validation / geometry) +
+    module_impl_native_cpu.cc:80-122 (computeSubmit: batch sum with decimation -> normalise -> clamp -> EMA). The
+    render half (present) is out of scope; `signal_points()` is the tensor the reference hands to its renderer. When
+    the input carries "b200.columnSums" (a fused spectral_chain upstream) the batch sum is taken from there."""
+    TYPE = "lineplot"
+    DEFAULTS = {"averaging": 1, "decimation": 1, "numberOfVerticalLines": 11, "numberOfHorizontalLines": 5,
+                "thickness": 1.0}
+
+    def validate(self):
+        c = self.config
+        if int(c["decimation"]) == 0:
+            return _error("[MODULE_LINEPLOT] Decimation must be at least 1.")
+        if int(c["averaging"]) == 0:
+            return _error("[MODULE_LINEPLOT] Averaging must be at least 1.")
+        if int(c["numberOfVerticalLines"]) < 2:
+            return _error("[MODULE_LINEPLOT] Number of vertical lines must be at least 2.")
+        if int(c["numberOfHorizontalLines"]) < 2:
+            return _error("[MODULE_LINEPLOT] Number of horizontal lines must be at least 2.")
+        if not math.isfinite(float(c["thickness"])) or float(c["thickness"]) <= 0.0:
+            return _error("[MODULE_LINEPLOT] Thickness must be finite and positive.")
+        self._geometry = None
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        if t.dtype != "F32":
+            return _error(f"[MODULE_LINEPLOT_B200] Unsupported input data type: {t.dtype}.")
+        layout = _element_layout(t, "MODULE_LINEPLOT")
+        if isinstance(layout, Result):
+            return layout
+        extent, batches, es, bs = layout
+        elements = extent // int(c["decimation"])
+        if elements < 2:
+            return _error(f"[MODULE_LINEPLOT] Invalid number of elements ({elements}), need at least 2.")
+        for key in ("frequency", "sampleRate"):
+            if t.has_attribute(key) and not isinstance(t.attribute(key), float):
+                return _error(f"[MODULE_LINEPLOT] Input {key} metadata must have type F32.")
+        self._geometry = (elements, batches, es, bs)
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.SURFACE)
+        return self.define_interface_input("signal")
+
+    def create_impl(self):
+        if self._geometry is None:
+            return _error("[MODULE_LINEPLOT] Input validation plan is unavailable.")
+        self.input = self.inputs["signal"].tensor
+        self.elements, self.batches, self.element_stride, self.batch_stride = self._geometry
+        self.normalization = float(np.float32(1.0) / (np.float32(0.5) * np.float32(self.batches)))
+        dev = self.input.device
+        self.points = Tensor.create(dev, "F32", (self.elements, 2))
+        self.average = Tensor.create(dev, "F32", (self.elements,))
+        need = ctypes.c_uint64()
+        result = _call("b200_lineplot_scratch_bytes", self.batches, self.elements, int(self.config["decimation"]),
+                       ctypes.byref(need))
+        if result != Result.SUCCESS:
+            return result
+        self._scratch = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        self._initialized = False
+        # the fused producer's column sums are usable when the input is its plain row-major [batches, extent] output
+        colsum = self.input.attributes.get(SpectralChain.COLUMN_SUMS_ATTRIBUTE)
+        extent = self.elements * int(self.config["decimation"])
+        self._colsum = colsum if (isinstance(colsum, Tensor) and self.element_stride == 1 and colsum.size >= extent and
+                                  self.batch_stride in (0, colsum.size)) else None
+        return Result.SUCCESS
+
+    def reconfigure_impl(self, candidate):     # module_impl.cc:223-234: only `averaging` changes in place
+        same = all(candidate[k] == self.config[k] for k in ("decimation", "numberOfVerticalLines",
+                                                            "numberOfHorizontalLines", "thickness"))
+        return Result.SUCCESS if same else Result.RECREATE
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.points)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        if not self._initialized:
+            result = _call("b200_lineplot_init", ctx.handle, self.points.ptr(), self.average.ptr(), self.elements, stream)
+            if result != Result.SUCCESS:
+                return result
+            self._initialized = True
+        c = self.config
+        if self._colsum is not None:
+            return _call("b200_lineplot_update_from_colsum", ctx.handle, self._colsum.ptr(), self.elements,
+                         int(c["decimation"]), ctypes.c_float(self.normalization), int(c["averaging"]),
+                         self.average.ptr(), self.points.ptr(), stream)
+        return _call("b200_lineplot_update", ctx.handle, self.input.ptr(), self.batches, self.elements,
+                     self.batch_stride, self.element_stride, int(c["decimation"]), ctypes.c_float(self.normalization),
+                     int(c["averaging"]), self.average.ptr(), self.points.ptr(),
+                     ctypes.c_void_p(self._scratch.data_ptr()), stream)
+
+    def signal_points(self) -> np.ndarray:
+        return self.points.numpy()
+
+
+@register_module
+class Waterfall(Module):
+    """`waterfall` compute — src/domains/visualization/waterfall/module_impl.cc:15-113 (validation / geometry) +
+    module_impl_native_cpu.cc:53-78 and ring_state.hh:18-44 (newest rows into the ring, cursor advance)."""
+    TYPE = "waterfall"
+    DEFAULTS = {"height": 512, "interpolate": True}
+
+    def validate(self):
+        height = int(self.config["height"])
+        if height == 0 or height > 2048:
+            return _error(f"[MODULE_WATERFALL] Invalid height value '{height}', must be between 1 and 2048.")
+        self._geometry = None
+        link = self.inputs.get("signal")
+        if link is None or not link.resolved() or link.tensor.size == 0:
+            return Result.SUCCESS
+        t = link.tensor
+        if t.dtype != "F32":
+            return _error(f"[MODULE_WATERFALL_B200] Unsupported input data type: {t.dtype}.")
+        layout = _element_layout(t, "MODULE_WATERFALL")
+        if isinstance(layout, Result):
+            return layout
+        self._geometry = layout
+        return Result.SUCCESS
+
+    def define(self):
+        self.define_taint(Taint.SURFACE)
+        return self.define_interface_input("signal")
+
+    def create_impl(self):
+        if self._geometry is None:
+            return _error("[MODULE_WATERFALL] Input validation plan is unavailable.")
+        self.input = self.inputs["signal"].tensor
+        self.elements, self.batches, self.element_stride, self.batch_stride = self._geometry
+        self.height = int(self.config["height"])
+        self.ring = Tensor.create(self.input.device, "F32", (self.height, self.elements))
+        self.write_index = 0
+        return Result.SUCCESS
+
+    def reconfigure_impl(self, candidate):     # module_impl.cc:115-124: height -> RECREATE, interpolate in place
+        return Result.RECREATE if int(candidate["height"]) != int(self.config["height"]) else Result.SUCCESS
+
+    def compute_submit(self, stream):
+        err = _require_cuda(self, self.input, self.ring)
+        if err:
+            return err
+        ctx = Context.get(self.input.device)
+        result = _call("b200_waterfall_update", ctx.handle, self.input.ptr(), self.batches, self.elements,
+                       self.batch_stride, self.element_stride, self.ring.ptr(), self.height, self.write_index, stream)
+        if result != Result.SUCCESS:
+            return result
+        cursor = ctypes.c_uint64(self.write_index)
+        result = _call("b200_waterfall_advance", ctypes.byref(cursor), self.batches, self.height)
+        self.write_index = int(cursor.value)
+        return result
+
+    def frequency_bins(self) -> np.ndarray:
+        return self.ring.numpy()
 
 
 # ---------------------------------------------------------------------------------------------

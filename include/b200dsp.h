@@ -204,6 +204,15 @@ int b200_chain_exec_agc(b200_chain_plan* plan, const void* x, int in_dtype, floa
                         int enable_range, float scale, float offset, double agc_reference, double agc_epsilon,
                         double agc_min_gain, double agc_max_gain, b200_stream stream);
 
+/* spectrum_engine -> lineplot without a second pass over the spectra: the chain output AND colsum[n] = sum over the batch
+ * of every output column (the first loop of LineplotImplNativeCpu::computeSubmit,
+ * src/domains/visualization/lineplot/module_impl_native_cpu.cc:93-98). n = 4096 with a real window and CF32 / CI8 / CU8 /
+ * CI16 / CU16 input: the running sums are kept in the kernel's registers (one extra FADD2 per output pair); every other
+ * plan runs the chain and then the row-split column-sum kernel. Reassociated F32 sum (CTA-partial order), reproducible
+ * run to run. Feed colsum to b200_lineplot_update_from_colsum. */
+int b200_chain_exec_colsum(b200_chain_plan* plan, const void* x, int in_dtype, float* out, uint64_t batch, float amp_coeff,
+                           int enable_range, float scale, float offset, float* colsum, b200_stream stream);
+
 /* Same computation for HOST-resident tensors (what the reference's TestContext hands a CUDA module:
  * host memory mapped onto the device, src/testing.cc:136, src/memory/buffer_cuda.cc:188). x_host and
  * out_host should be pinned (b200_host_alloc) for full PCIe rate. The batch is cut into chunks of
@@ -214,6 +223,36 @@ int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* 
 int b200_chain_plan_destroy(b200_chain_plan* plan);
 /* Name of the kernel variant exec() launches for this plan (for logs / profiles). */
 const char* b200_chain_plan_variant(const b200_chain_plan* plan);
+
+/* ---- lineplot / waterfall consumers ------------------------------------------------------------- */
+
+/* lineplot — LineplotImplNativeCpu::computeSubmit, src/domains/visualization/lineplot/module_impl_native_cpu.cc:80-122
+ * (geometry of LineplotImpl::validate, module_impl.cc:95-187; CUDA counterpart module_impl_native_cuda.cc:21-60):
+ *   sum[e]  = sum_b in[b * batch_stride + e * decimation * element_stride]        e < elements = extent / decimation
+ *   amp     = fmin(fmax(sum[e] * normalization - 1, -1), 1)                        normalization = 1 / (0.5 * batches)
+ *   average[e] -= average[e] / averaging;  average[e] += amp / averaging;  points[2 e + 1] = average[e]
+ * `average` [elements] is the module's persistent state, `points` [elements, 2] the signalPoints tensor (x in column 0,
+ * written once by b200_lineplot_init: e * 2.0f / (elements - 1) - 1.0f). Strides in ELEMENTS. The batch sum is a
+ * row-split partial sum + fixed-order reduction (reassociated vs the reference's sequential loop; identical for
+ * batches <= 64). `scratch`: b200_lineplot_scratch_bytes() bytes of device memory. */
+int b200_lineplot_scratch_bytes(uint64_t batches, uint64_t elements, uint64_t decimation, uint64_t* bytes);
+int b200_lineplot_init(b200_ctx* ctx, float* points, float* average, uint64_t elements, b200_stream stream);
+int b200_lineplot_update(b200_ctx* ctx, const float* in, uint64_t batches, uint64_t elements, uint64_t batch_stride,
+                         uint64_t element_stride, uint64_t decimation, float normalization, uint64_t averaging,
+                         float* average, float* points, void* scratch, b200_stream stream);
+/* The same update from column sums that already exist (b200_chain_exec_colsum): colsum is indexed e * decimation. */
+int b200_lineplot_update_from_colsum(b200_ctx* ctx, const float* colsum, uint64_t elements, uint64_t decimation,
+                                     float normalization, uint64_t averaging, float* average, float* points,
+                                     b200_stream stream);
+
+/* waterfall — WaterfallImplNativeCpu::computeSubmit, src/domains/visualization/waterfall/module_impl_native_cpu.cc:53-78
+ * with PlanWaterfallWrite / WaterfallRingState::advance (waterfall/ring_state.hh:18-44): the newest min(batches, height)
+ * input rows go to ring rows (write_index + ...) % height; ring is [height, elements] F32. Bit-exact (a copy).
+ * b200_waterfall_advance is the host-side cursor update the caller applies after each update. */
+int b200_waterfall_update(b200_ctx* ctx, const float* in, uint64_t batches, uint64_t elements, uint64_t batch_stride,
+                          uint64_t element_stride, float* ring, uint64_t height, uint64_t write_index,
+                          b200_stream stream);
+int b200_waterfall_advance(uint64_t* write_index, uint64_t batches, uint64_t height);
 
 /* ---- filter block ---------------------------------------------------------------------------- */
 

@@ -455,3 +455,56 @@ class FmWide:
                         out[f, lane, i, 0], out[f, lane, i, 1] = left, right
                         self._advance(s)
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# lineplot / waterfall consumers
+# ---------------------------------------------------------------------------------------------
+
+class Lineplot:
+    """LineplotImplNativeCpu::computeSubmit, src/domains/visualization/lineplot/module_impl_native_cpu.cc:80-122, with the
+    geometry of LineplotImpl::validate (module_impl.cc:129-187): numberOfElements = extent // decimation,
+    normalizationFactor = 1 / (0.5 * batches). x is [batches, extent] (batch axis first) or [extent]."""
+
+    def __init__(self, extent: int, batches: int = 1, decimation: int = 1, averaging: int = 1):
+        self.n = extent // decimation
+        self.batches, self.decimation, self.averaging = batches, decimation, averaging
+        self.norm = F32(1.0) / F32(F32(0.5) * F32(batches))
+        self.average = np.zeros(self.n, F32)
+        # signalPoints x coordinates (module_impl_native_cpu.cc:66-70): i * 2.0f / (n - 1) - 1.0f
+        i = np.arange(self.n, dtype=F32)
+        self.x = F32(F32(i * F32(2.0)) / F32(self.n - 1)) - F32(1.0)
+
+    def compute(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, F32).reshape(self.batches, -1)
+        sums = np.zeros(self.n, F32)
+        for b in range(self.batches):                                  # :93-98 sequential F32 accumulation over rows
+            sums = (sums + x[b, : self.n * self.decimation: self.decimation]).astype(F32)
+        with np.errstate(invalid="ignore"):
+            amp = np.fmin(np.fmax((sums * self.norm).astype(F32) - F32(1.0), F32(-1.0)), F32(1.0)).astype(F32)   # :105
+        avg = self.average
+        avg = (avg - (avg / F32(self.averaging)).astype(F32)).astype(F32)          # :109
+        avg = (avg + (amp / F32(self.averaging)).astype(F32)).astype(F32)          # :110
+        self.average = avg
+        return np.stack([self.x, avg], axis=1)
+
+
+class Waterfall:
+    """WaterfallImplNativeCpu::computeSubmit (waterfall/module_impl_native_cpu.cc:53-78) with PlanWaterfallWrite /
+    WaterfallRingState::advance (waterfall/ring_state.hh:18-44). ring is [height, n]."""
+
+    def __init__(self, n: int, height: int = 512):
+        self.n, self.height = n, height
+        self.ring = np.zeros((height, n), F32)
+        self.write_index = 0
+
+    def compute(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, F32).reshape(-1, self.n)
+        batches = x.shape[0]
+        retained = min(batches, self.height)
+        source = batches - retained
+        dest = (self.write_index + (source % self.height)) % self.height
+        for row in range(retained):
+            self.ring[(dest + row) % self.height] = x[source + row]
+        self.write_index = (self.write_index + (batches % self.height)) % self.height
+        return self.ring

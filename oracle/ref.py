@@ -246,3 +246,66 @@ def spectrum_engine(x: np.ndarray, enable_scale: bool = True, range_min: float =
     return run_block("spectrum_engine", {"buffer": x},
                      {"enableScale": enable_scale, "rangeMin": range_min, "rangeMax": range_max},
                      "buffer", sample_axis)
+
+
+# ---------------------------------------------------------------------------------------------
+# lineplot / waterfall: the reference modules' computeSubmit() run directly
+# through Registry::BuildModule + Runtime (oracle/ref_driver.cc: jst_ref_viz_*).
+# ---------------------------------------------------------------------------------------------
+
+class VizSession:
+    """One reference `lineplot` or `waterfall` module on a caller-filled F32 input; state (EMA / ring) persists
+    across compute() calls like in the running reference."""
+
+    def __init__(self, type_: str, shape: Sequence[int], config: Optional[dict] = None, sample_axis: int = -1,
+                 batch_axis: int = -1, channel_axis: int = -1):
+        L = lib()
+        L.jst_ref_viz_create.restype = ctypes.c_void_p
+        L.jst_ref_viz_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int,
+                                         ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.c_int64]
+        L.jst_ref_viz_compute.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.jst_ref_viz_reconfigure.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.jst_ref_viz_read.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.jst_ref_viz_read.restype = ctypes.c_int64
+        L.jst_ref_viz_write_index.argtypes = [ctypes.c_void_p]
+        L.jst_ref_viz_write_index.restype = ctypes.c_int64
+        L.jst_ref_viz_destroy.argtypes = [ctypes.c_void_p]
+        self._L, self.type = L, type_
+        arr = (ctypes.c_uint64 * len(shape))(*[int(v) for v in shape])
+        self._h = L.jst_ref_viz_create(type_.encode(), _kv(config), len(shape), arr, sample_axis, batch_axis,
+                                       channel_axis)
+        if not self._h:
+            raise RefError(L.jst_ref_last_error().decode())
+        self.shape = tuple(int(v) for v in shape)
+
+    def compute(self, x: np.ndarray):
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        assert a.shape == self.shape
+        if self._L.jst_ref_viz_compute(self._h, a.ctypes.data_as(ctypes.c_void_p), a.size) != 0:
+            raise RefError(self._L.jst_ref_last_error().decode())
+
+    def reconfigure(self, config: dict):
+        if self._L.jst_ref_viz_reconfigure(self._h, _kv(config)) != 0:
+            raise RefError(self._L.jst_ref_last_error().decode())
+
+    def read(self) -> np.ndarray:
+        """lineplot: signalPoints [n, 2]; waterfall: the ring [height, n]."""
+        n = self._L.jst_ref_viz_read(self._h, None, 0)
+        out = np.empty(n, np.float32)
+        self._L.jst_ref_viz_read(self._h, out.ctypes.data_as(ctypes.c_void_p), n)
+        return out
+
+    def write_index(self) -> int:
+        return int(self._L.jst_ref_viz_write_index(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.jst_ref_viz_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

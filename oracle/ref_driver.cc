@@ -19,6 +19,7 @@
 #include <cstring>
 #include <memory>
 #include <sstream>
+#include <unordered_set>
 #include <string>
 #include <vector>
 
@@ -31,8 +32,12 @@
 #include "jetstream/module.hh"
 #include "jetstream/module_context.hh"
 #include "jetstream/registry.hh"
+#include "jetstream/runtime.hh"
 #include "jetstream/runtime_context_native_cpu.hh"
 #include "jetstream/scheduler_context.hh"
+
+#include "domains/visualization/lineplot/module_impl.hh"
+#include "domains/visualization/waterfall/module_impl.hh"
 
 namespace Jetstream {
 
@@ -397,6 +402,117 @@ int jst_ref_metrics(void* handle, const char* block, char* buffer, uint64_t capa
         buffer[n] = 0;
     }
     return static_cast<int>(text.size());
+}
+
+// ---- lineplot / waterfall: the reference modules driven directly through Registry::BuildModule +
+// Runtime, the way the reference's own module_tests.cc do (lineplot/module_tests.cc:63-94), with their internal
+// state read through Module::getImpl<> (module_tests.cc:25-46). Compute is the reference's module_impl_native_cpu.cc;
+// the non-compute halves are oracle/viz_headless.cc.
+
+namespace {
+
+struct LineplotPeek : Modules::LineplotImpl {
+    static auto points() { return &LineplotPeek::signalPoints; }
+};
+struct WaterfallPeek : Modules::WaterfallImpl {
+    static auto bins() { return &WaterfallPeek::frequencyBins; }
+    static auto ring() { return &WaterfallPeek::ringState; }
+};
+
+struct VizSession {
+    std::string type;
+    Tensor input;
+    std::shared_ptr<Module> module;
+    std::unique_ptr<Runtime> runtime;
+};
+
+}  // namespace
+
+void* jst_ref_viz_create(const char* type, const char* config, int rank, const uint64_t* shape, int64_t sampleAxis,
+                         int64_t batchAxis, int64_t channelAxis) {
+    auto v = std::make_unique<VizSession>();
+    v->type = type;
+    Shape dims(shape, shape + rank);
+    if (v->input.create(DeviceType::CPU, DataType::F32, dims) != Result::SUCCESS) {
+        Fail("viz input", Result::ERROR);
+        return nullptr;
+    }
+    if (sampleAxis >= 0) v->input.setAttribute("sampleAxis", Index{static_cast<U64>(sampleAxis)});
+    if (batchAxis >= 0) v->input.setAttribute("batchAxis", Index{static_cast<U64>(batchAxis)});
+    if (channelAxis >= 0) v->input.setAttribute("channelAxis", Index{static_cast<U64>(channelAxis)});
+    TensorMap inputs;
+    inputs["signal"].requested("source", "signal");
+    inputs["signal"].tensor = v->input;
+    auto result = Registry::BuildModule(type, DeviceType::CPU, RuntimeType::NATIVE, "generic", v->module);
+    if (result == Result::SUCCESS) {
+        result = v->module->create(type, ParseKv(config), inputs);
+    }
+    if (result != Result::SUCCESS) {
+        Fail(std::string("viz create ") + type, result);
+        return nullptr;
+    }
+    v->runtime = std::make_unique<Runtime>(type, DeviceType::CPU, RuntimeType::NATIVE);
+    result = v->runtime->create({{type, v->module}});
+    if (result != Result::SUCCESS) {
+        Fail("viz runtime", result);
+        return nullptr;
+    }
+    return v.release();
+}
+
+int jst_ref_viz_compute(void* handle, const float* data, uint64_t count) {
+    auto* v = static_cast<VizSession*>(handle);
+    if (count != v->input.size()) {
+        g_error = "viz_compute: size mismatch";
+        return -1;
+    }
+    std::memcpy(v->input.data(), data, count * sizeof(float));
+    std::unordered_set<std::string> skipped, failed;
+    const auto result = v->runtime->compute({}, skipped, failed);
+    return result == Result::SUCCESS ? 0 : Fail("viz compute", result);
+}
+
+int jst_ref_viz_reconfigure(void* handle, const char* config) {
+    auto* v = static_cast<VizSession*>(handle);
+    const auto result = v->module->reconfigure(ParseKv(config));
+    return result == Result::SUCCESS ? 0 : Fail("viz reconfigure", result);
+}
+
+// lineplot: signalPoints [n, 2] (x, averaged amplitude); waterfall: frequencyBins [height, n] ring. Returns the
+// element count; copies min(count, capacity) floats.
+int64_t jst_ref_viz_read(void* handle, float* dst, uint64_t capacity) {
+    auto* v = static_cast<VizSession*>(handle);
+    const Tensor* tensor = nullptr;
+    if (v->type == "lineplot") {
+        const auto* impl = v->module->getImpl<Modules::LineplotImpl>();
+        tensor = impl ? &(impl->*LineplotPeek::points()) : nullptr;
+    } else {
+        const auto* impl = v->module->getImpl<Modules::WaterfallImpl>();
+        tensor = impl ? &(impl->*WaterfallPeek::bins()) : nullptr;
+    }
+    if (!tensor) {
+        g_error = "viz_read: implementation unavailable";
+        return -1;
+    }
+    const uint64_t n = std::min<uint64_t>(capacity, tensor->size());
+    std::memcpy(dst, tensor->data(), n * sizeof(float));
+    return static_cast<int64_t>(tensor->size());
+}
+
+int64_t jst_ref_viz_write_index(void* handle) {
+    auto* v = static_cast<VizSession*>(handle);
+    const auto* impl = v->module->getImpl<Modules::WaterfallImpl>();
+    return impl ? static_cast<int64_t>((impl->*WaterfallPeek::ring()).writeIndex) : -1;
+}
+
+void jst_ref_viz_destroy(void* handle) {
+    auto* v = static_cast<VizSession*>(handle);
+    if (!v) {
+        return;
+    }
+    (void)v->runtime->destroy();
+    (void)v->module->destroy();
+    delete v;
 }
 
 }  // extern "C"

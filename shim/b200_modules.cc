@@ -336,9 +336,6 @@ struct SpectralChainImplB200 : public Module::Impl, public DynamicConfig<Spectra
                       "fft -> agc -> amplitude for other lengths.");
             return Result::ERROR;
         }
-        if (enableScale != config.enableScale || enableAgc != config.enableAgc) {
-            return Result::RECREATE;
-        }
         return Result::SUCCESS;
     }
     Result define() override {
@@ -462,9 +459,6 @@ struct FirFilterImplB200 : public Module::Impl, public DynamicConfig<FirFilter>,
         if (rank == 2 && !validatedAxes.batch && tensor.shape(0) > kMaxLanes) {
             JST_ERROR("[MODULE_FIR_FILTER_B200] At most {} independent lanes (rows without a batchAxis).", kMaxLanes);
             return Result::ERROR;
-        }
-        if (config.decimation != decimation || config.centerBins != centerBins) {
-            return Result::RECREATE;
         }
         return Result::SUCCESS;
     }

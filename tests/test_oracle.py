@@ -212,3 +212,91 @@ def test_port_fm_wide_matches_reference(ref, deemphasis):
             assert np.array_equal(np.isnan(got), np.isnan(want))
             m = ~np.isnan(want)
             assert np.abs(got[m] - want[m]).max() <= 2e-5
+
+
+# ---- lineplot / waterfall consumers — port.py pinned to the reference's own compute TUs ----------------
+
+def test_lineplot_port_matches_reference_module_and_known_answers(ref):
+    """Known answers of src/domains/visualization/lineplot/module_tests.cc: -inf input stays finite after the clamp
+    (:363-425), a later finite frame raises the average, 2.0 saturates at <= 1; decimation indexes with the ORIGINAL
+    row width (:438-457: sums 11 and 33)."""
+    from oracle import port
+    with ref.VizSession("lineplot", (2, 4), {"averaging": 2}, sample_axis=1, batch_axis=0) as v:
+        p = port.Lineplot(4, batches=2, averaging=2)
+        v.compute(np.full((2, 4), -np.inf, np.float32))
+        first = v.read().reshape(-1, 2)
+        assert np.all(np.isfinite(first)) and np.array_equal(first, p.compute(np.full((2, 4), -np.inf, np.float32)))
+        assert np.array_equal(first[:, 1], np.full(4, -0.5, np.float32))          # clamp(-inf) = -1, EMA over 2
+        v.compute(np.ones((2, 4), np.float32))
+        second = v.read().reshape(-1, 2)
+        assert np.array_equal(second, p.compute(np.ones((2, 4), np.float32))) and np.all(second[:, 1] > first[:, 1])
+        v.compute(np.full((2, 4), 2.0, np.float32))
+        third = v.read().reshape(-1, 2)
+        assert np.array_equal(third, p.compute(np.full((2, 4), 2.0, np.float32))) and np.all(third[:, 1] <= 1.0)
+    x = np.array([[1, 2, 3, 4, 5], [10, 20, 30, 40, 50]], np.float32)
+    with ref.VizSession("lineplot", (2, 5), {"decimation": 2}, sample_axis=1, batch_axis=0) as v:
+        v.compute(x)
+        got = v.read().reshape(-1, 2)
+    # sums 11, 33 -> amplitude = clamp(sum * (1 / (0.5 * 2)) - 1, -1, 1) = 1, 1
+    assert np.array_equal(got[:, 1], np.array([1.0, 1.0], np.float32))
+    assert np.array_equal(got, port.Lineplot(5, batches=2, decimation=2).compute(x))
+
+
+@pytest.mark.parametrize("shape,dec,avg", [((64, 4096), 1, 1), ((64, 4096), 4, 8), ((7, 1000), 3, 2), ((1, 256), 1, 4)])
+def test_lineplot_port_random_cycles(ref, shape, dec, avg):
+    from oracle import port
+    rng = np.random.default_rng(1)
+    p = port.Lineplot(shape[1], batches=shape[0], decimation=dec, averaging=avg)
+    with ref.VizSession("lineplot", shape, {"decimation": dec, "averaging": avg}, sample_axis=1, batch_axis=0) as v:
+        for _ in range(4):
+            x = rng.uniform(0.0, 1.2, shape).astype(np.float32)
+            v.compute(x)
+            assert np.array_equal(v.read().reshape(-1, 2), p.compute(x))
+
+
+def test_lineplot_sample_and_channel_layouts_are_equivalent(ref):
+    """lineplot/module_tests.cc:459-518: [2, 4] batch-leading == [4, 2] batch-trailing, sample or channel axis."""
+    lead = np.array([[0.1, 0.2, 0.3, 0.4], [0.2, 0.2, 0.2, 0.2]], np.float32)
+    outs = []
+    for use_channel in (False, True):
+        kw = {"channel_axis": 1} if use_channel else {"sample_axis": 1}
+        with ref.VizSession("lineplot", (2, 4), None, batch_axis=0, **kw) as v:
+            v.compute(lead)
+            outs.append(v.read())
+        kw = {"channel_axis": 0} if use_channel else {"sample_axis": 0}
+        with ref.VizSession("lineplot", (4, 2), None, batch_axis=1, **kw) as v:
+            v.compute(np.ascontiguousarray(lead.T))
+            outs.append(v.read())
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+
+
+def test_waterfall_port_matches_reference_ring(ref):
+    """waterfall/module_tests.cc:186-217 (newest rows retained for arbitrary batch counts, height 5) and :262-333
+    (2 * height + 2 batches twice: the cursor advances by batches % height)."""
+    from oracle import port
+    height, n = 5, 3
+    p = port.Waterfall(n, height)
+    next_value = 1.0
+    sessions = {}
+    for batches in (1, 5, 6, 10, 13, 3):
+        x = (next_value + np.arange(batches * n, dtype=np.float32)).reshape(batches, n)
+        next_value += batches * n
+        # the reference module is created per input shape; the ring + cursor are carried by replaying into a fresh module
+        # is not possible, so each batch count gets its own module fed the same history
+        with ref.VizSession("waterfall", (batches, n), {"height": height}, sample_axis=1, batch_axis=0) as v:
+            q = port.Waterfall(n, height)
+            for _ in range(3):
+                v.compute(x)
+                q.compute(x)
+                assert np.array_equal(v.read().reshape(height, n), q.ring) and v.write_index() == q.write_index
+        p.compute(x)
+    chrono = [p.ring[(p.write_index + r) % height] for r in range(height)]
+    flat = np.concatenate(chrono)
+    assert np.array_equal(flat, next_value - height * n + np.arange(height * n, dtype=np.float32))   # the newest 5 rows, in order
+    x = (1.0 + np.arange(12 * 3, dtype=np.float32)).reshape(12, 3)
+    with ref.VizSession("waterfall", (12, 3), {"height": 5}, sample_axis=1, batch_axis=0) as v:
+        v.compute(x)
+        assert v.write_index() == 2
+        v.compute(x)
+        assert v.write_index() == 4
