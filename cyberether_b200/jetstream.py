@@ -1904,8 +1904,10 @@ class SynchronousScheduler:
     def is_static(self, module: Module) -> bool:
         if module.taint & Taint.STATIC_OUTPUT:
             return True
-        producers = [l.producer[0] for l in module.inputs.values() if l.producer]
-        if not producers or not all(p in self.modules for p in producers):
+        links = list(module.inputs.values())
+        producers = [l.producer[0] for l in links if l.producer]
+        # an input without a producer is a caller-filled tensor: it may change every cycle, so nothing downstream settles
+        if not producers or len(producers) != len(links) or not all(p in self.modules for p in producers):
             return False
         return all(self.is_static(self.modules[p]) for p in producers)
 

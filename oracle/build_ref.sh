@@ -10,6 +10,7 @@
 # Recipe follows SURVEY.md Appendix A.  Usage: oracle/build_ref.sh [-j N]
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(dirname "$HERE")"
 R="${JST_REFERENCE:-/root/reference}"
 OUT="$HERE/_ref"
 B="$OUT/build"
@@ -51,7 +52,7 @@ cat > "$B/gen/jetstream/config.hh" <<'EOF'
 #define JETSTREAM_VIEWPORT_HEADLESS_AVAILABLE
 EOF
 
-INC="-I$B/gen -I$B/fmt_src -I$R/include -I$R/src -I$R/include/jetstream/render/tools -I$HERE/stubs"
+INC="-I$B/gen -I$B/fmt_src -I$R/include -I$R/src -I$R/include/jetstream/render/tools -I$ROOT/shim/stubs"
 CXXFLAGS="-std=c++20 $OPT -fPIC -DJST_FMT_HEADER_ONLY -w $INC"
 
 CORE="logger memory/axis memory/buffer memory/buffer_cpu memory/tensor memory/token memory/types
@@ -79,9 +80,9 @@ done
 for b in $BLOCKS; do
   [ -f "$R/src/domains/$b/block_impl.cc" ] && SRCS+=("$R/src/domains/$b/block_impl.cc")
 done
-# the reference's lineplot / waterfall COMPUTE TUs (their render halves are oracle/viz_headless.cc)
+# the reference's lineplot / waterfall COMPUTE TUs (their render halves are shim/viz_headless.cc)
 for v in lineplot waterfall; do SRCS+=("$R/src/domains/visualization/$v/module_impl_native_cpu.cc"); done
-SRCS+=("$HERE/ref_stubs.cc" "$HERE/viz_headless.cc" "$HERE/ref_driver.cc")
+SRCS+=("$HERE/ref_stubs.cc" "$ROOT/shim/viz_headless.cc" "$HERE/ref_driver.cc")
 
 compile_one() {
   src="$1"; obj="$B/obj/$(echo "$src" | sed -e 's#^/##' -e 's#[/.]#_#g').o"

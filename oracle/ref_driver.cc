@@ -407,7 +407,7 @@ int jst_ref_metrics(void* handle, const char* block, char* buffer, uint64_t capa
 // ---- lineplot / waterfall: the reference modules driven directly through Registry::BuildModule +
 // Runtime, the way the reference's own module_tests.cc do (lineplot/module_tests.cc:63-94), with their internal
 // state read through Module::getImpl<> (module_tests.cc:25-46). Compute is the reference's module_impl_native_cpu.cc;
-// the non-compute halves are oracle/viz_headless.cc.
+// the non-compute halves are shim/viz_headless.cc.
 
 namespace {
 

@@ -13,6 +13,7 @@
 //   selection        blockCreate(name, type, config, inputs, DeviceType::CUDA, RuntimeType::NATIVE, "b200")
 //                    or `device: cuda / runtime: native / provider: b200` in a flowgraph YAML
 #include <cmath>
+#include <any>
 #include <cstdint>
 #include <memory>
 #include <vector>
@@ -37,6 +38,8 @@
 #include "domains/dsp/fm/module_impl.hh"
 #include "domains/dsp/invert/module_impl.hh"
 #include "domains/dsp/window/module_impl.hh"
+#include "domains/visualization/lineplot/module_impl.hh"
+#include "domains/visualization/waterfall/module_impl.hh"
 
 #include "b200_provider.hh"
 
@@ -358,12 +361,18 @@ struct SpectralChainImplB200 : public Module::Impl, public DynamicConfig<Spectra
         JST_CHECK(Check(b200_range_coefficients(rangeMin, rangeMax, &scalingCoeff, &offsetCoeff), "SPECTRAL_CHAIN"));
         JST_CHECK(output.create(input.device(), DataType::F32, input.shape()));
         JST_CHECK(output.propagateAttributes(input));
+        columnSums = Tensor();
+        if (publishColumnSums && !enableAgc) {
+            JST_CHECK(columnSums.create(input.device(), DataType::F32, {n}));
+            JST_CHECK(output.setAttribute(B200::kColumnSumsAttribute, columnSums));
+        }
         outputs()["buffer"].produced(name(), "buffer", output);
         return Result::SUCCESS;
     }
     Result reconfigure() override {     // range limits change in place, like RangeImpl::reconfigure
         const auto& config = *candidate();
-        if (config.enableScale != enableScale || config.enableAgc != enableAgc) {
+        if (config.enableScale != enableScale || config.enableAgc != enableAgc ||
+            config.publishColumnSums != publishColumnSums) {
             return Result::RECREATE;
         }
         rangeMin = config.rangeMin;
@@ -390,6 +399,11 @@ struct SpectralChainImplB200 : public Module::Impl, public DynamicConfig<Spectra
                                              amplitudeCoeff, enableScale ? 1 : 0, scalingCoeff, offsetCoeff,
                                              agcReference, agcEpsilon, agcMinGain, agcMaxGain, stream), "SPECTRAL_CHAIN");
         }
+        if (columnSums.size() != 0) {
+            return Check(b200_chain_exec_colsum(plan, DevicePtr<void>(input), dtypeCode, DevicePtr<float>(output), batch,
+                                                amplitudeCoeff, enableScale ? 1 : 0, scalingCoeff, offsetCoeff,
+                                                DevicePtr<float>(columnSums), stream), "SPECTRAL_CHAIN");
+        }
         return Check(b200_chain_exec_typed(plan, DevicePtr<void>(input), dtypeCode, DevicePtr<float>(output), batch,
                                            amplitudeCoeff, enableScale ? 1 : 0, scalingCoeff, offsetCoeff, stream),
                      "SPECTRAL_CHAIN");
@@ -399,7 +413,7 @@ struct SpectralChainImplB200 : public Module::Impl, public DynamicConfig<Spectra
         plan = nullptr;
         return result;
     }
-    Tensor input, window, output;
+    Tensor input, window, output, columnSums;
     U64 n = 0, batch = 0;
     int dtypeCode = B200_DTYPE_CF32;
     float amplitudeCoeff = 0.0f, scalingCoeff = 0.0f, offsetCoeff = 0.0f;
@@ -551,5 +565,96 @@ struct FirFilterImplB200 : public Module::Impl, public DynamicConfig<FirFilter>,
     std::vector<b200_fir_plan*> plans;
 };
 JST_REGISTER_MODULE(FirFilterImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+// ---- lineplot / waterfall: the consumers right after the chain --------------------------------
+// validate / create / reconfigure / present are the reference's LineplotImpl / WaterfallImpl; computeSubmit replaces
+// the NVRTC kernels of lineplot/module_impl_native_cuda.cc:21-60 and waterfall/module_impl_native_cuda.cc:19-60.
+struct LineplotImplB200 : public LineplotImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
+    Result validate() final {
+        JST_CHECK(LineplotImpl::validate());
+        if (inputs().contains("signal")) {
+            const Tensor& tensor = inputs().at("signal").tensor;
+            if (tensor.validShape() && tensor.size() != 0 && tensor.dtype() != DataType::F32) {
+                JST_ERROR("[MODULE_LINEPLOT_B200] Unsupported input data type: {}.", tensor.dtype());
+                return Result::ERROR;
+            }
+        }
+        return Result::SUCCESS;
+    }
+    Result create() final {
+        JST_CHECK(LineplotImpl::create());
+        JST_CHECK(averagingBuffer.create(device(), DataType::F32, {numberOfElements}));
+        uint64_t bytes = 0;
+        JST_CHECK(Check(b200_lineplot_scratch_bytes(numberOfBatches, numberOfElements, decimation, &bytes), "LINEPLOT"));
+        JST_CHECK(scratch.create(device(), DataType::F32, {bytes / sizeof(F32) + 1}));
+        initialized = false;
+        // A fused spectral_chain upstream publishes the batch sums of its output (shim/b200_provider.hh): usable when
+        // the input is that module's plain row-major [batches, extent] tensor.
+        columnSums = Tensor();
+        if (input.hasAttribute(B200::kColumnSumsAttribute)) {
+            const std::any attribute = input.attribute(B200::kColumnSumsAttribute);
+            const auto* published = std::any_cast<Tensor>(&attribute);
+            const U64 extent = numberOfElements * decimation;
+            if (published && published->dtype() == DataType::F32 && published->size() >= extent &&
+                inputElementStride == 1 && (numberOfBatches == 1 || inputBatchStride == published->size())) {
+                columnSums = *published;
+            }
+        }
+        return Result::SUCCESS;
+    }
+    Result presentInitialize() override { return createPresent(); }
+    Result presentSubmit() override { return present(); }
+    Result computeSubmit(const cudaStream_t& stream) override {
+        if (numberOfElements == 0 || numberOfBatches == 0) {
+            return Result::SUCCESS;
+        }
+        if (!initialized) {
+            JST_CHECK(Check(b200_lineplot_init(B200Ctx(), DevicePtr<float>(signalPoints), DevicePtr<float>(averagingBuffer),
+                                               numberOfElements, stream), "LINEPLOT"));
+            initialized = true;
+        }
+        updateSignalPointsFlag = true;
+        if (columnSums.size() != 0) {
+            return Check(b200_lineplot_update_from_colsum(B200Ctx(), DevicePtr<float>(columnSums), numberOfElements,
+                                                          decimation, normalizationFactor, averaging,
+                                                          DevicePtr<float>(averagingBuffer), DevicePtr<float>(signalPoints),
+                                                          stream), "LINEPLOT");
+        }
+        return Check(b200_lineplot_update(B200Ctx(), DevicePtr<float>(input), numberOfBatches, numberOfElements,
+                                          inputBatchStride, inputElementStride, decimation, normalizationFactor, averaging,
+                                          DevicePtr<float>(averagingBuffer), DevicePtr<float>(signalPoints),
+                                          DevicePtr<void>(scratch), stream), "LINEPLOT");
+    }
+    Tensor averagingBuffer, scratch, columnSums;
+    bool initialized = false;
+};
+JST_REGISTER_MODULE(LineplotImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
+
+struct WaterfallImplB200 : public WaterfallImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
+    Result validate() final {
+        JST_CHECK(WaterfallImpl::validate());
+        if (inputs().contains("signal")) {
+            const Tensor& tensor = inputs().at("signal").tensor;
+            if (tensor.validShape() && tensor.size() != 0 && tensor.dtype() != DataType::F32) {
+                JST_ERROR("[MODULE_WATERFALL_B200] Unsupported input data type: {}.", tensor.dtype());
+                return Result::ERROR;
+            }
+        }
+        return Result::SUCCESS;
+    }
+    Result presentInitialize() override { return createPresent(); }
+    Result presentSubmit() override { return present(); }
+    Result computeSubmit(const cudaStream_t& stream) override {
+        if (numberOfElements == 0 || numberOfBatches == 0) {
+            return Result::SUCCESS;
+        }
+        JST_CHECK(Check(b200_waterfall_update(B200Ctx(), DevicePtr<float>(input), numberOfBatches, numberOfElements,
+                                              inputBatchStride, inputElementStride, DevicePtr<float>(frequencyBins), height,
+                                              ringState.writeIndex, stream), "WATERFALL"));
+        ringState.advance(numberOfBatches, height);     // the reference's own cursor + dirty-row bookkeeping
+        return Result::SUCCESS;
+    }
+};
+JST_REGISTER_MODULE(WaterfallImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
 
 }  // namespace Jetstream::Modules

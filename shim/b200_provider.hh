@@ -5,7 +5,8 @@
 //   spectral_chain  multiply(window) -> fft -> [agc] -> amplitude -> [range]   (spectrum_engine block, one kernel)
 //   fir_filter      pad -> fft -> multiply -> fold -> ifft -> normalize -> phase_correction -> unpad -> overlap_add
 //                   (filter block, one time-domain polyphase kernel)
-//   spectrum_sink   lineplot / waterfall computeSubmit() (batch-sum + decimate + normalise + clamp + EMA; ring write)
+// and implements for the reference's own types `lineplot` / `waterfall` (computeSubmit: batch sum + decimate +
+// normalise + clamp + EMA; ring write), fed by the chain's fused column sums when the producer publishes them.
 //
 // The config records follow the reference's own declaration style (include/jetstream/module.hh JST_MODULE_TYPE /
 // JST_MODULE_PARAMS) so flowgraph YAML, Parser::Map and block reconfigure work on them unchanged.
@@ -36,9 +37,14 @@ struct SpectralChain : public Module::Config {
     F64 agcEpsilon = 1e-12;
     F64 agcMinGain = 0.01;
     F64 agcMaxGain = 100.0;
+    // The kernel's epilogue also accumulates sum-over-batch of every output column and the output tensor carries them
+    // as attribute "b200.columnSums" (Tensor [n] F32): a `lineplot` on this provider downstream then skips its own
+    // pass over the [batch, n] spectra (b200_chain_exec_colsum -> b200_lineplot_update_from_colsum).
+    bool publishColumnSums = true;
 
     JST_MODULE_TYPE(spectral_chain);
-    JST_MODULE_PARAMS(enableScale, rangeMin, rangeMax, enableAgc, agcReference, agcEpsilon, agcMinGain, agcMaxGain);
+    JST_MODULE_PARAMS(enableScale, rangeMin, rangeMax, enableAgc, agcReference, agcEpsilon, agcMinGain, agcMaxGain,
+                      publishColumnSums);
 };
 
 struct FirFilter : public Module::Config {
@@ -52,6 +58,8 @@ struct FirFilter : public Module::Config {
 }  // namespace Jetstream::Modules
 
 namespace Jetstream::B200 {
+
+inline constexpr const char* kColumnSumsAttribute = "b200.columnSums";
 
 // One b200_ctx per CUDA device, keyed by the device that is current on the calling thread (the reference's CUDA
 // backend activates its device before every create / compute, src/runtime/native/cuda/impl.cc:36,186).

@@ -57,6 +57,11 @@ def lib():
         L.jst_shim_output_pointer.restype = vp
         L.jst_shim_output_read.argtypes = [vp, cp, cp, vp, u64]
         L.jst_shim_metrics.argtypes = [vp, cp, cp, u64]
+        L.jst_shim_viz_list.argtypes = [cp, u64]
+        L.jst_shim_viz_read.argtypes = [cp, vp, u64]
+        L.jst_shim_viz_read.restype = i64
+        L.jst_shim_viz_write_index.argtypes = [cp]
+        L.jst_shim_viz_write_index.restype = i64
         _lib = L
     return _lib
 
@@ -177,3 +182,30 @@ class Session:
             name, cycles, ms = line.rsplit(" ", 2)
             out[name] = (int(cycles), float(ms))
         return out
+
+
+def viz_modules() -> Dict[str, str]:
+    """Live lineplot / waterfall modules of every session: module name -> type."""
+    buf = ctypes.create_string_buffer(8192)
+    lib().jst_shim_viz_list(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        kind, name = line.split(":", 1)
+        out[name] = kind
+    return out
+
+
+def viz_read(module: str) -> np.ndarray:
+    """signalPoints (flat [n * 2]) of a lineplot module or the ring (flat [height * n]) of a waterfall module."""
+    L = lib()
+    n = L.jst_shim_viz_read(module.encode(), None, 0)
+    if n < 0:
+        raise ShimError(L.jst_shim_last_error().decode(errors="replace"))
+    out = np.empty(n, np.float32)
+    if L.jst_shim_viz_read(module.encode(), out.ctypes.data_as(ctypes.c_void_p), n) < 0:
+        raise ShimError(L.jst_shim_last_error().decode(errors="replace"))
+    return out
+
+
+def viz_write_index(module: str) -> int:
+    return int(lib().jst_shim_viz_write_index(module.encode()))

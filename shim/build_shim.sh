@@ -25,7 +25,7 @@ if [ ! -f "$B/gen/jetstream/config.hh" ] || [ "$NEWCFG" != "$(cat "$B/gen/jetstr
   printf '%s\n' "$NEWCFG" > "$B/gen/jetstream/config.hh"
 fi
 CUDA=/usr/local/cuda
-INC="-I$B/gen -I$FMT -I$R/include -I$R/src -I$R/include/jetstream/render/tools -I$CUDA/include -I$ROOT/include -I$HERE"
+INC="-I$B/gen -I$FMT -I$R/include -I$R/src -I$R/include/jetstream/render/tools -I$CUDA/include -I$ROOT/include -I$HERE -I$HERE/stubs"
 CXXFLAGS="-std=c++20 -O2 -fPIC -DJST_FMT_HEADER_ONLY -w $INC"
 CORE="logger memory/axis memory/buffer memory/buffer_cpu memory/buffer_cuda memory/tensor memory/token memory/types
  module module_impl module_context module_interface module_surface registry
@@ -45,7 +45,11 @@ SRCS=()
 for c in $CORE; do SRCS+=("$R/src/$c.cc"); done
 for m in $MODS; do SRCS+=("$R/src/domains/$m/module_impl.cc" "$R/src/domains/$m/module_impl_native_cpu.cc"); done
 for b in $BLOCKS; do [ -f "$R/src/domains/$b/block_impl.cc" ] && SRCS+=("$R/src/domains/$b/block_impl.cc"); done
-SRCS+=("$HERE/shim_stubs.cc" "$HERE/b200_modules.cc" "$HERE/b200_blocks.cc" "$HERE/shim_capi.cc")
+# lineplot / waterfall: the reference's CPU compute TUs + blocks; their render halves are shim/viz_headless.cc
+for v in lineplot waterfall; do
+  SRCS+=("$R/src/domains/visualization/$v/module_impl_native_cpu.cc" "$R/src/domains/visualization/$v/block_impl.cc")
+done
+SRCS+=("$HERE/shim_stubs.cc" "$HERE/viz_headless.cc" "$HERE/b200_modules.cc" "$HERE/b200_blocks.cc" "$HERE/shim_capi.cc")
 objname() { echo "$B/obj/$(echo "$1" | sed -e 's#^/##' -e 's#[/.]#_#g').o"; }
 compile_one() {
   src="$1"; obj="$B/obj/$(echo "$src" | sed -e 's#^/##' -e 's#[/.]#_#g').o"

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -30,6 +31,14 @@
 #include "jetstream/runtime_context_native_cpu.hh"
 #include "jetstream/runtime_context_native_cuda.hh"
 #include "jetstream/scheduler_context.hh"
+
+#include "domains/visualization/lineplot/module_impl.hh"
+#include "domains/visualization/waterfall/module_impl.hh"
+
+namespace Jetstream::Headless {       // shim/viz_headless.cc: lineplot / waterfall modules by name
+std::map<std::string, Modules::LineplotImpl*>& Lineplots();
+std::map<std::string, Modules::WaterfallImpl*>& Waterfalls();
+}  // namespace Jetstream::Headless
 
 namespace Jetstream {
 
@@ -401,6 +410,64 @@ int jst_shim_metrics(void* handle, const char* block, char* buffer, uint64_t cap
         buffer[n] = 0;
     }
     return static_cast<int>(text.size());
+}
+
+// ---- lineplot / waterfall state (the tensors the reference hands to its renderer), by MODULE name --------------------
+// A block named "lp" of type lineplot holds the module "lp-lineplot" (Block::Impl::moduleCreate naming).
+
+namespace {
+
+struct LineplotPeek : Modules::LineplotImpl {
+    static auto points() { return &LineplotPeek::signalPoints; }
+};
+struct WaterfallPeek : Modules::WaterfallImpl {
+    static auto bins() { return &WaterfallPeek::frequencyBins; }
+    static auto ring() { return &WaterfallPeek::ringState; }
+};
+
+int64_t CopyOut(const Tensor& tensor, float* dst, const uint64_t capacity) {
+    const uint64_t n = std::min<uint64_t>(capacity, tensor.size());
+    if (n != 0 && tensor.device() == DeviceType::CUDA) {
+        if (cudaMemcpy(dst, RawPointer(tensor), n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            g_error = "viz read: device copy failed";
+            return -1;
+        }
+    } else if (n != 0) {
+        std::memcpy(dst, RawPointer(tensor), n * sizeof(float));
+    }
+    return static_cast<int64_t>(tensor.size());
+}
+
+}  // namespace
+
+// Lists "lineplot:<name>\n" / "waterfall:<name>\n" for every live module (to discover the naming).
+int jst_shim_viz_list(char* buffer, uint64_t capacity) {
+    std::string text;
+    for (const auto& [name, _] : Headless::Lineplots()) text += "lineplot:" + name + "\n";
+    for (const auto& [name, _] : Headless::Waterfalls()) text += "waterfall:" + name + "\n";
+    if (buffer && capacity > 0) {
+        const auto n = std::min<uint64_t>(capacity - 1, text.size());
+        std::memcpy(buffer, text.data(), n);
+        buffer[n] = 0;
+    }
+    return static_cast<int>(text.size());
+}
+
+// signalPoints [n, 2] of a lineplot module / frequencyBins [height, n] of a waterfall module. Returns the element count.
+int64_t jst_shim_viz_read(const char* module, float* dst, uint64_t capacity) {
+    if (const auto it = Headless::Lineplots().find(module); it != Headless::Lineplots().end()) {
+        return CopyOut(it->second->*LineplotPeek::points(), dst, capacity);
+    }
+    if (const auto it = Headless::Waterfalls().find(module); it != Headless::Waterfalls().end()) {
+        return CopyOut(it->second->*WaterfallPeek::bins(), dst, capacity);
+    }
+    g_error = std::string("viz_read: no lineplot / waterfall module named '") + module + "'";
+    return -1;
+}
+
+int64_t jst_shim_viz_write_index(const char* module) {
+    const auto it = Headless::Waterfalls().find(module);
+    return it == Headless::Waterfalls().end() ? -1 : static_cast<int64_t>((it->second->*WaterfallPeek::ring()).writeIndex);
 }
 
 }  // extern "C"

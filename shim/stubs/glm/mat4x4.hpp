@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE (oracle/_ref build only): the two glm types the reference's visualization module headers
+// HARNESS (oracle/_ref and shim/_build builds only): the two glm types the reference's visualization module headers
 // (src/domains/visualization/{lineplot,waterfall}/module_impl.hh) name in their render-uniform structs. glm is an
 // un-vendored render dependency; nothing on the compute path touches these members.
 #pragma once

@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE (oracle/_ref build only): see mat4x4.hpp.
+// HARNESS (oracle/_ref and shim/_build builds only): see mat4x4.hpp.
 #pragma once
 namespace glm {
 struct vec2 {

@@ -212,3 +212,43 @@ def test_unfused_modules_still_reachable(sb):
     want, got = outs["generic"], outs["b200"]
     assert np.abs(got[0] - want[0]).max() <= 2e-6 * np.abs(want[0]).max()
     assert np.abs(got[1] - want[1]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("rows,decimation", [(48, 1), (700, 2)])
+def test_spectrum_analyzer_flowgraph_with_consumers(sb, rows, decimation):
+    """examples/flowgraphs/spectrum-analyzer.yml in small: source -> spectrum_engine -> lineplot + waterfall, every
+    block on provider b200, next to the same flowgraph on the reference CPU provider. On b200 the lineplot takes its
+    batch sums from the chain kernel's epilogue (attribute "b200.columnSums"); only signalPoints [n, 2] and the ring
+    [height, 4096] would have to leave the device."""
+    from cyberether_b200.synthetic import spectral_rows
+    cycles = [spectral_rows(17 * k, rows) for k in range(3)]
+    state = {}
+    for target in (sb.CPU, sb.B200):
+        with sb.Session() as s:
+            s.add_source("src", (rows, 4096), "CF32", target=target, sampleAxis=1, batchAxis=0)
+            s.add_block("spec", "spectrum_engine", {"enableScale": True}, {"buffer": "src.signal"}, target=target)
+            s.add_block("lp", "lineplot", {"averaging": 2, "decimation": decimation}, {"signal": "spec.buffer"}, target=target)
+            s.add_block("wf", "waterfall", {"height": 64}, {"signal": "spec.buffer"}, target=target)
+            assert sb.viz_modules() == {"lp-lineplot": "lineplot", "wf-waterfall": "waterfall"}
+            per_cycle = []
+            for x in cycles:
+                s.write_source("src", x)
+                s.compute()
+                per_cycle.append((sb.viz_read("lp-lineplot").reshape(-1, 2), sb.viz_read("wf-waterfall").reshape(64, 4096),
+                                  sb.viz_write_index("wf-waterfall"), s.read("spec", "buffer")))
+            state[target[1]] = per_cycle
+            mods = {**s.modules("spec"), **s.modules("lp"), **s.modules("wf")}
+            if target is sb.B200:
+                assert mods["runtime:spectral_chain"][0] == 3 and mods["runtime:lineplot"][0] == 3 \
+                    and mods["runtime:waterfall"][0] == 3
+    for (lp_c, wf_c, wi_c, spec_c), (lp_g, wf_g, wi_g, spec_g) in zip(state["generic"], state["b200"]):
+        assert wi_c == wi_g
+        # the ring holds copies of the block's own spectra: identical to the b200 spectra, row for row
+        kept = min(rows, 64)
+        assert np.array_equal(np.sort(wf_g.ravel()), np.sort(np.concatenate([spec_g[-kept:].ravel(),
+                                                                              np.zeros((64 - kept) * 4096, np.float32)]))) \
+            or rows > 64
+        assert np.array_equal(lp_c[:, 0], lp_g[:, 0])
+        # spectra agree within the chain allowance; their batch mean mapped to [-1, 1] within 2e-4
+        assert np.abs(lp_c[:, 1] - lp_g[:, 1]).max() <= 2e-4
+        assert np.abs(wf_c - wf_g).max() <= 2e-3
