@@ -36,6 +36,14 @@ SIGNATURES = {
     "b200_stream_create": (c_int, [c_vp, P(c_vp)]),
     "b200_stream_destroy": (c_int, [c_vp, c_vp]),
     "b200_stream_synchronize": (c_int, [c_vp, c_vp]),
+    "b200_malloc_managed": (c_int, [c_vp, c_u64, P(c_vp)]),
+    "b200_host_register": (c_int, [c_vp, c_vp, c_u64, P(c_int)]),
+    "b200_host_unregister": (c_int, [c_vp, c_vp]),
+    "b200_event_create": (c_int, [c_vp, P(c_vp)]),
+    "b200_event_record": (c_int, [c_vp, c_vp, c_vp]),
+    "b200_event_elapsed_ms": (c_int, [c_vp, c_vp, c_vp, P(c_f32)]),
+    "b200_event_destroy": (c_int, [c_vp, c_vp]),
+    "b200_check_async_error": (c_int, [c_vp]),
     "b200_window_blackman_cf32": (c_int, [c_vp, c_vp, c_u64, c_vp]),
     "b200_invert_cf32": (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_u64, c_vp]),
     "b200_multiply_cf32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, P(c_u64), P(c_u64), P(c_u64), c_vp]),
@@ -69,6 +77,7 @@ SIGNATURES = {
     "b200_waterfall_update": (c_int, [c_vp, c_vp, c_u64, c_u64, c_u64, c_u64, c_vp, c_u64, c_u64, c_vp]),
     "b200_waterfall_advance": (c_int, [P(c_u64), c_u64, c_u64]),
     "b200_chain_exec_host": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_u64]),
+    "b200_chain_exec_host_typed": (c_int, [c_vp, c_vp, c_int, c_vp, c_u64, c_f32, c_int, c_f32, c_f32, c_u64]),
     "b200_chain_plan_destroy": (c_int, [c_vp]),
     "b200_chain_plan_variant": (ctypes.c_char_p, [c_vp]),
     "b200_filter_taps_host": (c_int, [ctypes.c_double, ctypes.c_double, P(ctypes.c_double), c_u64, c_u64, c_vp]),

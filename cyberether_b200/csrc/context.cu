@@ -154,14 +154,14 @@ int b200_host_free(b200_ctx* ctx, void* ptr) {
 
 int b200_memcpy(b200_ctx* ctx, void* dst, const void* src, uint64_t bytes, int kind, b200_stream stream) {
     B200_REQUIRE(ctx != nullptr, "b200_memcpy: null context");
-    B200_REQUIRE(kind >= 0 && kind <= 2, "b200_memcpy: kind must be 0 (h2d), 1 (d2h) or 2 (d2d)");
+    B200_REQUIRE(kind >= 0 && kind <= 3, "b200_memcpy: kind must be 0 (h2d), 1 (d2h), 2 (d2d) or 3 (by address, UVA)");
     if (bytes == 0) {
         return B200_SUCCESS;
     }
     B200_REQUIRE(dst && src, "b200_memcpy: null pointer");
     DeviceGuard guard(ctx);
     const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice
-                                       : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+                             : (kind == 1 ? cudaMemcpyDeviceToHost : (kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyDefault));
     B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, k, as_stream(stream)));
     return B200_SUCCESS;
 }
@@ -199,6 +199,90 @@ int b200_stream_synchronize(b200_ctx* ctx, b200_stream stream) {
     B200_REQUIRE(ctx != nullptr, "b200_stream_synchronize: null context");
     DeviceGuard guard(ctx);
     B200_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+    return B200_SUCCESS;
+}
+
+int b200_malloc_managed(b200_ctx* ctx, uint64_t bytes, void** ptr) {
+    B200_REQUIRE(ctx && ptr, "b200_malloc_managed: null argument");
+    *ptr = nullptr;
+    if (bytes == 0) {
+        return B200_SUCCESS;
+    }
+    DeviceGuard guard(ctx);
+    B200_CUDA_CHECK(cudaMallocManaged(ptr, bytes));
+    const cudaError_t e = cudaMemset(*ptr, 0, bytes);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return fail("b200_malloc_managed: cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+    return B200_SUCCESS;
+}
+
+int b200_host_register(b200_ctx* ctx, void* host, uint64_t bytes, int* registered) {
+    B200_REQUIRE(ctx && host && registered, "b200_host_register: null argument");
+    *registered = 0;
+    DeviceGuard guard(ctx);
+    cudaPointerAttributes attributes = {};
+    const cudaError_t query = cudaPointerGetAttributes(&attributes, host);
+    if (query == cudaSuccess && attributes.type != cudaMemoryTypeUnregistered) {
+        return B200_SUCCESS;                 // already pinned / mapped by someone else: nothing to own
+    }
+    if (query != cudaSuccess) {
+        cudaGetLastError();
+    }
+    B200_CUDA_CHECK(cudaHostRegister(host, bytes, cudaHostRegisterPortable));
+    *registered = 1;
+    return B200_SUCCESS;
+}
+
+int b200_host_unregister(b200_ctx* ctx, void* host) {
+    B200_REQUIRE(ctx && host, "b200_host_unregister: null argument");
+    DeviceGuard guard(ctx);
+    B200_CUDA_CHECK(cudaHostUnregister(host));
+    return B200_SUCCESS;
+}
+
+int b200_event_create(b200_ctx* ctx, b200_event* event) {
+    B200_REQUIRE(ctx && event, "b200_event_create: null argument");
+    DeviceGuard guard(ctx);
+    cudaEvent_t e;
+    B200_CUDA_CHECK(cudaEventCreate(&e));
+    *event = e;
+    return B200_SUCCESS;
+}
+
+int b200_event_record(b200_ctx* ctx, b200_event event, b200_stream stream) {
+    B200_REQUIRE(ctx && event, "b200_event_record: null argument");
+    DeviceGuard guard(ctx);
+    B200_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(event), as_stream(stream)));
+    return B200_SUCCESS;
+}
+
+int b200_event_elapsed_ms(b200_ctx* ctx, b200_event start, b200_event end, float* ms) {
+    B200_REQUIRE(ctx && start && end && ms, "b200_event_elapsed_ms: null argument");
+    DeviceGuard guard(ctx);
+    B200_CUDA_CHECK(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(end)));
+    return B200_SUCCESS;
+}
+
+int b200_event_destroy(b200_ctx* ctx, b200_event event) {
+    B200_REQUIRE(ctx != nullptr, "b200_event_destroy: null context");
+    if (!event) {
+        return B200_SUCCESS;
+    }
+    DeviceGuard guard(ctx);
+    B200_CUDA_CHECK(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+    return B200_SUCCESS;
+}
+
+/* The last asynchronous CUDA error of the calling thread, cleared (what NativeCudaRuntime checks after every submit,
+ * src/runtime/native/cuda/impl.cc:228-231). */
+int b200_check_async_error(b200_ctx* ctx) {
+    B200_REQUIRE(ctx != nullptr, "b200_check_async_error: null context");
+    DeviceGuard guard(ctx);
+    B200_CUDA_CHECK(cudaGetLastError());
     return B200_SUCCESS;
 }
 

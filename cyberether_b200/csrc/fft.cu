@@ -163,11 +163,9 @@ template <int MODE, int WIN, int CTAS>
 static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
     auto kernel = fft4096_kernel<MODE, WIN, CTAS>;
     constexpr int smem = fft4096_smem_bytes(CTAS);
-    static bool configured[64] = {};
-    if (!configured[ctx->device & 63]) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[ctx->device & 63] = true;
-    }
+    // Set on every launch (a cheap runtime call): the attribute belongs to the CUDA *context*, and a host such as the
+    // reference's CUDA backend runs this library inside its own driver context next to the primary one.
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const uint64_t cap = static_cast<uint64_t>(ctx->sms) * CTAS;
     const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
     kernel<<<grid, kFft4096Threads, smem, stream>>>(p);
@@ -180,11 +178,9 @@ template <int MODE, int ITYPE, bool AGC = false, bool COLSUM = false>
 static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream, unsigned* grid_out = nullptr) {
     auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE, AGC, COLSUM>;
     constexpr int smem = ITYPE == IN_CF32 ? fft4096_smem_bytes(2) : fft4096_int_smem_bytes(ITYPE);
-    static bool configured[64] = {};
-    if (!configured[ctx->device & 63]) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[ctx->device & 63] = true;
-    }
+    // Set on every launch (a cheap runtime call): the attribute belongs to the CUDA *context*, and a host such as the
+    // reference's CUDA backend runs this library inside its own driver context next to the primary one.
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
     const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
     if (grid_out) {
@@ -238,11 +234,9 @@ static int launch_radix(const b200_ctx* ctx, const FftParams& p, cudaStream_t st
     constexpr int smem = radix_smem_bytes(LOG2N);
     constexpr int threads = radix_threads(LOG2N);
     constexpr int per_sm = threads > 256 ? 1 : 2;
-    static bool configured[64] = {};
-    if (!configured[ctx->device & 63]) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[ctx->device & 63] = true;
-    }
+    // Set on every launch (a cheap runtime call): the attribute belongs to the CUDA *context*, and a host such as the
+    // reference's CUDA backend runs this library inside its own driver context next to the primary one.
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const uint64_t rows_per_block = static_cast<uint64_t>(threads) * 16 >> LOG2N;
     const uint64_t blocks = (p.rows + rows_per_block - 1) / rows_per_block;
     const uint64_t cap = static_cast<uint64_t>(ctx->sms) * per_sm;
@@ -1017,16 +1011,33 @@ int b200_chain_exec_colsum(b200_chain_plan* plan, const void* x, int in_dtype, f
     return rc == B200_SUCCESS ? colsum_reduce(plan->colsum_partial, grid, n, colsum, s) : rc;
 }
 
+static uint64_t dtype_sample_bytes(const int in_dtype) {
+    switch (in_dtype) {
+        case B200_DTYPE_CI8: case B200_DTYPE_CU8: return 2;
+        case B200_DTYPE_CI16: case B200_DTYPE_CU16: return 4;
+        default: return 8;      // CF32, CI32, CU32
+    }
+}
+
 int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* out_host, uint64_t batch,
                          float amp_coeff, int enable_range, float scale, float offset, uint64_t chunk_rows) {
+    return b200_chain_exec_host_typed(plan, x_host, B200_DTYPE_CF32, out_host, batch, amp_coeff, enable_range, scale,
+                                      offset, chunk_rows);
+}
+
+int b200_chain_exec_host_typed(b200_chain_plan* plan, const void* x_host, int in_dtype, float* out_host, uint64_t batch,
+                               float amp_coeff, int enable_range, float scale, float offset, uint64_t chunk_rows) {
     B200_REQUIRE(plan, "b200_chain_exec_host: null plan");
+    B200_REQUIRE(in_dtype == B200_DTYPE_CF32 || (in_dtype >= B200_DTYPE_CI8 && in_dtype <= B200_DTYPE_CU32),
+                 "b200_chain_exec_host: input dtype code %d is not CF32 or a complex integer type", in_dtype);
     if (batch == 0) {
         return B200_SUCCESS;
     }
     B200_REQUIRE(x_host && out_host, "b200_chain_exec_host: null buffer");
     DeviceGuard guard(plan->ctx);
+    const uint64_t sample_bytes = dtype_sample_bytes(in_dtype);
     if (chunk_rows == 0) {
-        chunk_rows = (128ull << 20) / (plan->n * sizeof(float2));  // 128 MiB of input per chunk
+        chunk_rows = (128ull << 20) / (plan->n * sizeof(float2));  // 128 MiB of CF32 input per chunk
         if (chunk_rows == 0) {
             chunk_rows = 1;
         }
@@ -1057,7 +1068,8 @@ int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* 
         }
     }
     const uint64_t chunks = (batch + chunk_rows - 1) / chunk_rows;
-    const float2* src = reinterpret_cast<const float2*>(x_host);
+    const unsigned char* src = static_cast<const unsigned char*>(x_host);
+    const uint64_t row_bytes = plan->n * sample_bytes;
     for (uint64_t c = 0; c < chunks; ++c) {
         const int slot = static_cast<int>(c % kSlots);
         const uint64_t row0 = c * chunk_rows;
@@ -1066,7 +1078,7 @@ int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* 
         if (c >= kSlots) {
             B200_CUDA_CHECK(cudaStreamWaitEvent(plan->s_h2d, plan->ev_exec[slot], 0));
         }
-        B200_CUDA_CHECK(cudaMemcpyAsync(plan->stage_in[slot], src + row0 * plan->n, rows * plan->n * sizeof(float2),
+        B200_CUDA_CHECK(cudaMemcpyAsync(plan->stage_in[slot], src + row0 * row_bytes, rows * row_bytes,
                                         cudaMemcpyHostToDevice, plan->s_h2d));
         B200_CUDA_CHECK(cudaEventRecord(plan->ev_in[slot], plan->s_h2d));
         // Kernel: needs the input, and the slot's output buffer drained by the D2H of chunk c - kSlots.
@@ -1074,8 +1086,12 @@ int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* 
         if (c >= kSlots) {
             B200_CUDA_CHECK(cudaStreamWaitEvent(plan->s_exec, plan->ev_out[slot], 0));
         }
-        if (chain_launch(plan, plan->stage_in[slot], plan->stage_out[slot], rows, amp_coeff, enable_range, scale,
-                         offset, plan->s_exec) != B200_SUCCESS) {
+        const int rc = in_dtype == B200_DTYPE_CF32
+                           ? chain_launch(plan, plan->stage_in[slot], plan->stage_out[slot], rows, amp_coeff,
+                                          enable_range, scale, offset, plan->s_exec)
+                           : b200_chain_exec_typed(plan, plan->stage_in[slot], in_dtype, plan->stage_out[slot], rows,
+                                                   amp_coeff, enable_range, scale, offset, plan->s_exec);
+        if (rc != B200_SUCCESS) {
             return B200_ERROR;
         }
         B200_CUDA_CHECK(cudaEventRecord(plan->ev_exec[slot], plan->s_exec));

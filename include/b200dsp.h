@@ -31,6 +31,7 @@ typedef struct b200_chain_plan b200_chain_plan;
 typedef struct b200_fir_plan b200_fir_plan;
 typedef struct b200_fm_plan b200_fm_plan;
 typedef void* b200_stream;                        /* cudaStream_t; NULL = legacy default stream */
+typedef void* b200_event;                         /* cudaEvent_t */
 typedef struct { float re, im; } b200_cf32;       /* CF32 = std::complex<float> layout */
 
 /* ---- backend / memory ------------------------------------------------------------------ */
@@ -52,7 +53,15 @@ int b200_free(b200_ctx* ctx, void* ptr);
 /* Pinned host staging (the reference maps host tensors with cudaHostRegister, buffer_cuda.cc:188). */
 int b200_host_alloc(b200_ctx* ctx, uint64_t bytes, void** ptr);
 int b200_host_free(b200_ctx* ctx, void* ptr);
-/* Tensor::copyFrom, src/memory/buffer_cuda.cc:284-306. kind: 0 h2d, 1 d2h, 2 d2d. Async on stream. */
+/* Host-accessible (managed) allocation: what the reference's CUDA Buffer hands out for Buffer::Config::hostAccessible
+ * (src/memory/buffer_cuda.cc:49-58), zero-filled. Freed with b200_free. */
+int b200_malloc_managed(b200_ctx* ctx, uint64_t bytes, void** ptr);
+/* Zero-copy mapping of an existing page-aligned host allocation onto the device (Tensor(device, cpuTensor),
+ * src/memory/buffer_cuda.cc:140-200): pins it unless somebody already did; *registered tells the caller whether it owns
+ * the registration (and must call b200_host_unregister). */
+int b200_host_register(b200_ctx* ctx, void* host, uint64_t bytes, int* registered);
+int b200_host_unregister(b200_ctx* ctx, void* host);
+/* Tensor::copyFrom, src/memory/buffer_cuda.cc:284-306. kind: 0 h2d, 1 d2h, 2 d2d, 3 by address (UVA). Async on stream. */
 int b200_memcpy(b200_ctx* ctx, void* dst, const void* src, uint64_t bytes, int kind, b200_stream stream);
 int b200_memset(b200_ctx* ctx, void* dst, int value, uint64_t bytes, b200_stream stream);
 
@@ -60,6 +69,13 @@ int b200_memset(b200_ctx* ctx, void* dst, int value, uint64_t bytes, b200_stream
 int b200_stream_create(b200_ctx* ctx, b200_stream* stream);
 int b200_stream_destroy(b200_ctx* ctx, b200_stream stream);
 int b200_stream_synchronize(b200_ctx* ctx, b200_stream stream);
+/* Per-module timing events of the runtime (src/runtime/native/cuda/impl.cc:96-118,206-262) and its post-submit check
+ * of the thread's asynchronous CUDA error state (:228-231). */
+int b200_event_create(b200_ctx* ctx, b200_event* event);
+int b200_event_record(b200_ctx* ctx, b200_event event, b200_stream stream);
+int b200_event_elapsed_ms(b200_ctx* ctx, b200_event start, b200_event end, float* ms);
+int b200_event_destroy(b200_ctx* ctx, b200_event event);
+int b200_check_async_error(b200_ctx* ctx);
 
 /* ---- module compute(): one call per reference computeSubmit() --------------------------- */
 
@@ -220,6 +236,11 @@ int b200_chain_exec_colsum(b200_chain_plan* plan, const void* x, int in_dtype, f
  * device staging slots. SYNCHRONOUS: returns when out_host is complete. */
 int b200_chain_exec_host(b200_chain_plan* plan, const b200_cf32* x_host, float* out_host, uint64_t batch,
                          float amp_coeff, int enable_range, float scale, float offset, uint64_t chunk_rows);
+/* The same pipeline for complex-integer host samples (in_dtype = B200_DTYPE_CI8 ... CU32; CF32 forwards): an SDR's
+ * native 8 / 16-bit samples cross PCIe at 2 / 4 bytes instead of 8 and are converted inside the kernel's load
+ * (b200_chain_exec_typed). Results are bit-identical to cast -> b200_chain_exec_host. */
+int b200_chain_exec_host_typed(b200_chain_plan* plan, const void* x_host, int in_dtype, float* out_host, uint64_t batch,
+                               float amp_coeff, int enable_range, float scale, float offset, uint64_t chunk_rows);
 int b200_chain_plan_destroy(b200_chain_plan* plan);
 /* Name of the kernel variant exec() launches for this plan (for logs / profiles). */
 const char* b200_chain_plan_variant(const b200_chain_plan* plan);

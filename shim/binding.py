@@ -44,7 +44,7 @@ def lib():
         L.jst_shim_create.argtypes = [ctypes.c_int]
         L.jst_shim_destroy.argtypes = [vp]
         L.jst_shim_add_source.argtypes = [vp, cp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u64), i64, i64, i64,
-                                          ctypes.c_int, cp]
+                                          ctypes.c_int, cp, ctypes.c_int]
         L.jst_shim_write_source.argtypes = [vp, cp, vp, u64]
         L.jst_shim_add_block.argtypes = [vp, cp, cp, cp, cp, ctypes.c_int, cp]
         L.jst_shim_reconfigure.argtypes = [vp, cp, cp]
@@ -114,10 +114,13 @@ class Session:
             raise ShimError(self._L.jst_shim_last_error().decode(errors="replace"))
 
     def add_source(self, name: str, shape: Sequence[int], dtype: str = "CF32", target: Tuple[int, str] = B200,
-                   sampleAxis: int = -1, batchAxis: int = -1, channelAxis: int = -1):
+                   sampleAxis: int = -1, batchAxis: int = -1, channelAxis: int = -1, mapped: bool = False):
+        """mapped (CUDA target only): the source is a CPU tensor mapped onto the device — Tensor(DeviceType::CUDA, cpu),
+        what the reference's TestContext hands a CUDA module (src/testing.cc:133-136)."""
         arr = (ctypes.c_uint64 * len(shape))(*[int(v) for v in shape])
         self._check(self._L.jst_shim_add_source(self._h, name.encode(), DTYPE_CODES[dtype], len(shape), arr,
-                                                sampleAxis, batchAxis, channelAxis, target[0], target[1].encode()))
+                                                sampleAxis, batchAxis, channelAxis, target[0], target[1].encode(),
+                                                1 if mapped else 0))
 
     def write_source(self, name: str, array: np.ndarray):
         a = np.ascontiguousarray(array)

@@ -1,8 +1,9 @@
 #!/usr/bin/env bash
 # Builds the reference-side binding of provider "b200" against the reference where it lies:
 #
-#   shim/_build/libjst_b200.so   the reference's Flowgraph / scheduler_synchronous / NativeCpuRuntime / NativeCudaRuntime /
-#                                CUDA backend + memory (compiled from /root/reference, CUDA enabled) + the reference CPU
+#   shim/_build/libjst_b200.so   the reference's Flowgraph / scheduler_synchronous / NativeCpuRuntime / CUDA backend singleton
+#                                (compiled from /root/reference, CUDA enabled) + OUR CUDA tensor allocation and CUDA runtime
+#                                behind the reference's interfaces (shim/b200_buffer.cc, shim/b200_runtime.cc) + the reference CPU
 #                                modules and blocks + shim/b200_modules.cc + shim/b200_blocks.cc (provider "b200" ->
 #                                libb200dsp.so; the latter REPLACES the spectrum_engine and filter block TUs) + the C-ABI
 #                                harness shim/shim_capi.cc. Loaded by tests/ and bench.py through shim/binding.py.
@@ -27,9 +28,11 @@ fi
 CUDA=/usr/local/cuda
 INC="-I$B/gen -I$FMT -I$R/include -I$R/src -I$R/include/jetstream/render/tools -I$CUDA/include -I$ROOT/include -I$HERE -I$HERE/stubs"
 CXXFLAGS="-std=c++20 -O2 -fPIC -DJST_FMT_HEADER_ONLY -w $INC"
-CORE="logger memory/axis memory/buffer memory/buffer_cpu memory/buffer_cuda memory/tensor memory/token memory/types
+# src/memory/buffer_cuda.cc and src/runtime/native/cuda/impl.cc are NOT in this list: shim/b200_buffer.cc and
+# shim/b200_runtime.cc define detail::CreateCudaBackend() / NativeCudaRuntimeFactory() over the C ABI instead (rows a14 / a12)
+CORE="logger memory/axis memory/buffer memory/buffer_cpu memory/tensor memory/token memory/types
  module module_impl module_context module_interface module_surface registry
- runtime/runtime runtime/native/cpu/impl runtime/native/cpu/context runtime/native/cuda/impl runtime/native/cuda/context
+ runtime/runtime runtime/native/cpu/impl runtime/native/cpu/context runtime/native/cuda/context
  scheduler scheduler_context scheduler_synchronous tensor_link
  parser_map parser_encode parser_decode
  backend/base backend/devices/cpu/base backend/devices/cuda/base
@@ -49,7 +52,8 @@ for b in $BLOCKS; do [ -f "$R/src/domains/$b/block_impl.cc" ] && SRCS+=("$R/src/
 for v in lineplot waterfall; do
   SRCS+=("$R/src/domains/visualization/$v/module_impl_native_cpu.cc" "$R/src/domains/visualization/$v/block_impl.cc")
 done
-SRCS+=("$HERE/shim_stubs.cc" "$HERE/viz_headless.cc" "$HERE/b200_modules.cc" "$HERE/b200_blocks.cc" "$HERE/shim_capi.cc")
+SRCS+=("$HERE/shim_stubs.cc" "$HERE/viz_headless.cc" "$HERE/b200_buffer.cc" "$HERE/b200_runtime.cc" "$HERE/b200_modules.cc"
+       "$HERE/b200_blocks.cc" "$HERE/shim_capi.cc")
 objname() { echo "$B/obj/$(echo "$1" | sed -e 's#^/##' -e 's#[/.]#_#g').o"; }
 compile_one() {
   src="$1"; obj="$B/obj/$(echo "$src" | sed -e 's#^/##' -e 's#[/.]#_#g').o"

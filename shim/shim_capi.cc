@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "jetstream/block.hh"
@@ -50,9 +51,10 @@ struct ShimSource : public Module::Config {
     I64 sampleAxis = -1;
     I64 batchAxis = -1;
     I64 channelAxis = -1;
+    bool mapped = false;          // CUDA only: a CPU tensor mapped onto the device (what TestContext hands a CUDA module)
 
     JST_MODULE_TYPE(shim_source);
-    JST_MODULE_PARAMS(shape, dataType, sampleAxis, batchAxis, channelAxis);
+    JST_MODULE_PARAMS(shape, dataType, sampleAxis, batchAxis, channelAxis, mapped);
 };
 
 struct ShimSourceBase : public Module::Impl, public DynamicConfig<ShimSource> {
@@ -72,7 +74,17 @@ struct ShimSourceBase : public Module::Impl, public DynamicConfig<ShimSource> {
                 dims.push_back(static_cast<U64>(std::stoull(item)));
             }
         }
-        JST_CHECK(signal.create(device(), dtype, dims));
+        if (mapped && device() == DeviceType::CUDA) {
+            // src/testing.cc:133-136: Tensor(deviceType, cpuTensor) = zero-copy host mapping (buffer backend create(source))
+            JST_CHECK(host.create(DeviceType::CPU, dtype, dims));
+            signal = Tensor(DeviceType::CUDA, host);
+            if (!signal.validShape() || signal.device() != DeviceType::CUDA) {
+                JST_ERROR("[SHIM_SOURCE] Mapping the host tensor onto the device failed.");
+                return Result::ERROR;
+            }
+        } else {
+            JST_CHECK(signal.create(device(), dtype, dims));
+        }
         if (sampleAxis >= 0) JST_CHECK(signal.setAttribute("sampleAxis", Index{static_cast<U64>(sampleAxis)}));
         if (batchAxis >= 0) JST_CHECK(signal.setAttribute("batchAxis", Index{static_cast<U64>(batchAxis)}));
         if (channelAxis >= 0) JST_CHECK(signal.setAttribute("channelAxis", Index{static_cast<U64>(channelAxis)}));
@@ -81,6 +93,7 @@ struct ShimSourceBase : public Module::Impl, public DynamicConfig<ShimSource> {
     }
 
     Tensor signal;
+    Tensor host;
 };
 
 struct ShimSourceCpu : public ShimSourceBase, public NativeCpuRuntimeContext, public Scheduler::Context {
@@ -102,10 +115,11 @@ struct ShimSource : public Block::Config {
     I64 sampleAxis = -1;
     I64 batchAxis = -1;
     I64 channelAxis = -1;
+    bool mapped = false;
 
     JST_BLOCK_TYPE(shim_source);
     JST_BLOCK_DOMAIN("Test");
-    JST_BLOCK_PARAMS(shape, dataType, sampleAxis, batchAxis, channelAxis);
+    JST_BLOCK_PARAMS(shape, dataType, sampleAxis, batchAxis, channelAxis, mapped);
     JST_BLOCK_DESCRIPTION("Shim Source", "Caller-filled source tensor.", "Harness source block of the b200 shim.");
 };
 
@@ -116,6 +130,7 @@ struct ShimSourceBlock : public Block::Impl, public DynamicConfig<Blocks::ShimSo
         moduleConfig->sampleAxis = sampleAxis;
         moduleConfig->batchAxis = batchAxis;
         moduleConfig->channelAxis = channelAxis;
+        moduleConfig->mapped = mapped;
         return Result::SUCCESS;
     }
     Result define() override { return defineInterfaceOutput("signal", "Output", "Caller-filled tensor."); }
@@ -188,6 +203,20 @@ I64 AxisOrMinusOne(const Tensor& tensor, const char* key) {
     }
 }
 
+// The reference's CUDA backend makes ITS driver context current on the calling thread (Backend::State<CUDA>::activate).
+// A host process that also uses the primary context (PyTorch, libb200dsp through ctypes) must get its own context back
+// when a harness call returns, or its next runtime-API call would run in the wrong context.
+struct ContextRestore {
+    CUcontext previous = nullptr;
+    bool valid = false;
+    ContextRestore() { valid = cuCtxGetCurrent(&previous) == CUDA_SUCCESS; }
+    ~ContextRestore() {
+        if (valid) {
+            cuCtxSetCurrent(previous);
+        }
+    }
+};
+
 DeviceType Device(const int code) { return code == 1 ? DeviceType::CUDA : DeviceType::CPU; }
 
 std::uint8_t* RawPointer(const Tensor& tensor) {
@@ -201,6 +230,7 @@ extern "C" {
 const char* jst_shim_last_error() { return g_error.c_str(); }
 
 void* jst_shim_create(int logLevel) {
+    const ContextRestore restore;
     JST_LOG_SET_DEBUG_LEVEL(logLevel);
     auto* s = new Session();
     s->flowgraph = std::make_unique<Flowgraph>();
@@ -214,6 +244,7 @@ void* jst_shim_create(int logLevel) {
 }
 
 void jst_shim_destroy(void* handle) {
+    const ContextRestore restore;
     auto* s = static_cast<Session*>(handle);
     if (!s) {
         return;
@@ -230,7 +261,8 @@ void jst_shim_destroy(void* handle) {
 
 // device: 0 CPU, 1 CUDA. dtype: the codes of include/b200dsp.h. axes: -1 = attribute absent.
 int jst_shim_add_source(void* handle, const char* name, int dtype, int rank, const uint64_t* shape, int64_t sampleAxis,
-                        int64_t batchAxis, int64_t channelAxis, int device, const char* provider) {
+                        int64_t batchAxis, int64_t channelAxis, int device, const char* provider, int mapped) {
+    const ContextRestore restore;
     auto* s = static_cast<Session*>(handle);
     static const char* const kNames[] = {"F32", "CF32", "I8", "U8", "I16", "U16", "I32", "U32",
                                          "CI8", "CU8", "CI16", "CU16", "CI32", "CU32"};
@@ -248,6 +280,7 @@ int jst_shim_add_source(void* handle, const char* name, int dtype, int rank, con
     config["sampleAxis"] = std::to_string(sampleAxis);
     config["batchAxis"] = std::to_string(batchAxis);
     config["channelAxis"] = std::to_string(channelAxis);
+    config["mapped"] = std::string(mapped ? "true" : "false");
     const auto result = s->flowgraph->blockCreate(name, "shim_source", config, {}, Device(device), RuntimeType::NATIVE,
                                                   provider);
     return result == Result::SUCCESS ? 0 : Fail("add_source", result);
@@ -255,6 +288,7 @@ int jst_shim_add_source(void* handle, const char* name, int dtype, int rank, con
 
 // Host bytes -> the source tensor (memcpy on the CPU target, a synchronous H2D copy on the CUDA target).
 int jst_shim_write_source(void* handle, const char* name, const void* data, uint64_t bytes) {
+    const ContextRestore restore;
     auto* s = static_cast<Session*>(handle);
     Tensor tensor;
     const auto result = FindOutput(s, name, "signal", tensor);
@@ -266,7 +300,7 @@ int jst_shim_write_source(void* handle, const char* name, const void* data, uint
         return -1;
     }
     if (tensor.device() == DeviceType::CUDA) {
-        const auto err = cudaMemcpy(RawPointer(tensor), data, bytes, cudaMemcpyHostToDevice);
+        const auto err = cudaMemcpy(RawPointer(tensor), data, bytes, cudaMemcpyDefault);
         if (err != cudaSuccess) {
             g_error = std::string("write_source: ") + cudaGetErrorString(err);
             return -1;
@@ -280,6 +314,7 @@ int jst_shim_write_source(void* handle, const char* name, const void* data, uint
 // config: "key=value\n..." (the strings a flowgraph YAML would carry). inputs: "port=block.port\n...".
 int jst_shim_add_block(void* handle, const char* name, const char* type, const char* config, const char* inputs,
                        int device, const char* provider) {
+    const ContextRestore restore;
     auto* s = static_cast<Session*>(handle);
     TensorMap links;
     for (const auto& [port, value] : ParseKv(inputs)) {
@@ -297,12 +332,14 @@ int jst_shim_add_block(void* handle, const char* name, const char* type, const c
 }
 
 int jst_shim_reconfigure(void* handle, const char* name, const char* config) {
+    const ContextRestore restore;
     auto* s = static_cast<Session*>(handle);
     const auto result = s->flowgraph->blockReconfigure(name, ParseKv(config));
     return result == Result::SUCCESS ? 0 : Fail("reconfigure", result);
 }
 
 int jst_shim_compute(void* handle) {
+    const ContextRestore restore;
     auto* s = static_cast<Session*>(handle);
     const auto t0 = std::chrono::steady_clock::now();
     const auto result = s->flowgraph->compute();
@@ -367,6 +404,7 @@ void* jst_shim_output_pointer(void* handle, const char* block, const char* port)
 }
 
 int jst_shim_output_read(void* handle, const char* block, const char* port, void* dst, uint64_t bytes) {
+    const ContextRestore restore;
     auto* s = static_cast<Session*>(handle);
     Tensor tensor;
     const auto result = FindOutput(s, block, port, tensor);
@@ -378,7 +416,7 @@ int jst_shim_output_read(void* handle, const char* block, const char* port, void
         return -1;
     }
     if (tensor.device() == DeviceType::CUDA) {
-        const auto err = cudaMemcpy(dst, RawPointer(tensor), bytes, cudaMemcpyDeviceToHost);
+        const auto err = cudaMemcpy(dst, RawPointer(tensor), bytes, cudaMemcpyDefault);
         if (err != cudaSuccess) {
             g_error = std::string("output_read: ") + cudaGetErrorString(err);
             return -1;
@@ -428,7 +466,7 @@ struct WaterfallPeek : Modules::WaterfallImpl {
 int64_t CopyOut(const Tensor& tensor, float* dst, const uint64_t capacity) {
     const uint64_t n = std::min<uint64_t>(capacity, tensor.size());
     if (n != 0 && tensor.device() == DeviceType::CUDA) {
-        if (cudaMemcpy(dst, RawPointer(tensor), n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        if (cudaMemcpy(dst, RawPointer(tensor), n * sizeof(float), cudaMemcpyDefault) != cudaSuccess) {
             g_error = "viz read: device copy failed";
             return -1;
         }
@@ -455,6 +493,7 @@ int jst_shim_viz_list(char* buffer, uint64_t capacity) {
 
 // signalPoints [n, 2] of a lineplot module / frequencyBins [height, n] of a waterfall module. Returns the element count.
 int64_t jst_shim_viz_read(const char* module, float* dst, uint64_t capacity) {
+    const ContextRestore restore;
     if (const auto it = Headless::Lineplots().find(module); it != Headless::Lineplots().end()) {
         return CopyOut(it->second->*LineplotPeek::points(), dst, capacity);
     }

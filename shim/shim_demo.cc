@@ -15,7 +15,7 @@ const char* jst_shim_last_error();
 void* jst_shim_create(int logLevel);
 void jst_shim_destroy(void* handle);
 int jst_shim_add_source(void* handle, const char* name, int dtype, int rank, const uint64_t* shape, int64_t sampleAxis,
-                        int64_t batchAxis, int64_t channelAxis, int device, const char* provider);
+                        int64_t batchAxis, int64_t channelAxis, int device, const char* provider, int mapped);
 int jst_shim_write_source(void* handle, const char* name, const void* data, uint64_t bytes);
 int jst_shim_add_block(void* handle, const char* name, const char* type, const char* config, const char* inputs,
                        int device, const char* provider);
@@ -48,7 +48,7 @@ bool Run(const Case& c, const int device, const char* provider, const std::vecto
         return false;
     }
     const uint64_t shape[2] = {c.rows, c.cols};
-    bool ok = jst_shim_add_source(s, "src", 1, 2, shape, 1, 0, -1, device, provider) == 0;
+    bool ok = jst_shim_add_source(s, "src", 1, 2, shape, 1, 0, -1, device, provider, 0) == 0;
     const std::string inputs = std::string(c.inputPort) + "=src.signal";
     ok = ok && jst_shim_add_block(s, "dut", c.type, c.config, inputs.c_str(), device, provider) == 0;
     for (const auto& x : cycles) {
