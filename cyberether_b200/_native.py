@@ -91,6 +91,7 @@ SIGNATURES = {
     "b200_fm_exec": (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_vp]),
     "b200_fm_reset": (c_int, [c_vp, c_vp]),
     "b200_fm_plan_destroy": (c_int, [c_vp]),
+    "b200_fm_nco_phases_host": (c_int, [c_f32, c_u64, c_u64, c_vp, P(c_u64), P(c_u64)]),
 }
 
 _lib = None

@@ -9,6 +9,10 @@
 // thread replaying its own samples from its carry-in in the reference's operation order.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -357,6 +361,36 @@ __global__ void __launch_bounds__(32) fm_wide_phase_kernel(float* __restrict__ p
     }
 }
 
+// The same phase sequence WITHOUT the serial chain. The NCO state is a single F32 and its update is input independent,
+// so the whole sequence is one orbit of a map on a finite set: the value right after a wrap is
+// fl(fl64(a) - 2 pi) for an F32 a in [2 pi, 2 pi + inc) — at most inc / ulp(2 pi) ~ 1e6 distinct values — hence the
+// post-wrap phase must repeat within ~1e6 laps = 2 pi / ulp(2 pi) ~ 1.3e7 samples, whatever the sample rate. The plan
+// walks that orbit ONCE on the host with the same three F32 operations (b200_fm_plan_create: a few tens of ms), keeps a
+// checkpoint every 4 samples over the transient (`pre` samples) and one period (`cycle` samples), and every call then
+// regenerates its slice of the sequence in parallel: sample n folds to orbit position pre + (n - pre) mod cycle, a
+// thread loads the checkpoint below it and steps <= 3 + 4 times with nco_step itself. Bit-identical to the serial walk
+// (tests/test_gpu_filter_fm.py compares against the reference over cycles; tests/test_index_algebra.py checks the
+// orbit bookkeeping on the host).
+__global__ void fm_wide_phase_table_kernel(float* __restrict__ phase, const float* __restrict__ checkpoints,
+                                           const uint64_t n0, const uint64_t len, const uint64_t pre,
+                                           const uint64_t cycle, const float inc) {
+    const uint64_t i0 = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) * 4;
+    if (i0 >= len) {
+        return;
+    }
+    const uint64_t n = n0 + i0;
+    const uint64_t m = n < pre ? n : pre + (n - pre) % cycle;
+    float ph = checkpoints[m >> 2];
+    for (uint32_t r = static_cast<uint32_t>(m & 3); r > 0; --r) {
+        ph = nco_step(ph, inc);
+    }
+    const uint32_t count = len - i0 < 4 ? static_cast<uint32_t>(len - i0) : 4u;
+    for (uint32_t k = 0; k < count; ++k) {
+        phase[i0 + k] = ph;
+        ph = nco_step(ph, inc);
+    }
+}
+
 // Generic blocked scan over S-state systems. System must provide:
 //   static constexpr int S;  __device__ void step(float* state, uint64_t n, lane, bool replay)  — one sample, reference op order;
 //   returns false when the sample is skipped (non-finite discriminator).
@@ -660,9 +694,94 @@ struct b200_fm_plan {
     float* power;             // [pilot 16 | audio 64 | stereo 4]  A^kWideChunk, row-major
     float* scratch;           // [sum total | diff total | phase lane_len | chunk_resp | chunk_count]
     uint64_t scratch_total, scratch_lane_len;
+    // pilot NCO orbit (fm_wide_phase_table_kernel): checkpoints every 4 samples over transient + one period
+    float* nco_checkpoints = nullptr;
+    uint64_t nco_pre = 0, nco_cycle = 0;   // cycle == 0: no period found within the cap -> serial kernel
+    uint64_t nco_samples = 0;              // samples demodulated since the last reset (host-side, in submission order)
 };
 
 namespace {
+
+// Host twin of nco_step (same three IEEE F32 operations; volatile keeps every intermediate in F32).
+float nco_step_host(const float ph, const float inc) {
+    volatile float a = ph + inc;
+    if (a >= 6.2831854820251465f) {
+        volatile float d = a - 6.2831854820251465f;
+        volatile float w = d + 1.7484555314695172e-07f;
+        return w;
+    }
+    return a;
+}
+
+// Walks the NCO orbit from phase 0 until a post-wrap phase repeats. checkpoints[j] = phase of sample 4 j.
+bool walk_nco_orbit_uncached(const float inc, std::vector<float>* checkpoints, uint64_t* pre, uint64_t* cycle);
+
+// One walk (0.05 - 0.25 s) per phase increment and process: plans of the same sample rate share it.
+bool walk_nco_orbit(const float inc, std::vector<float>* checkpoints, uint64_t* pre, uint64_t* cycle) {
+    struct Orbit {
+        bool found;
+        std::vector<float> checkpoints;
+        uint64_t pre, cycle;
+    };
+    static std::mutex mutex;
+    static std::unordered_map<uint32_t, Orbit> cache;
+    uint32_t key;
+    memcpy(&key, &inc, sizeof(key));
+    std::lock_guard<std::mutex> guard(mutex);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        Orbit orbit{};
+        orbit.found = walk_nco_orbit_uncached(inc, &orbit.checkpoints, &orbit.pre, &orbit.cycle);
+        it = cache.emplace(key, std::move(orbit)).first;
+    }
+    *checkpoints = it->second.checkpoints;
+    *pre = it->second.pre;
+    *cycle = it->second.cycle;
+    return it->second.found;
+}
+
+bool walk_nco_orbit_uncached(const float inc, std::vector<float>* checkpoints, uint64_t* pre, uint64_t* cycle) {
+    constexpr uint64_t kCap = 1ull << 25;          // > 2 pi / ulp(2 pi) = 1.3e7 samples: the repeat must come earlier
+    std::unordered_map<uint32_t, uint64_t> seen;
+    seen.reserve(1u << 21);
+    checkpoints->clear();
+    float ph = 0.0f;
+    uint32_t bits;
+    memcpy(&bits, &ph, sizeof(bits));
+    seen.emplace(bits, 0);
+    bool found = false;
+    uint64_t n = 0;
+    for (; n < kCap; ++n) {
+        if ((n & 3) == 0) {
+            checkpoints->push_back(ph);
+        }
+        const float next = nco_step_host(ph, inc);
+        if (next < ph) {                             // wrapped: `next` starts a lap
+            memcpy(&bits, &next, sizeof(bits));
+            const auto it = seen.find(bits);
+            if (it != seen.end()) {
+                *pre = it->second;
+                *cycle = n + 1 - it->second;
+                found = true;
+                ph = next;
+                ++n;
+                break;
+            }
+            seen.emplace(bits, n + 1);
+        }
+        ph = next;
+    }
+    if (!found) {
+        return false;
+    }
+    for (int extra = 0; extra < 8; ++extra, ++n) {   // the checkpoint at and just past pre + cycle
+        if ((n & 3) == 0) {
+            checkpoints->push_back(ph);
+        }
+        ph = nco_step_host(ph, inc);
+    }
+    return true;
+}
 
 // A^kWideChunk of a linear update, evaluated in F64 by stepping unit vectors through `homogeneous`.
 template <int S, class Fn>
@@ -849,6 +968,20 @@ int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wi
         }
         pl->power = static_cast<float*>(dev);
         pl->wide_state = static_cast<float*>(wst);
+        std::vector<float> checkpoints;
+        uint64_t pre = 0, cycle = 0;
+        if (walk_nco_orbit(w.pilot_phase_increment, &checkpoints, &pre, &cycle)) {
+            void* cp = nullptr;
+            if (b200_malloc(ctx, checkpoints.size() * sizeof(float), &cp) != B200_SUCCESS ||
+                cudaMemcpy(cp, checkpoints.data(), checkpoints.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaFree(cp);
+                b200_fm_plan_destroy(pl);
+                return fail("b200_fm_plan_create: NCO orbit upload failed");
+            }
+            pl->nco_checkpoints = static_cast<float*>(cp);
+            pl->nco_pre = pre;
+            pl->nco_cycle = cycle;
+        }
     }
     cudaStreamSynchronize(cudaStreamLegacy);   // uploads / zero-fills above ran on the legacy stream: settle them before a non-blocking stream executes
     *plan = pl;
@@ -862,6 +995,7 @@ int b200_fm_reset(b200_fm_plan* plan, b200_stream stream) {
     if (plan->wide) {
         const size_t state_floats = 1 + plan->lanes * 4 + 2 * plan->lanes * 8 + plan->lanes * 2;
         B200_CUDA_CHECK(cudaMemsetAsync(plan->wide_state, 0, state_floats * sizeof(float), as_stream(stream)));
+        plan->nco_samples = 0;
     }
     return B200_SUCCESS;
 }
@@ -907,8 +1041,16 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
             B200_SUCCESS) {
             return B200_ERROR;
         }
-        fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
+        if (plan->nco_cycle != 0) {
+            const uint64_t quads = (lane_len + 3) / 4;
+            fm_wide_phase_table_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, s>>>(
+                phase, plan->nco_checkpoints, plan->nco_samples, lane_len, plan->nco_pre, plan->nco_cycle,
+                plan->wc.pilot_phase_increment);
+        } else {
+            fm_wide_phase_kernel<<<1, 32, 0, s>>>(phase, phase_state, lane_len, plan->wc.pilot_phase_increment);
+        }
         B200_LAUNCH_CHECK();
+        plan->nco_samples += lane_len;
         const unsigned ucap = static_cast<unsigned>(cap);
         PilotSystem pilot{sum, phase, diff, at, plan->wc.pilot_alpha};
         if (run_scan(pilot, chunk_resp, chunk_count, plan->power, pilot_state, plan->lanes, lane_len, chunks_per_lane,
@@ -956,7 +1098,38 @@ int b200_fm_plan_destroy(b200_fm_plan* plan) {
     cudaFree(plan->wide_state);
     cudaFree(plan->power);
     cudaFree(plan->scratch);
+    cudaFree(plan->nco_checkpoints);
     delete plan;
+    return B200_SUCCESS;
+}
+
+/* Host-only twin of the wideband pilot NCO bookkeeping (walk_nco_orbit + the fold of fm_wide_phase_table_kernel): the
+ * phases of samples n0 .. n0 + len - 1 since reset, and the orbit's transient / period. For tests and diagnostics. */
+int b200_fm_nco_phases_host(float sample_rate, uint64_t n0, uint64_t len, float* out, uint64_t* pre, uint64_t* cycle) {
+    B200_REQUIRE(std::isfinite(sample_rate) && sample_rate > 0.0f, "b200_fm_nco_phases_host: bad sample rate");
+    const double kPi = 3.14159265358979323846;
+    const float inc = static_cast<float>(2.0f * kPi * 19e3f / sample_rate);      // as b200_fm_plan_create
+    std::vector<float> checkpoints;
+    uint64_t p = 0, c = 0;
+    B200_REQUIRE(walk_nco_orbit(inc, &checkpoints, &p, &c), "b200_fm_nco_phases_host: no period within the cap");
+    if (pre) {
+        *pre = p;
+    }
+    if (cycle) {
+        *cycle = c;
+    }
+    for (uint64_t i0 = 0; out && i0 < len; i0 += 4) {
+        const uint64_t n = n0 + i0;
+        const uint64_t m = n < p ? n : p + (n - p) % c;
+        float ph = checkpoints[m >> 2];
+        for (uint64_t r = m & 3; r > 0; --r) {
+            ph = nco_step_host(ph, inc);
+        }
+        for (uint64_t k = 0; k < 4 && i0 + k < len; ++k) {
+            out[i0 + k] = ph;
+            ph = nco_step_host(ph, inc);
+        }
+    }
     return B200_SUCCESS;
 }
 

@@ -323,6 +323,10 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
                  b200_stream stream);
 int b200_fm_reset(b200_fm_plan* plan, b200_stream stream);
 int b200_fm_plan_destroy(b200_fm_plan* plan);
+/* Host-only: the wideband decoder's pilot NCO phases (F32 running sum with wrap, fm/module_impl_native_cpu.cc:172-175) of
+ * samples n0 .. n0 + len - 1 since reset, reconstructed from the orbit table the plan uses on the device instead of a
+ * serial walk (the F32 state is periodic: *pre transient samples, then *cycle samples repeating). out may be NULL. */
+int b200_fm_nco_phases_host(float sample_rate, uint64_t n0, uint64_t len, float* out, uint64_t* pre, uint64_t* cycle);
 
 #ifdef __cplusplus
 }

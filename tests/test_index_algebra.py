@@ -213,3 +213,54 @@ def test_fm_nco_wrap_identity_exhaustive():
     reference = (a.astype(np.float64) - two_pi).astype(np.float32)
     ours = ((a - t).astype(np.float32) + c).astype(np.float32)
     assert len(a) == 1 << 21 and np.array_equal(reference, ours)
+
+
+def test_fm_wide_nco_orbit_table_reproduces_the_serial_walk():
+    """The wideband pilot NCO is an F32 running sum with wrap (fm/module_impl_native_cpu.cc:172-175). Its state is
+    one float and the update is input independent, so the sequence is eventually periodic; the plan walks the orbit
+    once and regenerates any slice in parallel (fm_wide_phase_table_kernel). Host twin of that bookkeeping
+    (b200_fm_nco_phases_host) against a plain serial F32 walk, for three sample rates, at the stream start, across
+    the transient / period boundary and many periods later."""
+    import ctypes
+    from cyberether_b200 import _native
+    lib = _native.load()
+    lib.b200_fm_nco_phases_host.argtypes = [ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
+                                            ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    two_pi = np.float64(2.0) * np.float64(3.14159265358979323846)
+
+    def serial(inc, count):
+        out = np.empty(count, np.float32)
+        ph = np.float32(0.0)
+        for i in range(count):
+            out[i] = ph
+            ph = np.float32(ph + inc)
+            if np.float64(ph) >= two_pi:                                   # the reference's F64 compare and subtract
+                ph = np.float32(np.float64(ph) - two_pi)
+        return out
+
+    for rate in (250e3, 200e3, 1.2e6):
+        inc = np.float32(np.float32(2.0) * np.float64(3.14159265358979323846) * np.float32(19e3) / np.float32(rate))
+        pre, cycle = ctypes.c_uint64(), ctypes.c_uint64()
+        head = np.empty(60000, np.float32)
+        _native.check(lib.b200_fm_nco_phases_host(rate, 0, head.size, head.ctypes.data_as(ctypes.c_void_p),
+                                                  ctypes.byref(pre), ctypes.byref(cycle)))
+        assert 0 < cycle.value <= 1 << 24 and pre.value < 1 << 24
+        want = serial(inc, head.size)
+        assert np.array_equal(head, want), rate
+        # any later slice continues the same recurrence: step the serial rule from its first element
+        for n0 in (pre.value + cycle.value - 7, pre.value + 3 * cycle.value + 12345, 10 ** 12 + 1):
+            part = np.empty(5000, np.float32)
+            _native.check(lib.b200_fm_nco_phases_host(rate, n0, part.size, part.ctypes.data_as(ctypes.c_void_p), None, None))
+            ph = part[0]
+            for i in range(1, part.size):
+                ph = np.float32(ph + inc)
+                if np.float64(ph) >= two_pi:
+                    ph = np.float32(np.float64(ph) - two_pi)
+                assert part[i] == ph, (rate, n0, i)
+        # periodicity claim itself: P(n) == P(n + cycle) for n >= pre
+        a = np.empty(4096, np.float32)
+        b = np.empty(4096, np.float32)
+        _native.check(lib.b200_fm_nco_phases_host(rate, pre.value, a.size, a.ctypes.data_as(ctypes.c_void_p), None, None))
+        _native.check(lib.b200_fm_nco_phases_host(rate, pre.value + cycle.value, b.size, b.ctypes.data_as(ctypes.c_void_p),
+                                                  None, None))
+        assert np.array_equal(a, b)
