@@ -137,13 +137,15 @@ __device__ __forceinline__ float2 spectral_epilogue2(const float2 X0, const floa
     const int b1 = __float_as_int(AGC ? sqrt_approx(p1) * gain : sqrt_approx(p1));
     const float2 f = make_float2(__int_as_float((b0 & 0x007fffff) | 0x3f000000),
                                  __int_as_float((b1 & 0x007fffff) | 0x3f000000));
-    // (float)(biased exponent field); the frexp bias (-126) is folded into the last polynomial constant.
-    const float2 e = make_float2(static_cast<float>(b0 >> 23), static_cast<float>(b1 >> 23));
+    // (float)(biased exponent field) without I2F (a quarter-rate XU instruction next to the three MUFU per output):
+    // (b >> 23) | 0x4B000000 is the F32 2^23 + exponent, exact; the 2^23 and the frexp bias (-126) leave in one exact
+    // integer-valued addition below, so the result is bit-identical to the conversion.
+    const float2 e = make_float2(__int_as_float((b0 >> 23) | 0x4B000000), __int_as_float((b1 >> 23) | 0x4B000000));
     float2 y = __ffma2_rn(make_float2(1.23149591368684f, 1.23149591368684f), f,
                           make_float2(-4.11852516267426f, -4.11852516267426f));
     y = __ffma2_rn(y, f, make_float2(6.02197014179219f, 6.02197014179219f));
     y = __ffma2_rn(y, f, make_float2(-3.13396450166353f, -3.13396450166353f));
-    y = __fadd2_rn(y, __fadd2_rn(e, make_float2(-126.0f, -126.0f)));
+    y = __fadd2_rn(y, __fadd2_rn(e, make_float2(-8388734.0f, -8388734.0f)));      // - (2^23 + 126)
     if constexpr (MODE == MODE_AMP) {
         const float2 r = __ffma2_rn(y, make_float2(p.amp_scale, p.amp_scale), make_float2(p.amp_coeff, p.amp_coeff));
         return make_float2(p0 == 0.0f ? -INFINITY : r.x, p1 == 0.0f ? -INFINITY : r.y);

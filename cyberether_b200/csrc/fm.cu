@@ -304,7 +304,6 @@ struct FmWideCoeffs {
     Biquad lowpass[3];
 };
 
-constexpr int kWideChunk = 256;
 
 // FmImpl::applyBiquad (src/domains/dsp/fm/module_impl.cc:157-164), transposed direct form II, no FMA.
 __device__ __forceinline__ float biquad_step(const float x, const Biquad& c, float& z1, float& z2) {
@@ -392,148 +391,271 @@ __global__ void fm_wide_phase_table_kernel(float* __restrict__ phase, const floa
 }
 
 // Generic blocked scan over S-state systems. System must provide:
-//   static constexpr int S;  __device__ void step(float* state, uint64_t n, lane, bool replay)  — one sample, reference op order;
-//   returns false when the sample is skipped (non-finite discriminator).
-template <class System>
-__global__ void scan_reduce_kernel(const System sys, float* __restrict__ chunk_resp, int* __restrict__ chunk_count,
-                                   const uint64_t lanes, const uint64_t lane_len, const uint64_t chunks_per_lane) {
-    const uint64_t total = lanes * chunks_per_lane;
-    for (uint64_t c = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; c < total;
-         c += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-        const uint64_t lane = c / chunks_per_lane, n0 = (c % chunks_per_lane) * kWideChunk;
-        float st[System::S];
+//   static constexpr int S;  __device__ bool step(float* state, uint64_t n, lane, bool replay)  — one sample, reference
+//   op order; returns false when the sample is skipped (non-finite discriminator); step_homogeneous(state).
+//
+// Every sample is an affine map of the state, state <- A state + u(n) (A constant per system), and a skipped sample is
+// the identity, so a run of samples is the pair (m, b): m = number of applied samples, b = its zero-state response, and
+// the state after it is A^m state + b. Pairs compose as (m2, b2) o (m1, b1) = (m1 + m2, A^m2 b1 + b2); A^m is applied
+// from a table of A^(2^k) (F64 on the host, rounded to F32) by the binary digits of m — one matrix-vector product for
+// the regular power-of-two run lengths, a few for runs shortened by non-finite samples.
+//   scan_tile_kernel    a thread steps kScanC samples from zero state (reference op order), the CTA scans the 256 pairs
+//                       of its tile (warp Kogge-Stone by shuffles, then across the 8 warps), stores every thread's
+//                       exclusive in-tile prefix and the tile aggregate;
+//   scan_tiles_kernel   one warp per lane composes the tile aggregates 32 at a time into per-tile carry-in states and the
+//                       lane's carry-out for the next call;
+//   scan_replay_kernel  thread carry-in = A^m_prefix tile_carry + b_prefix, then the kScanC samples are replayed with the
+//                       reference's own operation order and the outputs written.
+// Round 1 stepped 256-sample chunks in one thread each (2048 threads for 2^19 samples, stride-256 reads) and chained the
+// 2048 chunk carries serially: 1.0 ms per 2^19 samples for the three systems.
+constexpr int kScanC = 16;
+constexpr int kScanThreads = 256;
+constexpr int kScanTile = kScanC * kScanThreads;      // 4096 samples
+constexpr int kPowBits = 40;                          // A^(2^k), k < 40: runs up to 2^40 samples
+
+// v <- A^m v with the table pw[k][S*S] (row-major) in shared or global memory
+template <int S>
+__device__ __forceinline__ void apply_power(const float* __restrict__ pw, uint64_t m, float (&v)[S]) {
+    for (int k = 0; m != 0 && k < kPowBits; ++k, m >>= 1) {
+        if (m & 1) {
+            const float* a = pw + k * S * S;
+            float r[S];
 #pragma unroll
-        for (int i = 0; i < System::S; ++i) {
-            st[i] = 0.0f;
-        }
-        int count = 0;
-        for (uint64_t n = n0; n < n0 + kWideChunk && n < lane_len; ++n) {
-            count += sys.step(st, n, lane, false) ? 1 : 0;
-        }
+            for (int i = 0; i < S; ++i) {
+                float acc = 0.0f;
 #pragma unroll
-        for (int i = 0; i < System::S; ++i) {
-            chunk_resp[c * System::S + i] = st[i];
+                for (int j = 0; j < S; ++j) {
+                    acc = fmaf(a[i * S + j], v[j], acc);
+                }
+                r[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                v[i] = r[i];
+            }
         }
-        chunk_count[c] = count;
     }
 }
 
-// carry-in of chunk c overwrites its response slot; `power` is A^kWideChunk (row-major S x S, F32).
-// One warp per lane. The recurrence over chunks is sequential, but its inputs are not: the warp loads the responses
-// of 32 chunks at once (the next batch is requested before the current one is consumed), every lane then steps the
-// same recurrence — chunk k's response arrives by shuffle from lane k — and lane k keeps the carry-in of its own chunk.
-// (A single thread walking the chunks paid a full global-memory latency per chunk: 0.6-0.9 ms per 2048 chunks.)
-template <class System>
-__global__ void __launch_bounds__(32) scan_carry_kernel(const System sys, float* __restrict__ chunk_resp,
-                                                        const int* __restrict__ chunk_count,
-                                                        const float* __restrict__ power, float* __restrict__ lane_state,
-                                                        const uint64_t lanes, const uint64_t chunks_per_lane) {
-    constexpr int S = System::S;
-    const uint32_t lid = threadIdx.x;
-    float a[S * S];
+// Inclusive scan of (m, b) pairs over the lanes of a warp, lane 0 = earliest samples.
+template <int S>
+__device__ __forceinline__ void warp_scan_pairs(const float* __restrict__ pw, uint64_t& m, float (&b)[S]) {
+    const uint32_t lid = threadIdx.x & 31;
 #pragma unroll
-    for (int i = 0; i < S * S; ++i) {
-        a[i] = power[i];
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint64_t m_left = __shfl_up_sync(0xffffffffu, m, off);
+        float left[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            left[i] = __shfl_up_sync(0xffffffffu, b[i], off);
+        }
+        if (lid >= static_cast<uint32_t>(off)) {
+            apply_power<S>(pw, m, left);              // A^m_mine * b_left
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                b[i] += left[i];
+            }
+            m += m_left;
+        }
     }
-    for (uint64_t lane = blockIdx.x; lane < lanes; lane += gridDim.x) {
-        float* const base = chunk_resp + lane * chunks_per_lane * S;
-        const int* const counts = chunk_count + lane * chunks_per_lane;
+}
+
+template <int S>
+__device__ __forceinline__ void load_power_table(const float* __restrict__ power, float* pw_smem) {
+    for (int i = threadIdx.x; i < kPowBits * S * S; i += blockDim.x) {
+        pw_smem[i] = power[i];
+    }
+    __syncthreads();
+}
+
+// tile t covers samples [chunk * kScanTile, +kScanTile) of lane; tiles are numbered lane-major: t = lane * tiles_per_lane + chunk
+template <class System>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_kernel(const System sys, const float* __restrict__ power,
+                                                                  float* __restrict__ thread_prefix,   // [threads][S + 1]
+                                                                  float* __restrict__ tile_agg,        // [tiles][S + 1]
+                                                                  const uint64_t lanes, const uint64_t lane_len,
+                                                                  const uint64_t tiles_per_lane) {
+    constexpr int S = System::S;
+    __shared__ float pw[kPowBits * S * S];
+    __shared__ float warp_b[kScanThreads / 32][S];
+    __shared__ uint64_t warp_m[kScanThreads / 32];
+    load_power_table<S>(power, pw);
+    const uint64_t tiles = lanes * tiles_per_lane;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t lane = tile / tiles_per_lane, chunk = tile - lane * tiles_per_lane;
+        const uint64_t n0 = chunk * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanC;
         float st[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            st[i] = lane_state[lane * S + i];
+            st[i] = 0.0f;
         }
-        float resp_next[S];
-        int count_next = 0;
-        auto fetch = [&](const uint64_t c0) {
-            const uint64_t c = c0 + lid;
+        uint64_t m = 0;
+        for (uint64_t n = n0; n < n0 + kScanC && n < lane_len; ++n) {
+            m += sys.step(st, n, lane, false) ? 1 : 0;
+        }
+        // inclusive scan inside the warp, then across the warps of the CTA
+        warp_scan_pairs<S>(pw, m, st);
+        const uint32_t wid = threadIdx.x >> 5, lid = threadIdx.x & 31;
+        if (lid == 31) {
+            warp_m[wid] = m;
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                resp_next[i] = c < chunks_per_lane ? base[c * S + i] : 0.0f;
+                warp_b[wid][i] = st[i];
             }
-            count_next = c < chunks_per_lane ? counts[c] : 0;
-        };
-        fetch(0);
-        for (uint64_t c0 = 0; c0 < chunks_per_lane; c0 += 32) {
-            float resp_mine[S], carry_mine[S];
+        }
+        __syncthreads();
+        // exclusive prefix of this thread = (pairs of the earlier warps) then (inclusive of the lane to the left)
+        uint64_t pm = 0;
+        float pb[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            pb[i] = 0.0f;
+        }
+        for (uint32_t w = 0; w < wid; ++w) {         // <= 7 compositions: (warp w) after (prefix so far)
+            apply_power<S>(pw, warp_m[w], pb);
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                resp_mine[i] = resp_next[i];
-                carry_mine[i] = 0.0f;
+                pb[i] += warp_b[w][i];
             }
-            const int count_mine = count_next;
-            if (c0 + 32 < chunks_per_lane) {
-                fetch(c0 + 32);                                  // in flight while this batch is stepped
+            pm += warp_m[w];
+        }
+        const uint64_t m_left = __shfl_up_sync(0xffffffffu, m, 1);
+        float left[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            left[i] = __shfl_up_sync(0xffffffffu, st[i], 1);
+        }
+        if (lid != 0) {                               // (inclusive of the left lane) after (earlier warps)
+            apply_power<S>(pw, m_left, pb);
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                pb[i] += left[i];
             }
-            const int batch = static_cast<int>(chunks_per_lane - c0 < 32 ? chunks_per_lane - c0 : 32);
-            for (int k = 0; k < batch; ++k) {
-                float resp[S], next[S];
+            pm += m_left;
+        }
+        float* const dst = thread_prefix + (tile * kScanThreads + threadIdx.x) * (S + 1);
+        dst[0] = __uint_as_float(static_cast<uint32_t>(pm));        // < kScanTile
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            dst[1 + i] = pb[i];
+        }
+        if (threadIdx.x == kScanThreads - 1) {
+            // tile aggregate = (this thread's inclusive warp pair (m, st)) after (the earlier warps)
+            float agg[S];
+            uint64_t am = 0;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                agg[i] = 0.0f;
+            }
+            for (uint32_t w = 0; w < wid; ++w) {
+                apply_power<S>(pw, warp_m[w], agg);
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
-                    resp[i] = __shfl_sync(0xffffffffu, resp_mine[i], k);
-                    if (static_cast<int>(lid) == k) {
-                        carry_mine[i] = st[i];                   // carry-in of chunk c0 + k
-                    }
+                    agg[i] += warp_b[w][i];
                 }
-                const int count = __shfl_sync(0xffffffffu, count_mine, k);
-                if (count == kWideChunk) {
+                am += warp_m[w];
+            }
+            apply_power<S>(pw, m, agg);
+            float* const out = tile_agg + tile * (S + 1);
+            out[0] = __uint_as_float(static_cast<uint32_t>(am + m));
 #pragma unroll
-                    for (int i = 0; i < S; ++i) {
-                        float acc = resp[i];
+            for (int i = 0; i < S; ++i) {
+                out[1 + i] = agg[i] + st[i];
+            }
+        }
+        __syncthreads();                              // warp_m / warp_b are reused by the next tile
+    }
+}
+
+// One warp per lane: carry-in of every tile (overwrites the tile's aggregate slot) and the lane's carry-out.
+template <class System>
+__global__ void __launch_bounds__(32) scan_tiles_kernel(const float* __restrict__ power, float* __restrict__ tile_agg,
+                                                        float* __restrict__ lane_state, const uint64_t lanes,
+                                                        const uint64_t tiles_per_lane) {
+    constexpr int S = System::S;
+    __shared__ float pw[kPowBits * S * S];
+    load_power_table<S>(power, pw);
+    const uint32_t lid = threadIdx.x;
+    for (uint64_t lane = blockIdx.x; lane < lanes; lane += gridDim.x) {
+        float carry[S];                                // state before the current batch of 32 tiles (uniform across lanes)
 #pragma unroll
-                        for (int j = 0; j < S; ++j) {
-                            acc = fmaf(a[i * S + j], st[j], acc);
-                        }
-                        next[i] = acc;
-                    }
-                } else {
-                    // homogeneous response by stepping `count` zero-input samples, then add the zero-state response
+        for (int i = 0; i < S; ++i) {
+            carry[i] = lane_state[lane * S + i];
+        }
+        float* const base = tile_agg + lane * tiles_per_lane * (S + 1);
+        for (uint64_t t0 = 0; t0 < tiles_per_lane; t0 += 32) {
+            const uint64_t t = t0 + lid;
+            const bool live = t < tiles_per_lane;
+            uint64_t m = live ? __float_as_uint(base[t * (S + 1)]) : 0;
+            float b[S];
 #pragma unroll
-                    for (int i = 0; i < S; ++i) {
-                        next[i] = st[i];
-                    }
-                    for (int q = 0; q < count; ++q) {
-                        sys.step_homogeneous(next);
-                    }
+            for (int i = 0; i < S; ++i) {
+                b[i] = live ? base[t * (S + 1) + 1 + i] : 0.0f;
+            }
+            warp_scan_pairs<S>(pw, m, b);              // inclusive over the batch
+            // state after tile t = A^m_incl carry + b_incl; carry-in of tile t = the state after tile t - 1
+            float after[S];
 #pragma unroll
-                    for (int i = 0; i < S; ++i) {
-                        next[i] += resp[i];
-                    }
-                }
+            for (int i = 0; i < S; ++i) {
+                after[i] = carry[i];
+            }
+            apply_power<S>(pw, m, after);
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                after[i] += b[i];
+            }
+            float in[S];
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                const float prev = __shfl_up_sync(0xffffffffu, after[i], 1);
+                in[i] = lid == 0 ? carry[i] : prev;
+            }
+            if (live) {
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
-                    st[i] = next[i];
+                    base[t * (S + 1) + 1 + i] = in[i];
                 }
             }
-            if (static_cast<int>(lid) < batch) {
+            const uint32_t last = static_cast<uint32_t>(tiles_per_lane - t0 < 32 ? tiles_per_lane - t0 : 32) - 1;
 #pragma unroll
-                for (int i = 0; i < S; ++i) {
-                    base[(c0 + lid) * S + i] = carry_mine[i];
-                }
+            for (int i = 0; i < S; ++i) {
+                carry[i] = __shfl_sync(0xffffffffu, after[i], last);
             }
         }
         if (lid == 0) {
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                lane_state[lane * S + i] = st[i];
+                lane_state[lane * S + i] = carry[i];
             }
         }
     }
 }
 
 template <class System>
-__global__ void scan_replay_kernel(const System sys, const float* __restrict__ chunk_carry, const uint64_t lanes,
-                                   const uint64_t lane_len, const uint64_t chunks_per_lane) {
-    const uint64_t total = lanes * chunks_per_lane;
-    for (uint64_t c = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; c < total;
-         c += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-        const uint64_t lane = c / chunks_per_lane, n0 = (c % chunks_per_lane) * kWideChunk;
-        float st[System::S];
+__global__ void __launch_bounds__(kScanThreads) scan_replay_kernel(const System sys, const float* __restrict__ power,
+                                                                    const float* __restrict__ thread_prefix,
+                                                                    const float* __restrict__ tile_carry,
+                                                                    const uint64_t lanes, const uint64_t lane_len,
+                                                                    const uint64_t tiles_per_lane) {
+    constexpr int S = System::S;
+    __shared__ float pw[kPowBits * S * S];
+    load_power_table<S>(power, pw);
+    const uint64_t tiles = lanes * tiles_per_lane;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t lane = tile / tiles_per_lane, chunk = tile - lane * tiles_per_lane;
+        const uint64_t n0 = chunk * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanC;
+        const float* const pre = thread_prefix + (tile * kScanThreads + threadIdx.x) * (S + 1);
+        float st[S];
 #pragma unroll
-        for (int i = 0; i < System::S; ++i) {
-            st[i] = chunk_carry[c * System::S + i];
+        for (int i = 0; i < S; ++i) {
+            st[i] = tile_carry[tile * (S + 1) + 1 + i];
         }
-        for (uint64_t n = n0; n < n0 + kWideChunk && n < lane_len; ++n) {
+        apply_power<S>(pw, __float_as_uint(pre[0]), st);
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            st[i] += pre[1 + i];
+        }
+        for (uint64_t n = n0; n < n0 + kScanC && n < lane_len; ++n) {
             sys.step(st, n, lane, true);
         }
     }
@@ -691,8 +813,8 @@ struct b200_fm_plan {
     // wide mode
     FmWideCoeffs wc;
     float* wide_state;        // [phase(1) | pilot lanes*4 | audio 2*lanes*8 | stereo lanes*2]
-    float* power;             // [pilot 16 | audio 64 | stereo 4]  A^kWideChunk, row-major
-    float* scratch;           // [sum total | diff total | phase lane_len | chunk_resp | chunk_count]
+    float* power;             // A^(2^k), k < kPowBits: [pilot kPowBits x 16 | audio kPowBits x 64 | stereo kPowBits x 4]
+    float* scratch;           // [sum total | diff total | phase lane_len | thread prefixes | tile aggregates]
     uint64_t scratch_total, scratch_lane_len;
     // pilot NCO orbit (fm_wide_phase_table_kernel): checkpoints every 4 samples over transient + one period
     float* nco_checkpoints = nullptr;
@@ -783,17 +905,35 @@ bool walk_nco_orbit_uncached(const float inc, std::vector<float>* checkpoints, u
     return true;
 }
 
-// A^kWideChunk of a linear update, evaluated in F64 by stepping unit vectors through `homogeneous`.
+// A^(2^k), k < kPowBits, of a linear update: the one-step matrix from unit vectors stepped through `homogeneous` in
+// F64, then repeated squaring in F64; each power rounded to F32 ([k][S*S], row-major).
 template <int S, class Fn>
-void transition_power(Fn homogeneous, float* out) {
+void transition_powers(Fn homogeneous, float* out) {
+    double a[S * S];
     for (int j = 0; j < S; ++j) {
         double st[S] = {};
         st[j] = 1.0;
-        for (int k = 0; k < kWideChunk; ++k) {
-            homogeneous(st);
-        }
+        homogeneous(st);
         for (int i = 0; i < S; ++i) {
-            out[i * S + j] = static_cast<float>(st[i]);
+            a[i * S + j] = st[i];
+        }
+    }
+    for (int k = 0; k < kPowBits; ++k) {
+        for (int i = 0; i < S * S; ++i) {
+            out[k * S * S + i] = static_cast<float>(a[i]);
+        }
+        double sq[S * S];
+        for (int i = 0; i < S; ++i) {
+            for (int j = 0; j < S; ++j) {
+                double acc = 0.0;
+                for (int q = 0; q < S; ++q) {
+                    acc += a[i * S + q] * a[q * S + j];
+                }
+                sq[i * S + j] = acc;
+            }
+        }
+        for (int i = 0; i < S * S; ++i) {
+            a[i] = sq[i];
         }
     }
 }
@@ -808,16 +948,18 @@ void biquad_h(const Biquad& c, double& z1, double& z2, double& x) {
 }  // namespace
 
 template <class System>
-static int run_scan(const System& sys, float* chunk_resp, int* chunk_count, const float* power, float* lane_state,
-                    uint64_t lanes, uint64_t lane_len, uint64_t chunks_per_lane, unsigned cap, cudaStream_t s) {
-    const uint64_t total = lanes * chunks_per_lane;
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((total + 63) / 64, cap));
-    scan_reduce_kernel<System><<<grid, 64, 0, s>>>(sys, chunk_resp, chunk_count, lanes, lane_len, chunks_per_lane);
+static int run_scan(const System& sys, float* thread_prefix, float* tile_agg, const float* power, float* lane_state,
+                    uint64_t lanes, uint64_t lane_len, uint64_t tiles_per_lane, unsigned cap, cudaStream_t s) {
+    const uint64_t tiles = lanes * tiles_per_lane;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, cap));
+    scan_tile_kernel<System><<<grid, kScanThreads, 0, s>>>(sys, power, thread_prefix, tile_agg, lanes, lane_len,
+                                                          tiles_per_lane);
     B200_LAUNCH_CHECK();
-    scan_carry_kernel<System><<<static_cast<unsigned>(std::min<uint64_t>(lanes, cap)), 32, 0, s>>>(
-        sys, chunk_resp, chunk_count, power, lane_state, lanes, chunks_per_lane);
+    scan_tiles_kernel<System><<<static_cast<unsigned>(std::min<uint64_t>(lanes, cap)), 32, 0, s>>>(
+        power, tile_agg, lane_state, lanes, tiles_per_lane);
     B200_LAUNCH_CHECK();
-    scan_replay_kernel<System><<<grid, 64, 0, s>>>(sys, chunk_resp, lanes, lane_len, chunks_per_lane);
+    scan_replay_kernel<System><<<grid, kScanThreads, 0, s>>>(sys, power, thread_prefix, tile_agg, lanes, lane_len,
+                                                            tiles_per_lane);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -933,33 +1075,33 @@ int b200_fm_plan_create(b200_ctx* ctx, uint64_t lanes, float sample_rate, int wi
             c.a1 = static_cast<float>(-2.0 * cosine / a0);
             c.a2 = static_cast<float>((1.0 - alpha) / a0);
         }
-        // Chunk transition matrices A^256 (F64 -> F32).
-        float host_power[16 + 64 + 4];
+        // Transition matrix powers A^(2^k) of the three systems (F64 -> F32): [pilot 4x4 | audio 8x8 | stereo 2x2] x kPowBits.
+        std::vector<float> host_power(static_cast<size_t>(kPowBits) * (16 + 64 + 4));
         const double pa = w.pilot_alpha;
-        transition_power<4>([pa](double* s) {
+        transition_powers<4>([pa](double* s) {
             s[0] += pa * (0.0 - s[0]);
             s[1] += pa * (0.0 - s[1]);
             s[2] += pa * (s[0] - s[2]);
             s[3] += pa * (s[1] - s[3]);
-        }, host_power);
-        transition_power<8>([&w](double* s) {
+        }, host_power.data());
+        transition_powers<8>([&w](double* s) {
             double x = 0.0;
             biquad_h(w.notch, s[0], s[1], x);
             biquad_h(w.lowpass[0], s[2], s[3], x);
             biquad_h(w.lowpass[1], s[4], s[5], x);
             biquad_h(w.lowpass[2], s[6], s[7], x);
-        }, host_power + 16);
+        }, host_power.data() + kPowBits * 16);
         const double da = w.deemphasis ? static_cast<double>(w.deemphasis_alpha) : 0.0;
-        transition_power<2>([da](double* s) {
+        transition_powers<2>([da](double* s) {
             s[0] += da * (0.0 - s[0]);
             s[1] += da * (0.0 - s[1]);
-        }, host_power + 80);
+        }, host_power.data() + kPowBits * (16 + 64));
         void* dev = nullptr;
         void* wst = nullptr;
         const size_t state_floats = 1 + lanes * 4 + 2 * lanes * 8 + lanes * 2;
-        if (b200_malloc(ctx, sizeof(host_power), &dev) != B200_SUCCESS ||
+        if (b200_malloc(ctx, host_power.size() * sizeof(float), &dev) != B200_SUCCESS ||
             b200_malloc(ctx, state_floats * sizeof(float), &wst) != B200_SUCCESS ||
-            cudaMemcpy(dev, host_power, sizeof(host_power), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaMemcpy(dev, host_power.data(), host_power.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
             cudaFree(dev);
             cudaFree(wst);
             cudaFree(pl->state);
@@ -1016,12 +1158,13 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
     (void)blocks;
 
     if (plan->wide) {
-        const uint64_t chunks_per_lane = (lane_len + kWideChunk - 1) / kWideChunk;
+        const uint64_t tiles_per_lane = (lane_len + kScanTile - 1) / kScanTile;
         const uint64_t vlanes = 2 * plan->lanes;
         if (plan->scratch_total < total || plan->scratch_lane_len < lane_len) {
             cudaFree(plan->scratch);
             plan->scratch = nullptr;
-            const uint64_t floats = 2 * total + lane_len + vlanes * chunks_per_lane * 8 + vlanes * chunks_per_lane;
+            // the widest system (audio: S = 8 over 2 * lanes virtual lanes) sizes the per-thread prefixes and tile slots
+            const uint64_t floats = 2 * total + lane_len + vlanes * tiles_per_lane * (kScanThreads + 1) * 9;
             B200_CUDA_CHECK(cudaMalloc(&plan->scratch, floats * sizeof(float)));
             plan->scratch_total = total;
             plan->scratch_lane_len = lane_len;
@@ -1029,8 +1172,8 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
         float* const sum = plan->scratch;
         float* const diff = sum + total;
         float* const phase = diff + total;
-        float* const chunk_resp = phase + lane_len;
-        int* const chunk_count = reinterpret_cast<int*>(chunk_resp + vlanes * chunks_per_lane * 8);
+        float* const thread_prefix = phase + lane_len;
+        float* const tile_agg = thread_prefix + vlanes * tiles_per_lane * kScanThreads * 9;
         float* const phase_state = plan->wide_state;
         float* const pilot_state = phase_state + 1;
         float* const audio_state = pilot_state + plan->lanes * 4;
@@ -1053,18 +1196,18 @@ int b200_fm_exec(b200_fm_plan* plan, const b200_cf32* x, float* out, uint64_t fr
         plan->nco_samples += lane_len;
         const unsigned ucap = static_cast<unsigned>(cap);
         PilotSystem pilot{sum, phase, diff, at, plan->wc.pilot_alpha};
-        if (run_scan(pilot, chunk_resp, chunk_count, plan->power, pilot_state, plan->lanes, lane_len, chunks_per_lane,
+        if (run_scan(pilot, thread_prefix, tile_agg, plan->power, pilot_state, plan->lanes, lane_len, tiles_per_lane,
                      ucap, s) != B200_SUCCESS) {
             return B200_ERROR;
         }
         AudioSystem audio{sum, diff, at, plan->wc.notch, {plan->wc.lowpass[0], plan->wc.lowpass[1], plan->wc.lowpass[2]}};
-        if (run_scan(audio, chunk_resp, chunk_count, plan->power + 16, audio_state, vlanes, lane_len, chunks_per_lane,
+        if (run_scan(audio, thread_prefix, tile_agg, plan->power + kPowBits * 16, audio_state, vlanes, lane_len, tiles_per_lane,
                      ucap, s) != B200_SUCCESS) {
             return B200_ERROR;
         }
         StereoSystem stereo{sum, diff, out, at, plan->wc.deemphasis_alpha, plan->wc.deemphasis};
-        if (run_scan(stereo, chunk_resp, chunk_count, plan->power + 80, stereo_state, plan->lanes, lane_len,
-                     chunks_per_lane, ucap, s) != B200_SUCCESS) {
+        if (run_scan(stereo, thread_prefix, tile_agg, plan->power + kPowBits * 80, stereo_state, plan->lanes, lane_len,
+                     tiles_per_lane, ucap, s) != B200_SUCCESS) {
             return B200_ERROR;
         }
         fm_state_update_kernel<<<static_cast<unsigned>((plan->lanes + 63) / 64), 64, 0, s>>>(
