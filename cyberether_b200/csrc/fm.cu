@@ -26,11 +26,36 @@ struct FmState {          // one per lane, device resident
 
 __device__ __forceinline__ bool finite2(const float2 v) { return isfinite(v.x) && isfinite(v.y); }
 
-// std::arg(std::conj(p) * c) * ref with the reference's F32 rounding sequence (no FMA contraction).
+// atan2 for finite arguments: a = min(|x|, |y|) / max(|x|, |y|) in [0, 1], atan(a) = a P(a^2) with a degree-8 minimax P
+// (max |error| 1.0e-7 evaluated in F32, i.e. < 2 ulp at pi/4; the fit is tools/atan_fit.py), octant fix-ups, IEEE signs
+// for zeros (atan2(+-0, x < 0 or -0) = +-pi). ~25 instructions against ~60 of libdevice's atan2f: the narrow kernel is
+// instruction-bound (one atan2 per 12 bytes), tools/fm_probe.py: 0.058 -> see DESIGN.md §4.5. The reference's std::arg is
+// glibc's correctly rounded atan2f; both sit inside the 1e-5 absolute tolerance of the fm tests by two orders.
+__device__ __forceinline__ float atan2_finite(const float y, const float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx == 0.0f ? 0.0f : __fdividef(mn, mx);
+    const float u = a * a;
+    float p = 0.0029035410843789577f;
+    p = fmaf(p, u, -0.016282962635159492f);
+    p = fmaf(p, u, 0.04303929582238197f);
+    p = fmaf(p, u, -0.07533670216798782f);
+    p = fmaf(p, u, 0.10654674470424652f);
+    p = fmaf(p, u, -0.14207133650779724f);
+    p = fmaf(p, u, 0.19993053376674652f);
+    p = fmaf(p, u, -0.3333309292793274f);
+    p = fmaf(p, u, 1.0f);
+    float r = p * a;
+    r = ay > ax ? 1.5707963705062866f - r : r;
+    r = __float_as_int(x) < 0 ? 3.1415927410125732f - r : r;
+    return copysignf(r, y);
+}
+
+// std::arg(std::conj(p) * c) * ref with the reference's F32 rounding sequence for the products (no FMA contraction).
 __device__ __forceinline__ float discriminate(const float2 p, const float2 c, const float ref) {
     const float re = __fadd_rn(__fmul_rn(p.x, c.x), __fmul_rn(p.y, c.y));
     const float im = __fsub_rn(__fmul_rn(p.x, c.y), __fmul_rn(p.y, c.x));
-    return __fmul_rn(atan2f(im, re), ref);
+    return __fmul_rn(atan2_finite(im, re), ref);
 }
 
 // ---- narrow mode in ONE pass: discriminator + de-emphasis with a decoupled look-back scan ---------------------
@@ -73,10 +98,11 @@ struct FmNarrowParams {
     uint64_t frames, lanes, frame_len, tiles_per_row, items;
     float ref, alpha;
     uint32_t epoch;
+    uint32_t lookback;      // predecessor tiles of finite samples after which (1 - alpha)^n < 2^-31, clamped to 1..32
 };
 
 template <bool DEEMPH, bool VEC>
-__global__ void __launch_bounds__(kFmTileThreads) fm_narrow_fused_kernel(const FmNarrowParams p) {
+__global__ void __launch_bounds__(kFmTileThreads, DEEMPH ? 6 : 8) fm_narrow_fused_kernel(const FmNarrowParams p) {
     __shared__ float warp_g[kFmTileThreads / 32], warp_o[kFmTileThreads / 32];
     const uint32_t t = threadIdx.x, lane_id = t & 31, warp = t >> 5;
     const float keep = 1.0f - p.alpha;
@@ -176,68 +202,79 @@ __global__ void __launch_bounds__(kFmTileThreads) fm_narrow_fused_kernel(const F
             }
             const float xg = lg * eg, xo = fmaf(lg, eo, lo);       // map of everything before this thread in the tile
 
-            // ---- 3. decoupled look-back, the whole CTA: 256 predecessors per round ---------------------------------
-            // A predecessor that already knows its carry-out y is the constant map (0, y); composing nearest-first, the
-            // first such map annihilates everything older, so the rounds stop as soon as one was seen.
+            // ---- 3. decoupled look-back by warp 0: 32 predecessors per round, nearest first -----------------------------
+            // A predecessor that already knows its carry-out y is the constant map (0, y) and ends the search. So does a
+            // vanishing gain: a full tile multiplies the state by (1 - alpha)^2048 (<= 0.26 at the module's maximum sample
+            // rate of 20 MHz with 75 us, 4e-48 -> 0 at 250 kHz), so once the composed gain of the tiles looked at is below
+            // 2^-31 nothing older can move the carry by half an ulp: normally ONE round over aggregates that the
+            // neighbouring tiles publish right after their step 2, instead of waiting for a tile ~600 ids back.
             FmScanSlot* const mine = p.slots + id;
             if (t == 0) {
                 st_slot(&mine->b, pack_slot((p.epoch << 2) | 1u, to));
                 st_slot(&mine->a, pack_slot((p.epoch << 2) | 1u, tg));
             }
-            float ag = 1.0f, ao = 0.0f;                              // map of the tiles looked at so far (nearest applied last)
-            for (uint64_t back = 1;; back += kFmTileThreads) {
-                const uint64_t steps = back + t;
-                float mg, mo;
-                bool is_carry;
-                if (steps * p.lanes > id) {                          // before the lane's first tile: the carried state
-                    is_carry = true;
-                    mg = 0.0f;
-                    mo = p.state[lane].deemphasis;
-                } else {
-                    const FmScanSlot* const slot = p.slots + (id - steps * p.lanes);
-                    unsigned long long a = ld_slot(&slot->a);
-                    while (static_cast<uint32_t>(a >> 34) != p.epoch) {
-                        a = ld_slot(&slot->a);
-                    }
-                    is_carry = ((a >> 32) & 3u) == 2u;
-                    if (is_carry) {
+            __syncthreads();                                         // warp_g / warp_o of step 2 consumed by every thread
+            if (warp == 0) {
+                float ag = 1.0f, ao = 0.0f;                          // map of the tiles looked at so far (nearest applied last)
+                // first round: only as many predecessors as a stream of finite samples needs for the gain to vanish
+                // (p.lookback, 1 for time constants up to ~95 samples): waiting on 32 neighbours that are all in flight
+                // makes every tile as slow as the slowest of them
+                uint32_t width = p.lookback;
+                for (uint64_t back = 1;; back += width, width = 32) {
+                    const uint64_t steps = back + lane_id;
+                    float mg, mo;
+                    bool is_carry;
+                    if (lane_id >= width) {                          // not examined this round: identity
+                        is_carry = false;
+                        mg = 1.0f;
+                        mo = 0.0f;
+                    } else if (steps * p.lanes > id) {               // before the lane's first tile: the carried state
+                        is_carry = true;
                         mg = 0.0f;
-                        mo = __uint_as_float(static_cast<uint32_t>(a));
+                        mo = p.state[lane].deemphasis;
                     } else {
-                        unsigned long long b = ld_slot(&slot->b);
-                        while (static_cast<uint32_t>(b >> 34) != p.epoch) {
-                            b = ld_slot(&slot->b);
+                        const FmScanSlot* const slot = p.slots + (id - steps * p.lanes);
+                        unsigned long long a = ld_slot(&slot->a);
+                        while (static_cast<uint32_t>(a >> 34) != p.epoch) {
+                            a = ld_slot(&slot->a);
                         }
-                        mg = __uint_as_float(static_cast<uint32_t>(a));
-                        mo = __uint_as_float(static_cast<uint32_t>(b));
+                        is_carry = ((a >> 32) & 3u) == 2u;
+                        if (is_carry) {
+                            mg = 0.0f;
+                            mo = __uint_as_float(static_cast<uint32_t>(a));
+                        } else {
+                            unsigned long long b = ld_slot(&slot->b);
+                            while (static_cast<uint32_t>(b >> 34) != p.epoch) {
+                                b = ld_slot(&slot->b);
+                            }
+                            mg = __uint_as_float(static_cast<uint32_t>(a));
+                            mo = __uint_as_float(static_cast<uint32_t>(b));
+                        }
                     }
-                }
-                // warp total, nearest (lowest lane) applied last: cur = cur o (cur of lane + off)
+                    // warp total, nearest (lowest lane) applied last: cur = cur o (cur of lane + off)
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const float fg = __shfl_down_sync(0xffffffffu, mg, off);
-                    const float fo = __shfl_down_sync(0xffffffffu, mo, off);
-                    if (lane_id + off < 32) {
-                        mo = fmaf(mg, fo, mo);
-                        mg *= fg;
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const float fg = __shfl_down_sync(0xffffffffu, mg, off);
+                        const float fo = __shfl_down_sync(0xffffffffu, mo, off);
+                        if (lane_id + off < 32) {
+                            mo = fmaf(mg, fo, mo);
+                            mg *= fg;
+                        }
+                    }
+                    const float wg = __shfl_sync(0xffffffffu, mg, 0), wo = __shfl_sync(0xffffffffu, mo, 0);
+                    ao = fmaf(ag, wo, ao);
+                    ag *= wg;
+                    if (__any_sync(0xffffffffu, is_carry) || fabsf(ag) < 4.6566129e-10f) {
+                        break;
                     }
                 }
-                __syncthreads();                                     // warp_g / warp_o free again
                 if (lane_id == 0) {
-                    warp_g[warp] = mg;
-                    warp_o[warp] = mo;
-                }
-                const int any_carry = __syncthreads_or(is_carry ? 1 : 0);
-#pragma unroll
-                for (int w = 0; w < kFmTileThreads / 32; ++w) {      // acc = acc o W_0 o W_1 ... (every thread, redundantly)
-                    ao = fmaf(ag, warp_o[w], ao);
-                    ag *= warp_g[w];
-                }
-                if (any_carry) {
-                    break;
+                    warp_o[0] = ao;
                 }
             }
-            const float carry = ao;                                  // ag == 0 by construction: constant map
+            __syncthreads();
+            const float ao = warp_o[0];
+            const float carry = ao;                                  // composed gain 0 or < 2^-31: a constant map
             if (t == 0) {
                 const float y_out = fmaf(tg, carry, to);
                 st_slot(&mine->a, pack_slot((p.epoch << 2) | 2u, y_out));
@@ -990,6 +1027,11 @@ static int launch_narrow_fused(b200_fm_plan* plan, const float2* x, float* out, 
         }
         q.slots = plan->slots;
         q.epoch = ++plan->epoch;
+        // tiles (of finite samples) until the composed gain (1 - alpha)^n drops below 2^-31
+        const double per_tile = static_cast<double>(std::min<uint64_t>(frame_len, kFmTile)) *
+                                -std::log1p(-static_cast<double>(plan->alpha));
+        const double tiles_needed = per_tile > 0.0 ? std::ceil(21.5 / per_tile) : 32.0;
+        q.lookback = static_cast<uint32_t>(std::min(32.0, std::max(1.0, tiles_needed)));
     }
     const bool vec = frame_len % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 15) == 0;
