@@ -336,7 +336,9 @@ class Env:
         self.numa = bind_to_gpu_numa_node(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            # a rank that fails inside a guarded extra must cost the others two minutes, not NCCL's default ten
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=120))
         self.lib = _native.load()          # raises if libb200dsp.so is missing
         self.ctx = Context.get(self.dev)
         self.stream = torch.cuda.current_stream(self.dev)
@@ -420,6 +422,27 @@ def guarded(fn, *a, **kw):
 
 # ---- e2e variants ---------------------------------------------------------------------------------
 
+def finish_e2e(env, result):
+    """The ONE collective of an e2e variant, outside its guarded body: MAX over ranks of the local wall time, and a
+    failure on any rank fails the variant for everyone (ranks never wait on each other inside the guarded part, so a
+    rank that raised cannot hang the rest)."""
+    failed = not isinstance(result, dict) or "local_seconds" not in result
+    seconds = -1.0 if failed else float(result["local_seconds"])
+    if env.world > 1:
+        t = env.torch.tensor([seconds, 1.0 if failed else 0.0], dtype=env.torch.float64, device=env.dev)
+        env.dist.all_reduce(t, op=env.dist.ReduceOp.MAX)
+        seconds, any_failed = float(t[0]), bool(t[1] > 0)
+    else:
+        any_failed = failed
+    if failed:
+        return result if isinstance(result, dict) else {"error": "no result"}
+    if any_failed:
+        return {"error": "the variant failed on another rank"}
+    out = {k: v for k, v in result.items() if k not in ("local_seconds", "samples_all_ranks")}
+    out["value"] = result["samples_all_ranks"] / seconds / 1e6
+    return out
+
+
 def e2e_shim(env, rows, x_host, steps, consumers):
     """The e2e metric through the REFERENCE's own Flowgraph (scheduler_synchronous + NativeCudaRuntime) with every
     block on provider b200: host bytes -> source tensor (H2D), Flowgraph::compute(), result back to the host (D2H).
@@ -427,11 +450,11 @@ def e2e_shim(env, rows, x_host, steps, consumers):
     consumers = True : spectrum_engine -> lineplot + waterfall (the spectrum-analyzer flowgraph); only signalPoints
     [4096, 2] and the ring [512, 4096] are read back (the chain's fused column sums feed the lineplot)."""
     from shim import binding as sb
-    import numpy as np
     if not sb.available():
         return {"unavailable": "shim/_build/libjst_b200.so not built"}
     n = N_FFT
     torch = env.torch
+    sb.set_cuda_device(env.local)
     with sb.Session(log_level=0) as s:
         s.add_source("src", (rows, n), "CF32", target=sb.B200, sampleAxis=1, batchAxis=0)
         s.add_block("spec", "spectrum_engine", {"enableScale": True, "rangeMin": RANGE_MIN, "rangeMax": RANGE_MAX},
@@ -451,15 +474,14 @@ def e2e_shim(env, rows, x_host, steps, consumers):
             s.read_into("spec", "buffer", out_host.data_ptr(), rows * n * 4)
             return 0.0
         step()                    # first cycle: static modules settle, plans are created
-        env.barrier()
         t0 = time.perf_counter()
         check = 0.0
         for _ in range(steps):
             check = step()
-        dt = env.max_over_ranks(time.perf_counter() - t0)
+        dt = time.perf_counter() - t0          # this rank's; no collective inside a guarded extra (finish_e2e reduces)
         modules = {**s.modules("spec"), **(s.modules("lp") if consumers else {}), **(s.modules("wf") if consumers else {})}
         kernel_ms = {k.split(":", 1)[1]: round(v[1] / max(1, v[0]), 4) for k, v in modules.items() if v[0] > 1}
-    return {"value": rows * n * env.world * steps / dt / 1e6, "unit": UNIT, "steps": steps,
+    return {"local_seconds": dt, "samples_all_ranks": rows * n * env.world * steps, "unit": UNIT, "steps": steps,
             "h2d_bytes_per_step": rows * n * 8, "d2h_bytes_per_step": d2h,
             "api": "reference Flowgraph::compute() with provider b200 (shim/libjst_b200.so): source write (H2D) -> "
                    + ("spectrum_engine -> lineplot + waterfall -> signalPoints + ring read (D2H)" if consumers
@@ -479,12 +501,11 @@ def e2e_ci8(env, plan, rows, coeff, scale, offset, steps):
         env.check(env.lib.b200_chain_exec_host_typed(plan, x_host.data_ptr(), 8, out_host.data_ptr(), rows, coeff, 1,
                                                      scale, offset, 0))
     step()
-    env.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    dt = env.max_over_ranks(time.perf_counter() - t0)
-    return {"value": rows * n * env.world * steps / dt / 1e6, "unit": UNIT, "steps": steps,
+    dt = time.perf_counter() - t0
+    return {"local_seconds": dt, "samples_all_ranks": rows * n * env.world * steps, "unit": UNIT, "steps": steps,
             "h2d_bytes_per_step": rows * n * 2, "d2h_bytes_per_step": rows * n * 4,
             "api": "b200_chain_exec_host_typed(CI8): cast fused into the kernel's load",
             "checksum": float(out_host[:: max(1, rows // 64)].double().sum())}
@@ -620,10 +641,29 @@ def bench_wideband(env, steps, warmup):
     n, world, rank = N_FFT, env.world, env.rank
     begin, end = shard_bounds(WIDEBAND_ROWS, world, rank)
     rows = end - begin
-    x = env.synthetic_rows(rows, first_row=begin, seed=1000 + rank)
-    out = torch.empty(rows, n, dtype=torch.float32, device=env.dev)
-    colsum = torch.zeros(n, dtype=torch.float32, device=env.dev)
-    plan = env.chain_plan(rows)
+    # Local set-up first, then ONE agreement collective: a rank that cannot allocate must not leave the others waiting
+    # inside the timed collectives below.
+    x = out = colsum = plan = parts = None
+    problem = None
+    try:
+        x = env.synthetic_rows(rows, first_row=begin, seed=1000 + rank)
+        out = torch.empty(rows, n, dtype=torch.float32, device=env.dev)
+        colsum = torch.zeros(n, dtype=torch.float32, device=env.dev)
+        plan = env.chain_plan(rows)
+        if world > 1 and rank == 0:
+            parts = [torch.empty(rows, n, dtype=torch.float32, device=env.dev) for _ in range(world)]
+        torch.cuda.synchronize(env.dev)
+    except BaseException as exc:      # noqa: BLE001
+        problem = f"{type(exc).__name__}: {exc}"[:300]
+    if world > 1:
+        flag = torch.tensor([1.0 if problem else 0.0], dtype=torch.float64, device=env.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if float(flag[0]) > 0:
+            problem = problem or "set-up failed on another rank"
+    if problem:
+        del x, out, parts
+        torch.cuda.empty_cache()
+        return {"error": problem}
     coeff = amplitude_scaling_coeff(n)
     scale, offset = range_coefficients(RANGE_MIN, RANGE_MAX)
 
@@ -634,10 +674,6 @@ def bench_wideband(env, steps, warmup):
     result = {"rows_total": WIDEBAND_ROWS, "rows_per_rank": rows, "scaling": "strong",
               "kernel_only": {"ms_per_step": ms_k_max, "value": WIDEBAND_ROWS * n / (ms_k_max * 1e-3) / 1e6, "unit": UNIT}}
     gather_bytes = (WIDEBAND_ROWS - rows) * n * 4 if world > 1 else 0
-    parts = None
-    if world > 1 and rank == 0:
-        parts = [torch.empty(shard_bounds(WIDEBAND_ROWS, world, r)[1] - shard_bounds(WIDEBAND_ROWS, world, r)[0], n,
-                             dtype=torch.float32, device=env.dev) for r in range(world)]
     same_size = WIDEBAND_ROWS % world == 0
 
     def kernel_gather():
@@ -747,10 +783,10 @@ def main_chain(env, args):
 
     variants, workloads = None, None
     if not args.no_extras:
-        variants = {"ci8_host": guarded(e2e_ci8, env, plan, rows, coeff, scale, offset, e2e_steps)}
+        variants = {"ci8_host": finish_e2e(env, guarded(e2e_ci8, env, plan, rows, coeff, scale, offset, e2e_steps))}
         del out_host
-        variants["shim_flowgraph"] = guarded(e2e_shim, env, rows, x_host, e2e_steps, False)
-        variants["shim_flowgraph_analyzer"] = guarded(e2e_shim, env, rows, x_host, e2e_steps, True)
+        variants["shim_flowgraph"] = finish_e2e(env, guarded(e2e_shim, env, rows, x_host, e2e_steps, False))
+        variants["shim_flowgraph_analyzer"] = finish_e2e(env, guarded(e2e_shim, env, rows, x_host, e2e_steps, True))
     variant_name = lib.b200_chain_plan_variant(plan).decode()
     env.check(lib.b200_chain_plan_destroy(plan))
     del x, out, x_host

@@ -40,6 +40,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         vp, cp, u64, i64 = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int64
         L.jst_shim_last_error.restype = cp
+        L.jst_shim_set_cuda_device.argtypes = [ctypes.c_int]
         L.jst_shim_create.restype = vp
         L.jst_shim_create.argtypes = [ctypes.c_int]
         L.jst_shim_destroy.argtypes = [vp]
@@ -68,6 +69,14 @@ def lib():
 
 class ShimError(RuntimeError):
     pass
+
+
+def set_cuda_device(index: int):
+    """One process per GPU: the device of the reference's CUDA backend singleton (default 0). Call before the first
+    Session."""
+    L = lib()
+    if L.jst_shim_set_cuda_device(int(index)) != 0:
+        raise ShimError(L.jst_shim_last_error().decode(errors="replace"))
 
 
 def _kv(d: Optional[Dict[str, object]]) -> bytes:

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "jetstream/backend/base.hh"
 #include "jetstream/block.hh"
 #include "jetstream/detail/block_impl.hh"
 #include "jetstream/detail/module_impl.hh"
@@ -228,6 +229,23 @@ std::uint8_t* RawPointer(const Tensor& tensor) {
 extern "C" {
 
 const char* jst_shim_last_error() { return g_error.c_str(); }
+
+// Selects the CUDA device of the reference's backend singleton (Backend::Config::deviceId, default 0) — one process per
+// GPU calls this with its LOCAL_RANK before the first session. A no-op when the backend already runs on that device.
+int jst_shim_set_cuda_device(int device) {
+    const ContextRestore restore;
+    if (Backend::Initialized<DeviceType::CUDA>()) {
+        if (static_cast<int>(Backend::State<DeviceType::CUDA>()->getDeviceId()) == device) {
+            return 0;
+        }
+        g_error = "set_cuda_device: the CUDA backend is already initialised on another device";
+        return -1;
+    }
+    Backend::Config config;
+    config.deviceId = static_cast<U64>(device);
+    const auto result = Backend::Initialize<DeviceType::CUDA>(config);
+    return result == Result::SUCCESS ? 0 : Fail("set_cuda_device", result);
+}
 
 void* jst_shim_create(int logLevel) {
     const ContextRestore restore;
