@@ -827,7 +827,7 @@ def main_chain(env, args):
             "workloads": workloads,
             "kernel_variant": variant_name,
         }
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 
@@ -847,11 +847,35 @@ def main_single_workload(env, args):
                 "scaling": "strong" if args.workload == "wideband" else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic"}
         line.update(res)
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Native libraries print banners to fd 1 (NCCL's version line, the reference backend's device table): the contract is
+    ONE JSON line on stdout, so fd 1 is pointed at stderr for the duration of the run and the line goes to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    text = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text)
+
+
 def main_ours(args):
+    quiet_stdout()
     env = Env()
     try:
         if args.workload == "chain":
