@@ -48,10 +48,25 @@ __global__ void __launch_bounds__(256) agc_tile_gain_kernel(const T* __restrict_
         const uint64_t start = tile * p.tile;
         const uint64_t length = p.samples - start < p.tile ? p.samples - start : p.tile;
         const T* const src = in + lane * p.samples + start;
-        double sum = 0.0;
-        for (uint64_t s = threadIdx.x; s < length; s += blockDim.x) {
-            sum = __dadd_rn(sum, sample_power(src[s]));
+        // four independent F64 accumulators per thread and all loads of a round in flight (the single dependent chain
+        // of round 1 paid one memory latency per sample); the order of the power sum was a parallel tree already
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        uint64_t s = threadIdx.x;
+        for (; s + 3 * blockDim.x < length; s += 4 * blockDim.x) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = src[s + u * blockDim.x];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc[u] = __dadd_rn(acc[u], sample_power(v[u]));
+            }
         }
+        for (; s < length; s += blockDim.x) {
+            acc[0] = __dadd_rn(acc[0], sample_power(src[s]));
+        }
+        double sum = __dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3]));
 #pragma unroll
         for (int offset = 16; offset > 0; offset >>= 1) {
             sum = __dadd_rn(sum, __shfl_down_sync(0xffffffffu, sum, offset));
@@ -102,16 +117,23 @@ __device__ __forceinline__ float clamp_to_f32(const double v) {
     const double m = static_cast<double>(FLT_MAX);
     return __double2float_rn(clamp_like_std(v, -m, m));
 }
+// The reference limits every product so it stays finite: gain' = |x| > limit / gain ? nextafter(limit / |x|, 0) : gain
+// (module_impl_native_cpu.cc:38-60). |x| gain <= limit / 2 implies |x| <= limit / gain with a factor-two margin over any
+// rounding of that quotient, so the per-sample F64 division (a ~25-instruction sequence on the quarter-rate pipe) is
+// only paid by samples within a factor two of overflowing F32 — results are unchanged.
 __device__ __forceinline__ float apply_gain(const float v, const double gain) {
     const double x = v;
-    return clamp_to_f32(__dmul_rn(x, limit_gain(fabs(x), gain, static_cast<double>(FLT_MAX))));
+    const double limit = static_cast<double>(FLT_MAX);
+    const double safe = __dmul_rn(fabs(x), gain) <= 0.5 * limit ? gain : limit_gain(fabs(x), gain, limit);
+    return clamp_to_f32(__dmul_rn(x, safe));
 }
 __device__ __forceinline__ float2 apply_gain(const float2 v, const double gain) {
     const double re = v.x, im = v.y;
     const double limit = 3.4028232635611926e+38;       // (F64) nextafter(FLT_MAX, 0): kMaxSafeCF32Magnitude
     double safe = gain;
-    // |z| <= |re| + |im|: the exact (and slow) hypot is only needed when that bound does not already clear the limit
-    if (!(__dadd_rn(fabs(re), fabs(im)) <= __ddiv_rn(limit, gain))) {
+    // |z| <= |re| + |im|: the exact (and slow) hypot and the division are only needed when that bound, times the gain,
+    // does not clear half the limit (see apply_gain(float) above)
+    if (!(__dmul_rn(__dadd_rn(fabs(re), fabs(im)), gain) <= 0.5 * limit)) {
         safe = limit_gain(hypot(re, im), gain, limit);
     }
     return make_float2(clamp_to_f32(__dmul_rn(re, safe)), clamp_to_f32(__dmul_rn(im, safe)));
@@ -129,7 +151,20 @@ __global__ void __launch_bounds__(256) agc_apply_kernel(const T* __restrict__ in
         const double step = __ddiv_rn(__dsub_rn(g.y, g.x), static_cast<double>(length));
         const T* const src = in + lane * p.samples + start;
         T* const dst = out + lane * p.samples + start;
-        for (uint64_t s = threadIdx.x; s < length; s += blockDim.x) {
+        uint64_t s = threadIdx.x;
+        for (; s + 3 * blockDim.x < length; s += 4 * blockDim.x) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = src[s + u * blockDim.x];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double gain = __dadd_rn(g.x, __dmul_rn(step, static_cast<double>(s + u * blockDim.x)));
+                dst[s + u * blockDim.x] = apply_gain(v[u], gain);
+            }
+        }
+        for (; s < length; s += blockDim.x) {
             const double gain = __dadd_rn(g.x, __dmul_rn(step, static_cast<double>(s)));
             dst[s] = apply_gain(src[s], gain);
         }
