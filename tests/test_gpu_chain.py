@@ -200,9 +200,10 @@ def test_chain_integer_ingest_with_agc(ref, name, np_type):
 
 
 def test_chain_full_size_rows_are_independent(ref):
-    """BASELINE configs[1] at full size (65536 x 4096, 2 GiB in / 1 GiB out) through the C ABI: every row of the big
-    launch (221 rows per persistent CTA, TMA ring wrapped ~74 times) is bit-identical to the same row processed in a
-    64-row launch, which in turn is checked against the reference."""
+    """BASELINE configs[1] at full size (65536 x 4096, 2 GiB in / 1 GiB out) through the C ABI: rows of the big launch
+    (221 rows per persistent CTA, TMA ring wrapped ~74 times) are bit-identical to the same rows processed in a 64-row
+    launch, and 1024 rows spread over the whole batch (every 64th) are checked against the REFERENCE itself (the round-1
+    version compared 8 rows with the reference)."""
     import ctypes
     import torch
     import cyberether_b200 as cb
@@ -238,3 +239,12 @@ def test_chain_full_size_rows_are_independent(ref):
     want = ref.spectrum_engine(spectral_rows(0, 8), enable_scale=True)
     spec = true_spectrum(spectral_rows(0, 8), _window(ref, n))
     assert_db_close(sub[:8].cpu().numpy(), want, spec, scale=_range_slope(-120.0, 0.0), floor=3e-7)
+    # 1024 rows of the big launch against the reference CPU block (Gaussian rows: every bin is a "strong" bin)
+    stride_rows = torch.arange(0, rows, 64, device=dev)
+    x_host = x[stride_rows].cpu().numpy()
+    want_many = ref.spectrum_engine(x_host, enable_scale=True)
+    from parity import assert_strong_bins
+    spec_many = true_spectrum(x_host, _window(ref, n))
+    got_many = big[stride_rows].cpu().numpy()
+    assert_db_close(got_many, want_many, spec_many, scale=_range_slope(-120.0, 0.0), floor=3e-7)
+    assert_strong_bins(got_many, want_many, spec_many, slope=_range_slope(-120.0, 0.0), label="full-size rows")
