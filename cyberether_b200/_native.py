@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200_ctx_destroy": (c_int, [c_vp]),
     "b200_ctx_device": (c_int, [c_vp, P(c_int)]),
     "b200_ctx_sm_count": (c_int, [c_vp, P(c_int)]),
+    "b200_ctx_info": (c_int, [c_vp, c_vp]),
     "b200_malloc": (c_int, [c_vp, c_u64, P(c_vp)]),
     "b200_free": (c_int, [c_vp, c_vp]),
     "b200_host_alloc": (c_int, [c_vp, c_u64, P(c_vp)]),

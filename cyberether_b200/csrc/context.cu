@@ -5,6 +5,8 @@
 // single-device singleton, include/jetstream/backend/base.hh:125-136).
 #include <cmath>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -283,6 +285,28 @@ int b200_check_async_error(b200_ctx* ctx) {
     B200_REQUIRE(ctx != nullptr, "b200_check_async_error: null context");
     DeviceGuard guard(ctx);
     B200_CUDA_CHECK(cudaGetLastError());
+    return B200_SUCCESS;
+}
+
+int b200_ctx_info(const b200_ctx* ctx, b200_device_info* info) {
+    B200_REQUIRE(ctx && info, "b200_ctx_info: null argument");
+    DeviceGuard guard(ctx);
+    cudaDeviceProp prop{};
+    B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
+    memset(info, 0, sizeof(*info));
+    strncpy(info->name, prop.name, sizeof(info->name) - 1);
+    info->device = ctx->device;
+    info->compute_capability_major = prop.major;
+    info->compute_capability_minor = prop.minor;
+    info->sm_count = prop.multiProcessorCount;
+    info->total_memory_bytes = prop.totalGlobalMem;
+    info->integrated = prop.integrated;
+    info->can_map_host_memory = prop.canMapHostMemory;
+    info->can_use_host_pointer_for_registered_memory = prop.canUseHostPointerForRegisteredMem;
+    info->shared_memory_per_block_optin = static_cast<uint64_t>(prop.sharedMemPerBlockOptin);
+    int runtime = 0;
+    B200_CUDA_CHECK(cudaRuntimeGetVersion(&runtime));
+    info->runtime_version = runtime;
     return B200_SUCCESS;
 }
 

@@ -46,6 +46,21 @@ int b200_ctx_create(int device, b200_ctx** ctx);
 int b200_ctx_destroy(b200_ctx* ctx);
 int b200_ctx_device(const b200_ctx* ctx, int* device);
 int b200_ctx_sm_count(const b200_ctx* ctx, int* sms);
+/* What Backend::CUDA caches about its device at construction (src/backend/devices/cuda/base.cc:46-107: name, compute
+ * capability, API version, integrated / discrete, memory, host-memory import capability). */
+typedef struct {
+    char name[256];
+    int device;
+    int compute_capability_major, compute_capability_minor;
+    int sm_count;
+    int integrated;
+    int can_map_host_memory;
+    int can_use_host_pointer_for_registered_memory;
+    int runtime_version;                    /* cudaRuntimeGetVersion: 1000 major + 10 minor */
+    uint64_t total_memory_bytes;
+    uint64_t shared_memory_per_block_optin;
+} b200_device_info;
+int b200_ctx_info(const b200_ctx* ctx, b200_device_info* info);
 
 /* src/memory/buffer_cuda.cc:31-124 (device allocation, zero-filled like cudaMemset at :119). */
 int b200_malloc(b200_ctx* ctx, uint64_t bytes, void** ptr);

@@ -196,6 +196,18 @@ class Session:
         return out
 
 
+def backend_info() -> dict:
+    """Device table of the reference-side CUDA backend singleton (Backend::CUDA = shim/b200_backend.cc here)."""
+    L = lib()
+    L.jst_shim_backend_info.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
+    buf = ctypes.create_string_buffer(1024)
+    if L.jst_shim_backend_info(buf, len(buf)) < 0:
+        raise ShimError(L.jst_shim_last_error().decode(errors="replace"))
+    device, name, cc, api, memory, primary = buf.value.decode().split("|")
+    return {"device": int(device), "name": name, "compute_capability": cc, "api_version": api,
+            "memory_bytes": int(memory), "primary_context": primary == "1"}
+
+
 def viz_modules() -> Dict[str, str]:
     """Live lineplot / waterfall modules of every session: module name -> type."""
     buf = ctypes.create_string_buffer(8192)

@@ -28,14 +28,15 @@ fi
 CUDA=/usr/local/cuda
 INC="-I$B/gen -I$FMT -I$R/include -I$R/src -I$R/include/jetstream/render/tools -I$CUDA/include -I$ROOT/include -I$HERE -I$HERE/stubs"
 CXXFLAGS="-std=c++20 -O2 -fPIC -DJST_FMT_HEADER_ONLY -w $INC"
-# src/memory/buffer_cuda.cc and src/runtime/native/cuda/impl.cc are NOT in this list: shim/b200_buffer.cc and
-# shim/b200_runtime.cc define detail::CreateCudaBackend() / NativeCudaRuntimeFactory() over the C ABI instead (rows a14 / a12)
+# src/memory/buffer_cuda.cc, src/runtime/native/cuda/impl.cc and src/backend/devices/cuda/base.cc are NOT in this list:
+# shim/b200_buffer.cc, shim/b200_runtime.cc and shim/b200_backend.cc define detail::CreateCudaBackend(),
+# NativeCudaRuntimeFactory() and Backend::CUDA over the C ABI instead
 CORE="logger memory/axis memory/buffer memory/buffer_cpu memory/tensor memory/token memory/types
  module module_impl module_context module_interface module_surface registry
  runtime/runtime runtime/native/cpu/impl runtime/native/cpu/context runtime/native/cuda/context
  scheduler scheduler_context scheduler_synchronous tensor_link
  parser_map parser_encode parser_decode
- backend/base backend/devices/cpu/base backend/devices/cuda/base
+ backend/base backend/devices/cpu/base
  platform/process platform/terminal platform/paths
  block block_impl block_context block_interface
  flowgraph flowgraph_environment flowgraph_metadata flowgraph_view"
@@ -52,7 +53,7 @@ for b in $BLOCKS; do [ -f "$R/src/domains/$b/block_impl.cc" ] && SRCS+=("$R/src/
 for v in lineplot waterfall; do
   SRCS+=("$R/src/domains/visualization/$v/module_impl_native_cpu.cc" "$R/src/domains/visualization/$v/block_impl.cc")
 done
-SRCS+=("$HERE/shim_stubs.cc" "$HERE/viz_headless.cc" "$HERE/b200_buffer.cc" "$HERE/b200_runtime.cc" "$HERE/b200_modules.cc"
+SRCS+=("$HERE/shim_stubs.cc" "$HERE/viz_headless.cc" "$HERE/b200_backend.cc" "$HERE/b200_buffer.cc" "$HERE/b200_runtime.cc" "$HERE/b200_modules.cc"
        "$HERE/b200_blocks.cc" "$HERE/shim_capi.cc")
 objname() { echo "$B/obj/$(echo "$1" | sed -e 's#^/##' -e 's#[/.]#_#g').o"; }
 compile_one() {

@@ -247,6 +247,34 @@ int jst_shim_set_cuda_device(int device) {
     return result == Result::SUCCESS ? 0 : Fail("set_cuda_device", result);
 }
 
+// "deviceId|name|computeCapability|apiVersion|memoryBytes|contextIsPrimary" of the CUDA backend singleton (initialising it
+// on the default device when nobody has): Backend::CUDA is shim/b200_backend.cc in this library.
+int jst_shim_backend_info(char* buffer, uint64_t capacity) {
+    const ContextRestore restore;
+    const auto& state = Backend::State<DeviceType::CUDA>();
+    if (!state || !state->isAvailable()) {
+        g_error = "backend_info: CUDA backend unavailable";
+        return -1;
+    }
+    CUcontext primary = nullptr;
+    unsigned flags = 0;
+    int active = 0;
+    cuDevicePrimaryCtxGetState(state->getDevice(), &flags, &active);
+    cuDevicePrimaryCtxRetain(&primary, state->getDevice());
+    const bool isPrimary = primary == state->getContext();
+    cuDevicePrimaryCtxRelease(state->getDevice());
+    std::ostringstream os;
+    os << state->getDeviceId() << '|' << state->getDeviceName() << '|' << state->getComputeCapability() << '|'
+       << state->getApiVersion() << '|' << state->getPhysicalMemory() << '|' << (isPrimary ? 1 : 0);
+    const std::string text = os.str();
+    if (buffer && capacity > 0) {
+        const auto n = std::min<uint64_t>(capacity - 1, text.size());
+        std::memcpy(buffer, text.data(), n);
+        buffer[n] = 0;
+    }
+    return static_cast<int>(text.size());
+}
+
 void* jst_shim_create(int logLevel) {
     const ContextRestore restore;
     JST_LOG_SET_DEBUG_LEVEL(logLevel);

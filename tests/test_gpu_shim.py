@@ -283,3 +283,27 @@ def test_backend_rows_a12_a14_through_the_reference_interfaces(sb):
     assert np.array_equal(got, want)                                  # amplitude is bit-exact on this provider
     assert np.allclose(got2 - got, 20 * np.log10(2.0), atol=5e-3)
     assert cycles0[0] == 1 and cycles1[0] == 2 and cycles1[1] >= cycles0[1] > 0.0
+
+
+def test_backend_singleton_is_ours_and_uses_the_primary_context(sb):
+    """SURVEY §8 a15 / north-star "src/backend (CUDA device)": Backend::CUDA of this library is shim/b200_backend.cc
+    (device table from b200_ctx_info). It retains the device's PRIMARY context instead of creating a second one, so
+    memory the host application allocated with the CUDA runtime (here: PyTorch) is valid inside the flowgraph."""
+    import torch
+    info = sb.backend_info()
+    props = torch.cuda.get_device_properties(info["device"])
+    assert info["name"] == props.name and "B200" in info["name"]
+    assert info["compute_capability"] == f"{props.major}{props.minor}" == "100"
+    assert info["memory_bytes"] == props.total_memory
+    assert info["primary_context"] is True
+    # a PyTorch tensor's device pointer handed to libb200dsp from inside a harness-created stream context still works
+    # after flowgraph calls (one context): run a block, then a torch kernel, then read both
+    x = (np.random.default_rng(0).standard_normal((4, 1024)) + 0j).astype(np.complex64)
+    with sb.Session() as s:
+        s.add_source("src", x.shape, "CF32", target=sb.B200, sampleAxis=1, batchAxis=0)
+        s.add_block("a", "amplitude", None, {"signal": "src.signal"}, target=sb.B200)
+        s.write_source("src", x)
+        s.compute()
+        t = torch.arange(8, device="cuda") * 2
+        assert int(t.sum()) == 56
+        assert np.isfinite(s.read("a", "signal")).all()
