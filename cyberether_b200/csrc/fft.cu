@@ -15,6 +15,7 @@
 #endif
 
 #include "fft_radix.cuh"
+#include "fft_twopass.cuh"
 
 namespace b200 {
 
@@ -305,6 +306,56 @@ static int launch_fft(const b200_ctx* ctx, const FftParams& p, cudaStream_t stre
     return launch_generic_bpt<MODE, WIN, 4>(ctx, p, stream);
 }
 
+// ---- two-pass plan (fft_twopass.cuh) -----------------------------------------------------------------------------
+constexpr uint64_t kTwoPassMinN = 16384, kTwoPassMaxN = 131072;      // n = 16 M, 1024 <= M <= 8192
+
+// Read at plan creation (A/B measurements in one process): B200_FFT_TWOPASS=0 falls back to the four-step plan,
+// B200_FFT_TWOPASS_MIN_N lowers the first two-pass length (down to 4096; default 16384), B200_FFT_TWOPASS_CHUNK_MB is the
+// chunk (= L2-resident scratch) size, B200_FFT_TWOPASS_HINTS=0 drops the L2 eviction-priority hints.
+static bool twopass_selected(const uint64_t n) {
+    const char* env = getenv("B200_FFT_TWOPASS");
+    if (env && atoi(env) == 0) {
+        return false;
+    }
+    const char* lo = getenv("B200_FFT_TWOPASS_MIN_N");
+    const uint64_t min_n = lo && atol(lo) >= 4096 ? static_cast<uint64_t>(atol(lo)) : kTwoPassMinN;
+    return is_pow2(n) && n >= min_n && n <= kTwoPassMaxN;
+}
+static uint64_t twopass_chunk_bytes() {
+    const char* env = getenv("B200_FFT_TWOPASS_CHUNK_MB");
+    const long v = env ? atol(env) : 0;
+    return static_cast<uint64_t>(v > 0 ? v : 32) << 20;
+}
+static int twopass_hints() {
+    const char* env = getenv("B200_FFT_TWOPASS_HINTS");
+    return env ? atoi(env) : 1;
+}
+
+static int launch_col16(const b200_ctx* ctx, const Col16Params& p, cudaStream_t stream) {
+    const unsigned col_blocks = p.m / kCol16Threads;
+    const uint64_t cap = (static_cast<uint64_t>(ctx->sms) * 2 + col_blocks - 1) / col_blocks;   // 2 CTAs per SM
+    const dim3 grid(col_blocks, static_cast<unsigned>(p.rows < cap ? p.rows : cap));
+    if (p.hints) {
+        fft_col16_kernel<true><<<grid, kCol16Threads, 0, stream>>>(p);
+    } else {
+        fft_col16_kernel<false><<<grid, kCol16Threads, 0, stream>>>(p);
+    }
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+static int launch_radix_transposed(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    switch (p.n) {
+        case 256: return launch_radix<8, MODE_C2C_T, WIN_NONE>(ctx, p, stream);
+        case 512: return launch_radix<9, MODE_C2C_T, WIN_NONE>(ctx, p, stream);
+        case 1024: return launch_radix<10, MODE_C2C_T, WIN_NONE>(ctx, p, stream);
+        case 2048: return launch_radix<11, MODE_C2C_T, WIN_NONE>(ctx, p, stream);
+        case 4096: return launch_radix<12, MODE_C2C_T, WIN_NONE>(ctx, p, stream);
+        case 8192: return launch_radix<13, MODE_C2C_T, WIN_NONE>(ctx, p, stream);
+        default: return fail("two-pass fft: unsupported row length %u", p.n);
+    }
+}
+
 static int make_twiddle_table(b200_ctx* ctx, const uint64_t n, float2** out) {
     std::vector<float2> host(n);
     const double kTwoPi = 6.283185307179586476925286766559;
@@ -329,7 +380,7 @@ static int make_twiddle_table(b200_ctx* ctx, const uint64_t n, float2** out) {
 
 using namespace b200;
 
-enum FftPlanKind { FFT_DIRECT = 0, FFT_FOURSTEP = 1, FFT_BLUESTEIN = 2 };
+enum FftPlanKind { FFT_DIRECT = 0, FFT_FOURSTEP = 1, FFT_BLUESTEIN = 2, FFT_TWOPASS = 3 };
 
 struct b200_fft_plan {
     b200_ctx* ctx;
@@ -350,6 +401,9 @@ struct b200_fft_plan {
     float2* chirp_spec_inv = nullptr; // [m]  same for the inverse transform (conjugated chirps)
     float2* scratch_a = nullptr;
     float2* scratch_b = nullptr;
+    // two-pass (n = 16 M, 16384 <= n <= 131072; fft_twopass.cuh): sub2 carries the W_M table, scratch_a one chunk
+    uint64_t chunk_rows = 0;
+    int hints = 1;
 };
 
 namespace b200 {
@@ -503,10 +557,29 @@ int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan**
     pl->batch = batch;
     pl->twiddle = nullptr;
     const double kPi = 3.14159265358979323846;
-    if (n == 1 || (is_pow2(n) && n <= kMaxDirectN)) {
+    if (n == 1 || (is_pow2(n) && n <= kMaxDirectN && !twopass_selected(n))) {
         pl->kind = FFT_DIRECT;
         if (n > 1 && make_twiddle_table(ctx, n, &pl->twiddle) != B200_SUCCESS) {
             delete pl;
+            return B200_ERROR;
+        }
+    } else if (twopass_selected(n)) {
+        // two-pass: radix-16 column pass + 16 row transforms of length n / 16 with a stride-16 store
+        pl->kind = FFT_TWOPASS;
+        pl->n1 = 16;
+        pl->n2 = n / 16;
+        pl->hints = twopass_hints();
+        const uint64_t fit = twopass_chunk_bytes() / (n * sizeof(float2));
+        pl->chunk_rows = std::min<uint64_t>(std::max<uint64_t>(fit, 1), std::max<uint64_t>(batch, 1));
+        int rc = make_twiddle_table(ctx, n, &pl->twiddle);
+        rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, pl->n2, 0, &pl->sub2) : rc;     // carries the W_M table
+        void* a = nullptr;
+        if (rc == B200_SUCCESS && batch > 0) {
+            rc = b200_malloc(ctx, pl->chunk_rows * n * sizeof(float2), &a);
+        }
+        pl->scratch_a = static_cast<float2*>(a);
+        if (rc != B200_SUCCESS) {
+            b200_fft_plan_destroy(pl);
             return B200_ERROR;
         }
     } else if (is_pow2(n)) {
@@ -609,6 +682,33 @@ static int fft_exec_impl(b200_fft_plan* plan, const float2* in, float2* out, int
         return launch_fft<MODE_C2C, WIN_NONE>(plan->ctx, p, s);
     }
     const uint64_t B = plan->batch, n = plan->n;
+    if (plan->kind == FFT_TWOPASS) {
+        for (uint64_t row0 = 0; row0 < B; row0 += plan->chunk_rows) {
+            const uint64_t rows = std::min(plan->chunk_rows, B - row0);
+            Col16Params c{};
+            c.in = in + row0 * n;
+            c.scratch = plan->scratch_a;
+            c.rows = rows;
+            c.m = static_cast<uint32_t>(plan->n2);
+            c.inverse = forward ? 0 : 1;
+            c.twiddle = plan->twiddle;
+            c.hints = plan->hints;
+            if (launch_col16(ctx, c, s) != B200_SUCCESS) {
+                return B200_ERROR;
+            }
+            FftParams p{};
+            p.in = plan->scratch_a;
+            p.out = out + row0 * n;
+            p.rows = rows * 16;
+            p.n = static_cast<uint32_t>(plan->n2);
+            p.inverse = forward ? 0 : 1;
+            p.twiddle = plan->sub2->twiddle;
+            if (launch_radix_transposed(ctx, p, s) != B200_SUCCESS) {
+                return B200_ERROR;
+            }
+        }
+        return B200_SUCCESS;
+    }
     if (plan->kind == FFT_FOURSTEP) {
         const uint64_t n1 = plan->n1, n2 = plan->n2;
         float2* a = plan->scratch_a;

@@ -6,7 +6,10 @@
 
 namespace b200 {
 
-enum : int { MODE_C2C = 0, MODE_AMP = 1, MODE_AMP_RANGE = 2 };
+// MODE_C2C_T (fft_radix_kernel only): the second pass of the two-pass plan (fft_twopass.cuh) — rows are [transform][k1 < 16]
+// slabs of a 16x longer transform; X[k2] of row r goes to out[(r / 16) * 16 n + (r % 16) + 16 k2], no input swap for the
+// inverse (the first pass did it), output swap as MODE_C2C.
+enum : int { MODE_C2C = 0, MODE_AMP = 1, MODE_AMP_RANGE = 2, MODE_C2C_T = 3 };
 enum : int { WIN_NONE = 0, WIN_REAL = 1, WIN_COMPLEX = 2 };
 
 struct FftParams {

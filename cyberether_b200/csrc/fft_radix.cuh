@@ -310,8 +310,11 @@ __global__ void __launch_bounds__(radix_threads(LOG2N), radix_threads(LOG2N) > 2
         // ---- epilogue: the last pass has Ns = N / RL, so k = j and output index = j + t Ns --------------------
         if (row_valid) {
             constexpr int NS_LAST = N / RL;
-            if constexpr (MODE == MODE_C2C) {
-                float2* const out = static_cast<float2*>(p.out) + row * N;
+            if constexpr (MODE == MODE_C2C || MODE == MODE_C2C_T) {
+                // MODE_C2C_T: row = 16 * transform + k1, element k2 lands at k1 + 16 k2 of the 16 N-point transform
+                constexpr int KS = MODE == MODE_C2C_T ? 16 : 1;
+                float2* const out = MODE == MODE_C2C_T ? static_cast<float2*>(p.out) + (row >> 4) * (16ull * N) + (row & 15)
+                                                       : static_cast<float2*>(p.out) + row * N;
 #pragma unroll
                 for (int b = 0; b < CL; ++b) {
 #pragma unroll
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(radix_threads(LOG2N), radix_threads(LOG2N) > 2
                         if (p.inverse) {
                             X = make_float2(X.y, X.x);
                         }
-                        stg_stream_f2(out + lt + b * T + t * NS_LAST, X);
+                        stg_stream_f2(out + (lt + b * T + t * NS_LAST) * KS, X);
                     }
                 }
             } else {

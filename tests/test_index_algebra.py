@@ -264,3 +264,28 @@ def test_fm_wide_nco_orbit_table_reproduces_the_serial_walk():
         _native.check(lib.b200_fm_nco_phases_host(rate, pre.value + cycle.value, b.size, b.ctypes.data_as(ctypes.c_void_p),
                                                   None, None))
         assert np.array_equal(a, b)
+
+
+def test_two_pass_plan_radix16_columns_then_strided_rows():
+    """fft_twopass.cuh: n = 16 M; pass 1 = radix-16 over the 16 slabs of a row + W_n^(n2 k1), scratch [k1][n2];
+    pass 2 = M-point transforms of the 16 scratch rows stored at k1 + 16 k2; inverse = swap on the way in (pass 1) and
+    on the way out (pass 2)."""
+    rng = np.random.default_rng(5)
+    for m in (64, 1024):
+        n = 16 * m
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        for inverse in (False, True):
+            xin = x.imag + 1j * x.real if inverse else x
+            slabs = xin.reshape(16, m)
+            z = np.empty((16, m), complex)
+            n2 = np.arange(m)
+            for col in range(m):
+                z[:, col] = dft16(slabs[:, col])
+            z *= np.exp(-2j * np.pi * np.outer(np.arange(16), n2) / n)
+            out = np.empty(n, complex)
+            for k1 in range(16):
+                out[k1 + 16 * np.arange(m)] = np.fft.fft(z[k1])
+            if inverse:
+                out = out.imag + 1j * out.real
+            want = np.fft.ifft(x) * n if inverse else np.fft.fft(x)
+            assert np.abs(out - want).max() < 1e-9 * np.abs(want).max()
