@@ -13,9 +13,14 @@
 #ifndef B200_FFT4096_DEFAULT_CTAS
 #define B200_FFT4096_DEFAULT_CTAS 2
 #endif
+#ifndef B200_FFT4096_DEFAULT_W
+#define B200_FFT4096_DEFAULT_W 0      // 1: fft4096w_kernel is the CF32 chain kernel unless B200_FFT4096_VARIANT says otherwise
+#endif
 
 #include "fft_radix.cuh"
 #include "fft_twopass.cuh"
+#include "fft_tile.cuh"
+#include "fft4096w.cuh"
 
 namespace b200 {
 
@@ -160,6 +165,58 @@ static int fft4096_ctas() {
     return value;
 }
 
+// ---- fft4096w_kernel (warp-local first exchange, 2-D swizzled TMA landing; fft4096w.cuh) -------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: the library does not link libcuda.
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static const TensorMapEncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult status = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &status) != cudaSuccess ||
+            status != cudaDriverEntryPointSuccess) {
+            f = nullptr;
+        }
+        return reinterpret_cast<TensorMapEncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// B200_FFT4096_VARIANT=w|classic selects the CF32 chain kernel (read per launch: A/B runs in one process).
+static bool fft4096_use_w(const FftParams& p) {
+    const char* env = getenv("B200_FFT4096_VARIANT");
+    const bool want = env ? (env[0] == 'w') : (B200_FFT4096_DEFAULT_W != 0);
+    return want && p.rows * 256ull < (1ull << 31) && (reinterpret_cast<uintptr_t>(p.in) & 15u) == 0 &&
+           tensor_map_encoder() != nullptr;
+}
+
+template <int MODE, int WIN, bool AGC = false, bool COLSUM = false>
+static int launch_4096w(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream, unsigned* grid_out = nullptr) {
+    // the batch as [rows * 256 lines][32 floats]: one box = one 4096-point row = 256 lines of 128 bytes, swizzled
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {32, p.rows * 256ull};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, 256};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult rc = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(p.in), dims,
+                                             strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        return fail("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(rc));
+    }
+    auto kernel = fft4096w_kernel<MODE, WIN, AGC, COLSUM>;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft4096wSmemBytes));
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
+    const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
+    if (grid_out) {
+        *grid_out = grid;
+    }
+    kernel<<<grid, kFft4096Threads, kFft4096wSmemBytes, stream>>>(p, map);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
 template <int MODE, int WIN, int CTAS>
 static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
     auto kernel = fft4096_kernel<MODE, WIN, CTAS>;
@@ -177,6 +234,11 @@ static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_
 // Fused complex-integer ingest (cast -> window -> fft -> [agc] -> amplitude -> range in one kernel), real window only.
 template <int MODE, int ITYPE, bool AGC = false, bool COLSUM = false>
 static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream, unsigned* grid_out = nullptr) {
+    if constexpr (ITYPE == IN_CF32) {
+        if (fft4096_use_w(p)) {
+            return launch_4096w<MODE, WIN_REAL, AGC, COLSUM>(ctx, p, stream, grid_out);
+        }
+    }
     auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE, AGC, COLSUM>;
     constexpr int smem = ITYPE == IN_CF32 ? fft4096_smem_bytes(2) : fft4096_int_smem_bytes(ITYPE);
     // Set on every launch (a cheap runtime call): the attribute belongs to the CUDA *context*, and a host such as the
@@ -194,6 +256,9 @@ static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t
 
 template <int MODE, int WIN>
 static int launch_4096(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    if (fft4096_use_w(p)) {
+        return launch_4096w<MODE, WIN>(ctx, p, stream);
+    }
     if (fft4096_ctas() == 3) {
         return launch_4096_ctas<MODE, WIN, 3>(ctx, p, stream);
     }
@@ -344,6 +409,34 @@ static int launch_col16(const b200_ctx* ctx, const Col16Params& p, cudaStream_t 
     return B200_SUCCESS;
 }
 
+static bool twopass_tiled(const uint64_t n) {
+    const char* env = getenv("B200_FFT_TWOPASS_TILE");
+    return !(env && atoi(env) == 0) && (n == 16384 || n == 32768 || n == 65536);
+}
+
+static int launch_tile_cols(const b200_ctx* ctx, const TileParams& p, cudaStream_t stream) {
+    const uint64_t columns_per_tile = kTileElems / p.m1;
+    const uint64_t tiles = p.transforms * (kTileRowLen / columns_per_tile);
+    void (*kernel)(TileParams) = p.m1 == 64 ? fft_cols_kernel<6> : (p.m1 == 128 ? fft_cols_kernel<7> : fft_cols_kernel<8>);
+    B200_REQUIRE(p.m1 == 64 || p.m1 == 128 || p.m1 == 256, "tiled two-pass fft: unsupported column length %u", p.m1);
+    int per_sm = 2;
+    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTileThreads, 0));
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * (per_sm > 0 ? per_sm : 1);
+    const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+    kernel<<<grid, kTileThreads, 0, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+static int launch_tile_rows(const b200_ctx* ctx, const TileParams& p, cudaStream_t stream) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(fft_rows256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRows256SmemBytes));
+    const uint64_t blocks = p.transforms * (p.m1 / 16);
+    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
+    fft_rows256_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), kTileThreads, kRows256SmemBytes, stream>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
 static int launch_radix_transposed(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
     switch (p.n) {
         case 256: return launch_radix<8, MODE_C2C_T, WIN_NONE>(ctx, p, stream);
@@ -404,6 +497,8 @@ struct b200_fft_plan {
     // two-pass (n = 16 M, 16384 <= n <= 131072; fft_twopass.cuh): sub2 carries the W_M table, scratch_a one chunk
     uint64_t chunk_rows = 0;
     int hints = 1;
+    // tiled form (n = M1 x 256, fft_tile.cuh): sub1 carries the W_M1 table, sub2 the W_256 table, step_twiddle [M1][256]
+    bool tiled = false;
 };
 
 namespace b200 {
@@ -571,7 +666,23 @@ int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan**
         pl->hints = twopass_hints();
         const uint64_t fit = twopass_chunk_bytes() / (n * sizeof(float2));
         pl->chunk_rows = std::min<uint64_t>(std::max<uint64_t>(fit, 1), std::max<uint64_t>(batch, 1));
-        int rc = make_twiddle_table(ctx, n, &pl->twiddle);
+        pl->tiled = twopass_tiled(n);
+        int rc = B200_SUCCESS;
+        if (pl->tiled) {
+            pl->n1 = n / kTileRowLen;
+            pl->n2 = kTileRowLen;
+            std::vector<float2> tw(n);                   // [k1][n2]: W_n^(k1 n2), F64-evaluated
+            for (uint64_t a = 0; a < pl->n1; ++a) {
+                for (uint64_t c = 0; c < pl->n2; ++c) {
+                    const double ang = -2.0 * kPi * static_cast<double>((a * c) % n) / static_cast<double>(n);
+                    tw[a * pl->n2 + c] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+                }
+            }
+            rc = upload(ctx, tw, &pl->step_twiddle);
+            rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, pl->n1, 0, &pl->sub1) : rc;   // carries the W_M1 table
+        } else {
+            rc = make_twiddle_table(ctx, n, &pl->twiddle);
+        }
         rc = rc == B200_SUCCESS ? b200_fft_plan_c2c(ctx, pl->n2, 0, &pl->sub2) : rc;     // carries the W_M table
         void* a = nullptr;
         if (rc == B200_SUCCESS && batch > 0) {
@@ -685,6 +796,27 @@ static int fft_exec_impl(b200_fft_plan* plan, const float2* in, float2* out, int
     if (plan->kind == FFT_TWOPASS) {
         for (uint64_t row0 = 0; row0 < B; row0 += plan->chunk_rows) {
             const uint64_t rows = std::min(plan->chunk_rows, B - row0);
+            if (plan->tiled) {
+                TileParams t{};
+                t.in = in + row0 * n;
+                t.out = plan->scratch_a;
+                t.transforms = rows;
+                t.m1 = static_cast<uint32_t>(plan->n1);
+                t.inverse = forward ? 0 : 1;
+                t.table = plan->sub1->twiddle;
+                t.stage_tw = plan->step_twiddle;
+                t.hints = plan->hints;
+                if (launch_tile_cols(ctx, t, s) != B200_SUCCESS) {
+                    return B200_ERROR;
+                }
+                t.in = plan->scratch_a;
+                t.out = out + row0 * n;
+                t.table = plan->sub2->twiddle;
+                if (launch_tile_rows(ctx, t, s) != B200_SUCCESS) {
+                    return B200_ERROR;
+                }
+                continue;
+            }
             Col16Params c{};
             c.in = in + row0 * n;
             c.scratch = plan->scratch_a;

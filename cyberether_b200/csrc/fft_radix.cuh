@@ -87,6 +87,23 @@ __device__ __forceinline__ void twiddle_inputs(float2* v, const TwiddleSet& s) {
 
 __device__ __forceinline__ uint32_t pad16(const uint32_t a) { return a + (a >> 4); }
 
+// x * W_16^b for a compile-time b in [0, 8) (call sites are fully unrolled).
+__device__ __forceinline__ float2 mul_w16(const float2 x, const int b) {
+    constexpr float kC = 0.92387953251128674f;  // cos(pi/8)
+    constexpr float kS = 0.38268343236508977f;  // sin(pi/8)
+    constexpr float kH = 0.70710678118654752f;  // sqrt(1/2)
+    switch (b) {
+        case 0: return x;
+        case 1: return cmul(x, make_float2(kC, -kS));
+        case 2: return cscale(csub_i(x, x), kH);
+        case 3: return cmul(x, make_float2(kS, -kC));
+        case 4: return make_float2(x.y, -x.x);
+        case 5: return cmul(x, make_float2(-kS, -kC));
+        case 6: return cscale(cadd_i(x, x), -kH);
+        default: return cmul(x, make_float2(-kC, -kS));
+    }
+}
+
 // Powers w^1, w^2, w^3, w^4, w^8, w^12 of w = W_n^base from the table W_n^j (indices wrap mod n; only the powers a
 // radix actually uses are consumed, the rest are dead code).
 __device__ __forceinline__ TwiddleSet load_twiddles_n(const float2* __restrict__ table, const uint32_t base,
@@ -188,6 +205,10 @@ __global__ void __launch_bounds__(radix_threads(LOG2N), radix_threads(LOG2N) > 2
         for (int t = 0; t < 16; ++t) {
             wr[t] = p.win_re[lt + t * T];
         }
+    }
+    float2 tw_last = make_float2(1.f, 0.f);            // pass 3 (N = 8192): W_N^lt
+    if constexpr (PASSES > 3) {
+        tw_last = p.twiddle[lt];
     }
 
     uint32_t stage = 0, parity = 0, refill_stage = 0;
@@ -298,11 +319,13 @@ __global__ void __launch_bounds__(radix_threads(LOG2N), radix_threads(LOG2N) > 2
         if constexpr (PASSES > 3) {
             __syncthreads();
             // ---- pass 3 (N = 8192): radix 2, Ns = 4096, single twiddle W_N^k per butterfly --------------------
+            // W_N^j with j = lt + b T and T = N / 16: W_N^lt (thread constant, tw_last) times the compile-time constant
+            // W_16^b — no table loads in the row loop (they were the kernel's long-scoreboard stalls).
 #pragma unroll
             for (int b = 0; b < CL; ++b) {
                 const uint32_t j = lt + b * T;                   // k = j (j < Ns)
                 v[b * RL] = x1[pad16(g * N + j)];
-                v[b * RL + 1] = cmul(x1[pad16(g * N + j + N / 2)], p.twiddle[j]);
+                v[b * RL + 1] = mul_w16(cmul(x1[pad16(g * N + j + N / 2)], tw_last), b);
                 bfly2(v[b * RL], v[b * RL + 1]);
             }
         }

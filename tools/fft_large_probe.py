@@ -70,15 +70,15 @@ for n in (8192, 16384, 32768, 65536, 131072):
     variants = []
     if n == 8192:
         variants.append(("single-CTA radix kernel", {"B200_FFT_TWOPASS": 0}))
-        for mb in ((32,) if QUICK else (16, 32, 64)):
-            variants.append((f"two-pass chunk {mb} MB hints", {"B200_FFT_TWOPASS_MIN_N": 4096, "B200_FFT_TWOPASS_CHUNK_MB": mb}))
     else:
         if not QUICK:
             variants.append(("four-step plan (round 1)", {"B200_FFT_TWOPASS": 0}))
-        for mb in ((32,) if QUICK else (8, 16, 32, 48, 64, 96)):
-            variants.append((f"two-pass chunk {mb} MB hints", {"B200_FFT_TWOPASS_CHUNK_MB": mb}))
-        variants.append(("two-pass chunk 32 MB no hints", {"B200_FFT_TWOPASS_CHUNK_MB": 32, "B200_FFT_TWOPASS_HINTS": 0}))
-        variants.append(("two-pass one chunk (no L2 residency)", {"B200_FFT_TWOPASS_CHUNK_MB": 4096}))
+        variants.append(("two-pass col16 chunk 64 MB", {"B200_FFT_TWOPASS_TILE": 0, "B200_FFT_TWOPASS_CHUNK_MB": 64}))
+        if n <= 65536:
+            for mb in ((32,) if QUICK else (16, 32, 48, 64, 96)):
+                variants.append((f"two-pass tiled chunk {mb} MB", {"B200_FFT_TWOPASS_CHUNK_MB": mb}))
+            variants.append(("two-pass tiled chunk 32 MB no hints", {"B200_FFT_TWOPASS_CHUNK_MB": 32, "B200_FFT_TWOPASS_HINTS": 0}))
+            variants.append(("two-pass tiled one chunk (no L2 residency)", {"B200_FFT_TWOPASS_CHUNK_MB": 4096}))
     for label, env in variants:
         pl = plan_with(env, n, rows)
         run = lambda f=1: _native.check(lib.b200_fft_exec(pl, xx.data_ptr(), yy.data_ptr(), f, sp))
@@ -89,4 +89,4 @@ for n in (8192, 16384, 32768, 65536, 131072):
         err_inv = (yy[rows - 4:] - inv).abs().max().item() / inv.abs().max().item()
         report(f"fft c2c {n} x {rows}: {label} [err {err:.1e}/{err_inv:.1e}]", timeit(run), total)
         _native.check(lib.b200_fft_plan_destroy(pl))
-    report(f"cuFFT {n} x {rows} [baseline]", timeit(lambda: torch.fft.fft(xx, out=yy)), total)
+    report(f"cuFFT {n} x {rows} [baseline]", timeit(lambda: torch.fft.fft(xx)), total)
