@@ -18,6 +18,7 @@
 // The scratch is one chunk of the batch that stays in the 126 MB L2 between the two launches (fft.cu).
 #pragma once
 
+#include "fft4096w.cuh"
 #include "fft_radix.cuh"
 #include "fft_twopass.cuh"
 
@@ -27,6 +28,13 @@ constexpr int kTileThreads = 256;
 constexpr int kTileElems = 4096;                         // complex samples per CTA iteration
 constexpr int kTileRowLen = 256;                         // the contiguous factor (pass 2 length)
 __host__ __device__ constexpr int tile_pitch(const int n) { return n + n / 16 + 1; }
+
+// Programmatic dependent launch (the chunk loop launches cols, rows, cols, rows ... on one stream): a kernel lets its
+// successor be scheduled right away and the successor blocks at pdl_wait() only where it touches what the predecessor
+// produces or still reads, so launch latency and the tail of one kernel overlap the head of the next. Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 struct TileParams {
     const float2* in;
@@ -40,8 +48,19 @@ struct TileParams {
 };
 
 // ---- pass 1: column transforms of length M1 over tiles of C adjacent columns ----------------------------------------
+// A tile ([M1 lines][C columns]) lands by ONE 2-D tensor-map TMA copy (box = 2 C floats x M1 lines, no swizzle: the
+// landing is [n1][C], read with lanes over the columns) into a 2-deep ring, so the strided HBM reads of the next tile run
+// under this tile's math. (M1 separate 1-D bulk copies of C * 8 = 128 bytes measured 1.6x slower than plain loads.)
+constexpr int kColsStages = 2;
+constexpr int kColsStageBytes = kTileElems * 8;                                   // 32 KiB
+__host__ __device__ constexpr int cols_x1_bytes(const int n) { return (kTileElems / n) * tile_pitch(n) * 8; }
+__host__ __device__ constexpr int cols_smem_bytes(const int n) {
+    return kColsStages * kColsStageBytes + ((cols_x1_bytes(n) + 127) / 128) * 128 + 64;
+}
+
 template <int LOG2M1>
-__global__ void __launch_bounds__(kTileThreads, 2) fft_cols_kernel(const TileParams p) {
+__global__ void __launch_bounds__(kTileThreads, 2)
+    fft_cols_kernel(const TileParams p, const __grid_constant__ CUtensorMap in_map) {
     constexpr int N = 1 << LOG2M1;               // 64, 128, 256
     constexpr int C = kTileElems / N;            // columns per tile
     constexpr int T = N / 16;                    // pass-A butterflies per column (= 256 / C)
@@ -49,7 +68,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_cols_kernel(const TilePar
     constexpr int CB = 16 / R;                   // pass-B butterflies per thread
     constexpr int P = tile_pitch(N);
     static_assert(T * C == kTileThreads, "one pass-A butterfly per thread");
-    __shared__ float2 x1[C * P];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* const x1 = reinterpret_cast<float2*>(smem_raw + kColsStages * kColsStageBytes);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + cols_smem_bytes(N) - 64);
 
     const uint32_t tid = threadIdx.x;
     const uint32_t g = tid % C;                  // column inside the tile: lanes run over columns
@@ -57,43 +78,93 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_cols_kernel(const TilePar
     const uint64_t n = static_cast<uint64_t>(N) * kTileRowLen;
     constexpr uint32_t kTilesPerTransform = kTileRowLen / C;
     const uint64_t tiles = p.transforms * kTilesPerTransform;
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    const uint32_t my_tiles = first < tiles ? static_cast<uint32_t>((tiles - first + stride - 1) / stride) : 0u;
+    pdl_launch_dependents();
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kColsStages; ++s) {
+            mbar_init(&full[s], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint64_t pol_in = 0, pol_out = 0;
+    if (p.hints) {
+        pol_in = l2_policy_evict_first();
+        pol_out = l2_policy_evict_last();
+    }
+    // thread 0: land tile `index` (of this CTA's sequence) in stage `s`: the input is [transforms * M1 lines][512 floats]
+    auto issue_tile = [&](const uint32_t index, const uint32_t s) {
+        const uint64_t tile = first + static_cast<uint64_t>(index) * stride;
+        const uint64_t r = tile / kTilesPerTransform;
+        const uint32_t c0 = static_cast<uint32_t>(tile % kTilesPerTransform) * C;
+        mbar_expect_tx(&full[s], kColsStageBytes);
+        tma_load_tile_2d(smem_raw + s * kColsStageBytes, &in_map, static_cast<int>(2 * c0), static_cast<int>(r * N), &full[s]);
+    };
+    uint32_t issued = 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kColsStages; ++s) {
+            if (issued < my_tiles) {
+                issue_tile(issued, s);
+                ++issued;
+            }
+        }
+    }
 
     TwiddleSet tw[CB];
 #pragma unroll
     for (int b = 0; b < CB; ++b) {
         tw[b] = load_twiddles_n(p.table, ja + R * b, N);              // powers of W_N^(jj), jj = ja + R b
     }
-    uint64_t pol_in = 0, pol_out = 0;
-    if (p.hints) {
-        pol_in = l2_policy_evict_first();
-        pol_out = l2_policy_evict_last();
-    }
 
-    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    uint32_t stage = 0, parity = 0;
+    for (uint32_t i = 0; i < my_tiles; ++i) {
+        const uint64_t tile = first + static_cast<uint64_t>(i) * stride;
         const uint64_t r = tile / kTilesPerTransform;
         const uint32_t c0 = static_cast<uint32_t>(tile % kTilesPerTransform) * C;
-        const float2* const src = p.in + r * n + c0 + g;
+        const float2* const land = reinterpret_cast<const float2*>(smem_raw + stage * kColsStageBytes);
+        mbar_wait(&full[stage], parity);
         float2 v[16];
         // ---- pass A: radix 16 over n1 = ja + t T -------------------------------------------------------
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-            const float2* const a = src + static_cast<uint32_t>(ja + t * T) * kTileRowLen;
-            float2 x = p.hints ? ldg_hint_f2(a, pol_in) : ldg_stream_f2(a);
+            float2 x = land[(ja + t * T) * C + g];
             if (p.inverse) {
                 x = make_float2(x.y, x.x);
             }
             v[t] = x;
         }
         dft16(*reinterpret_cast<float2(*)[16]>(v));
-        __syncthreads();                         // the previous tile's pass-B reads of x1 are complete
+        __syncthreads();                         // landing consumed; the previous tile's pass-B reads of x1 are complete
+        if (tid == 0 && issued < my_tiles) {     // refill this stage with the tile two ahead
+            fence_proxy_async();
+            issue_tile(issued, stage);
+            ++issued;
+        }
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             x1[g * P + pad16(16 * ja + t)] = v[dft_pos<16>(t)];
         }
+        // the stage twiddles of this thread's 16 outputs: issued before the barrier, consumed after pass B
+        const float2* const stw = p.stage_tw + c0 + g;
+        float2 sw[16];
+#pragma unroll
+        for (int b = 0; b < CB; ++b) {
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                sw[b * R + t] = stw[(ja + R * b + 16 * t) * kTileRowLen];
+            }
+        }
         __syncthreads();
         // ---- pass B: radix R, Ns = 16: butterfly jj reads jj + 16 t, writes k1 = jj + 16 t ---------------
+        if (i == 0) {
+            pdl_wait();                          // the previous chunk's row pass has finished reading the scratch
+        }
         float2* const dst = p.out + r * n + c0 + g;
-        const float2* const stw = p.stage_tw + c0 + g;
 #pragma unroll
         for (int b = 0; b < CB; ++b) {
             const uint32_t jj = ja + R * b;
@@ -110,13 +181,17 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_cols_kernel(const TilePar
 #pragma unroll
             for (int t = 0; t < R; ++t) {
                 const uint32_t off = (jj + 16 * t) * kTileRowLen;
-                const float2 y = cmul(v[b * R + dft_pos<R>(t)], stw[off]);
+                const float2 y = cmul(v[b * R + dft_pos<R>(t)], sw[b * R + t]);
                 if (p.hints) {
                     stg_hint_f2(dst + off, y, pol_out);
                 } else {
                     dst[off] = y;
                 }
             }
+        }
+        if (++stage == kColsStages) {
+            stage = 0;
+            parity ^= 1;
         }
     }
 }
@@ -143,6 +218,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_rows256_kernel(const Tile
     const uint32_t my_blocks =
         first < blocks_total ? static_cast<uint32_t>((blocks_total - first + stride - 1) / stride) : 0u;
 
+    pdl_launch_dependents();
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kRows256Stages; ++s) {
@@ -151,12 +227,15 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_rows256_kernel(const Tile
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();                                              // the column pass has written the scratch
+    // Blocks are taken from the END of the scratch: the column pass wrote it front to back, so its most recently written
+    // (most likely still L2-resident) lines are read first.
     uint32_t issued = 0;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kRows256Stages; ++s) {
             if (issued < my_blocks) {
-                const uint64_t b = first + issued * stride;
+                const uint64_t b = blocks_total - 1 - (first + issued * stride);
                 mbar_expect_tx(&full[s], kRows256StageBytes);
                 tma_load_row(smem_raw + s * kRows256StageBytes, p.in + b * kTileElems, kRows256StageBytes, &full[s]);
                 ++issued;
@@ -167,7 +246,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_rows256_kernel(const Tile
 
     uint32_t stage = 0, parity = 0;
     for (uint32_t i = 0; i < my_blocks; ++i) {
-        const uint64_t blk = first + static_cast<uint64_t>(i) * stride;
+        const uint64_t blk = blocks_total - 1 - (first + static_cast<uint64_t>(i) * stride);
         const uint64_t row0 = blk * 16;                      // scratch row = transform * M1 + k1
         const uint64_t r = row0 / p.m1;
         const uint32_t k1_0 = static_cast<uint32_t>(row0 % p.m1);
@@ -183,7 +262,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_rows256_kernel(const Tile
         dft16(*reinterpret_cast<float2(*)[16]>(v));
         __syncthreads();                                     // landing consumed; previous block's x1 reads complete
         if (tid == 0 && issued < my_blocks) {                // refill this stage with the block two ahead
-            const uint64_t b = first + static_cast<uint64_t>(issued) * stride;
+            const uint64_t b = blocks_total - 1 - (first + static_cast<uint64_t>(issued) * stride);
             fence_proxy_async();
             mbar_expect_tx(&full[stage], kRows256StageBytes);
             tma_load_row(smem_raw + stage * kRows256StageBytes, p.in + b * kTileElems, kRows256StageBytes, &full[stage]);

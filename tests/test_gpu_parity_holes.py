@@ -3,6 +3,7 @@ C ABI directly — the block path bypasses decimation for 127 taps exactly as th
 b200_fir_* call reaches it; (2) b200_chain_exec_host (the e2e headline path) against b200_chain_exec bit for bit;
 (3) the backend / memory entry points of SURVEY §8 row a14 (b200_malloc ... b200_stream_*)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -235,3 +236,125 @@ def test_strong_bin_statistic_of_the_fused_chain(ref):
         want = ref.spectrum_engine(x, enable_scale=scale)
         st = assert_strong_bins(got, want, spec, slope=(2.0 / 120.0) if scale else None, label=f"scale={scale}")
         print(f"strong-bin statistic (within 60 dB of the row maximum), enableScale={scale}: {st}")
+
+
+# ---- large power-of-two transforms: the two-pass plans (fft_tile.cuh / fft_twopass.cuh) through the C ABI ------------------
+
+def _fft_c2c(x, forward=True, env=None, inplace=False, misalign=False):
+    """b200_fft_plan_c2c + b200_fft_exec on a [batch, n] CF32 array; env = plan-creation knobs (B200_FFT_TWOPASS_*)."""
+    import ctypes
+    import torch
+    from cyberether_b200 import _native
+    from cyberether_b200.jetstream import Context
+    lib = _native.load()
+    dev = torch.device("cuda:0")
+    ctx = Context.get(dev)
+    batch, n = x.shape
+    saved = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update({k: str(v) for k, v in (env or {}).items()})
+    try:
+        plan = ctypes.c_void_p()
+        _native.check(lib.b200_fft_plan_c2c(ctx.handle, n, batch, ctypes.byref(plan)))
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    if misalign:        # a view that starts on an odd sample: 8-byte but not 16-byte aligned
+        base = torch.zeros(batch * n + 1, dtype=torch.complex64, device=dev)
+        base[1:] = torch.from_numpy(x).to(dev).reshape(-1)
+        xin = base[1:]
+        assert xin.data_ptr() % 16 == 8
+    else:
+        xin = torch.from_numpy(x).to(dev).reshape(-1).clone()
+    out = xin if inplace else torch.empty(batch * n, dtype=torch.complex64, device=dev)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _native.check(lib.b200_fft_exec(plan, xin.data_ptr(), out.data_ptr(), 1 if forward else 0, s))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(batch, n).copy()
+    _native.check(lib.b200_fft_plan_destroy(plan))
+    return got
+
+
+@pytest.mark.parametrize("n", [16384, 32768, 65536, 131072])
+@pytest.mark.parametrize("forward", [True, False])
+def test_two_pass_fft_chunked_with_a_ragged_last_chunk(n, forward):
+    """Chunk size forced down to a few transforms: 11 transforms run as several chunks with a shorter last one; tolerance
+    2e-6 of the largest bin against the F64 transform (north star 1e-5; pocketfft F32 itself sits at ~3e-7)."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((11, n), 17 * n)
+    chunk_mb = max(1, (4 * n * 8) >> 20)             # 4 transforms per chunk -> chunks of 4, 4, 3
+    got = _fft_c2c(x, forward, env={"B200_FFT_TWOPASS_CHUNK_MB": chunk_mb})
+    want = np.fft.fft(x.astype(np.complex128), axis=1) if forward else np.fft.ifft(x.astype(np.complex128), axis=1) * n
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_two_pass_fft_in_place_and_misaligned_input(n):
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((5, n), 3 * n)
+    want = np.fft.fft(x.astype(np.complex128), axis=1)
+    scale = np.abs(want).max()
+    assert np.abs(_fft_c2c(x, inplace=True) - want).max() <= 2e-6 * scale
+    assert np.abs(_fft_c2c(x, misalign=True) - want).max() <= 2e-6 * scale
+    assert np.abs(_fft_c2c(x, env={"B200_FFT_TWOPASS_CHUNK_MB": 1}, inplace=True) - want).max() <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_two_pass_plans_agree_with_each_other_and_with_the_four_step_plan(n):
+    """Three independent decompositions of the same transform (tiled M1 x 256, radix-16 columns + rows, four-step)."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((3, n), n + 1)
+    tiled = _fft_c2c(x)
+    col16 = _fft_c2c(x, env={"B200_FFT_TWOPASS_TILE": 0})
+    four = _fft_c2c(x, env={"B200_FFT_TWOPASS": 0})
+    scale = np.abs(four).max()
+    assert np.abs(tiled - four).max() <= 2e-6 * scale and np.abs(col16 - four).max() <= 2e-6 * scale
+
+
+def test_fft_8192_roundtrip_and_reference(ref):
+    """The 8192-point kernel's last pass takes its twiddles from one register times W_16^b constants."""
+    from cyberether_b200.synthetic import gaussian_cf32
+    x = gaussian_cf32((7, 8192), 99)
+    got = _fft_c2c(x)
+    want = ref.fft(x, forward=True)
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    back = _fft_c2c(got, forward=False) / 8192
+    assert np.abs(back - x).max() <= 1e-5 * np.abs(x).max()
+
+
+def test_fft4096w_variant_matches_the_classic_chain_kernel():
+    """fft4096w_kernel (warp-local first exchange, opt-in) against fft4096_kernel on the same batch: same algorithm,
+    same twiddle products, different shared-memory routes — agreement to the chain tolerance on strong bins."""
+    import ctypes
+    import torch
+    import cyberether_b200 as cb
+    from cyberether_b200 import _native
+    from cyberether_b200.jetstream import Context
+    from cyberether_b200.synthetic import spectral_rows
+    lib = _native.load()
+    dev = torch.device("cuda:0")
+    ctx = Context.get(dev)
+    rows, n = 777, 4096
+    x = torch.from_numpy(spectral_rows(0, rows, n)).to(dev)
+    win = torch.zeros(n, dtype=torch.complex64, device=dev)
+    _native.check(lib.b200_window_blackman_cf32(ctx.handle, win.data_ptr(), n, None))
+    torch.cuda.synchronize()
+    plan = ctypes.c_void_p()
+    _native.check(lib.b200_chain_plan_create(ctx.handle, n, rows, win.data_ptr(), ctypes.byref(plan)))
+    coeff = cb.amplitude_scaling_coeff(n)
+    sc, off = cb.range_coefficients(-120.0, 0.0)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = {}
+    saved = os.environ.get("B200_FFT4096_VARIANT")
+    try:
+        for variant in ("classic", "w"):
+            os.environ["B200_FFT4096_VARIANT"] = variant
+            out = torch.full((rows, n), 7.0, dtype=torch.float32, device=dev)
+            _native.check(lib.b200_chain_exec(plan, x.data_ptr(), out.data_ptr(), rows, coeff, 0, sc, off, s))
+            torch.cuda.synchronize()
+            outs[variant] = out.cpu().numpy()
+    finally:
+        os.environ.pop("B200_FFT4096_VARIANT", None) if saved is None else os.environ.__setitem__("B200_FFT4096_VARIANT", saved)
+    a, b = outs["classic"], outs["w"]
+    strong = a >= a.max(axis=1, keepdims=True) - 60.0
+    assert np.abs(a - b)[strong].max() <= 1e-3
+    assert np.median(np.abs(a - b)) <= 1e-5

@@ -73,12 +73,14 @@ for n in (8192, 16384, 32768, 65536, 131072):
     else:
         if not QUICK:
             variants.append(("four-step plan (round 1)", {"B200_FFT_TWOPASS": 0}))
-        variants.append(("two-pass col16 chunk 64 MB", {"B200_FFT_TWOPASS_TILE": 0, "B200_FFT_TWOPASS_CHUNK_MB": 64}))
+        if n > 65536 or not QUICK:
+            variants.append(("two-pass col16 chunk 64 MB", {"B200_FFT_TWOPASS_TILE": 0, "B200_FFT_TWOPASS_CHUNK_MB": 64}))
         if n <= 65536:
-            for mb in ((32,) if QUICK else (16, 32, 48, 64, 96)):
+            for mb in ((96,) if QUICK else (32, 64, 96, 128, 192)):
                 variants.append((f"two-pass tiled chunk {mb} MB", {"B200_FFT_TWOPASS_CHUNK_MB": mb}))
-            variants.append(("two-pass tiled chunk 32 MB no hints", {"B200_FFT_TWOPASS_CHUNK_MB": 32, "B200_FFT_TWOPASS_HINTS": 0}))
-            variants.append(("two-pass tiled one chunk (no L2 residency)", {"B200_FFT_TWOPASS_CHUNK_MB": 4096}))
+            variants.append(("two-pass tiled chunk 96 MB no PDL", {"B200_FFT_TWOPASS_CHUNK_MB": 96, "B200_FFT_TWOPASS_PDL": 0}))
+            variants.append(("two-pass tiled chunk 96 MB no hints", {"B200_FFT_TWOPASS_CHUNK_MB": 96, "B200_FFT_TWOPASS_HINTS": 0}))
+            variants.append(("two-pass tiled one chunk", {"B200_FFT_TWOPASS_CHUNK_MB": 4096}))
     for label, env in variants:
         pl = plan_with(env, n, rows)
         run = lambda f=1: _native.check(lib.b200_fft_exec(pl, xx.data_ptr(), yy.data_ptr(), f, sp))
