@@ -439,8 +439,17 @@ static bool twopass_pdl() {
 static int launch_tile_cols(const b200_ctx* ctx, const TileParams& p, cudaStream_t stream, const bool pdl) {
     const uint64_t columns_per_tile = kTileElems / p.m1;
     const uint64_t tiles = p.transforms * (kTileRowLen / columns_per_tile);
-    void (*kernel)(TileParams, CUtensorMap) =
-        p.m1 == 64 ? fft_cols_kernel<6> : (p.m1 == 128 ? fft_cols_kernel<7> : fft_cols_kernel<8>);
+    void (*kernel)(TileParams, CUtensorMap) = nullptr;
+#define B200_COLS_PICK(WIN)                                                                                        \
+    kernel = p.m1 == 64 ? fft_cols_kernel<6, WIN> : (p.m1 == 128 ? fft_cols_kernel<7, WIN> : fft_cols_kernel<8, WIN>)
+    if (p.win_re) {
+        B200_COLS_PICK(WIN_REAL);
+    } else if (p.win_c) {
+        B200_COLS_PICK(WIN_COMPLEX);
+    } else {
+        B200_COLS_PICK(WIN_NONE);
+    }
+#undef B200_COLS_PICK
     B200_REQUIRE(p.m1 == 64 || p.m1 == 128 || p.m1 == 256, "tiled two-pass fft: unsupported column length %u", p.m1);
     B200_REQUIRE(tensor_map_encoder() != nullptr, "tiled two-pass fft: cuTensorMapEncodeTiled is not available");
     // the chunk as [transforms * M1 lines][512 floats]; one box = one tile = M1 lines x 2 C floats
@@ -463,12 +472,15 @@ static int launch_tile_cols(const b200_ctx* ctx, const TileParams& p, cudaStream
     return B200_SUCCESS;
 }
 
-static int launch_tile_rows(const b200_ctx* ctx, const TileParams& p, cudaStream_t stream, const bool pdl) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(fft_rows256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRows256SmemBytes));
+static int launch_tile_rows(const b200_ctx* ctx, const TileParams& p, cudaStream_t stream, const bool pdl,
+                            const int mode = MODE_C2C) {
+    void (*kernel)(TileParams) = mode == MODE_AMP ? fft_rows256_kernel<MODE_AMP>
+                                                  : (mode == MODE_AMP_RANGE ? fft_rows256_kernel<MODE_AMP_RANGE>
+                                                                            : fft_rows256_kernel<MODE_C2C>);
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRows256SmemBytes));
     const uint64_t blocks = p.transforms * (p.m1 / 16);
     const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
-    B200_CUDA_CHECK(launch_pdl(fft_rows256_kernel, static_cast<unsigned>(blocks < cap ? blocks : cap), kRows256SmemBytes,
-                               stream, pdl, p));
+    B200_CUDA_CHECK(launch_pdl(kernel, static_cast<unsigned>(blocks < cap ? blocks : cap), kRows256SmemBytes, stream, pdl, p));
     return B200_SUCCESS;
 }
 
@@ -642,6 +654,7 @@ struct b200_chain_plan {
     float2* win_c;    // non-null: general complex window
     const char* variant;
     bool composite = false;           // lengths without a single-kernel path
+    bool tiled = false;               // n = 16384 / 32768 / 65536: two fused kernels over the tiled two-pass plan (fft_tile.cuh)
     b200_fft_plan* fft = nullptr;
     float2* scratch = nullptr;
     float2* cast_scratch = nullptr;   // typed input without a fused path: cast -> CF32 here, then the CF32 chain
@@ -981,7 +994,8 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
     pl->win_re = nullptr;
     pl->win_c = nullptr;
     pl->variant = "";
-    if (!fft_size_supported(n)) {
+    const bool tiled = twopass_selected(n) && twopass_tiled(n);
+    if (!fft_size_supported(n) && !tiled) {
         // Lengths the single-kernel paths do not cover (not a power of two, or > 16384): the reference's own module
         // sequence on this provider — multiply -> fft (four-step / Bluestein plan) -> amplitude -> range — through a
         // plan-owned CF32 scratch. Same results, 4+ passes over the data instead of one.
@@ -1007,7 +1021,14 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
         *plan = pl;
         return B200_SUCCESS;
     }
-    if (make_twiddle_table(ctx, n, &pl->twiddle) != B200_SUCCESS) {
+    if (tiled) {
+        // window multiply fused into the column pass, amplitude / range into the row pass of the tiled two-pass plan
+        pl->tiled = true;
+        if (b200_fft_plan_c2c(ctx, n, std::max<uint64_t>(1, max_batch), &pl->fft) != B200_SUCCESS) {
+            delete pl;
+            return B200_ERROR;
+        }
+    } else if (make_twiddle_table(ctx, n, &pl->twiddle) != B200_SUCCESS) {
         delete pl;
         return B200_ERROR;
     }
@@ -1048,7 +1069,8 @@ int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const 
             return fail("b200_chain_plan_create: window upload failed: %s", cudaGetErrorString(e));
         }
     }
-    pl->variant = n == kFft4096N ? "fft4096_kernel<tma,radix16x3>"
+    pl->variant = pl->tiled ? "fft_cols_kernel<window> + fft_rows256_kernel<amplitude,range> (tiled two-pass, L2-resident scratch)"
+                  : n == kFft4096N ? "fft4096_kernel<tma,radix16x3>"
                                  : (n >= 16 && n <= 8192 ? "fft_radix_kernel<tma,radix16 stockham>"
                                                          : "fft_generic_kernel<stockham4>");
     cudaStreamSynchronize(cudaStreamLegacy);   // uploads / zero-fills above ran on the legacy stream: settle them before a non-blocking stream executes
@@ -1113,6 +1135,40 @@ static int chain_launch(b200_chain_plan* plan, const float2* x, float* out, uint
     }
     FftParams p{};
     chain_params(plan, x, out, batch, amp_coeff, enable_range, scale, offset, &p);
+    if (plan->tiled) {
+        b200_fft_plan* fft = plan->fft;
+        const uint64_t n = plan->n;
+        const bool pdl = twopass_pdl();
+        for (uint64_t row0 = 0; row0 < batch; row0 += fft->chunk_rows) {
+            TileParams t{};
+            t.in = x + row0 * n;
+            t.out = fft->scratch_a;
+            t.transforms = std::min(fft->chunk_rows, batch - row0);
+            t.m1 = static_cast<uint32_t>(fft->n1);
+            t.inverse = 0;
+            t.table = fft->sub1->twiddle;
+            t.stage_tw = fft->step_twiddle;
+            t.hints = fft->hints;
+            t.win_re = plan->win_re;
+            t.win_c = plan->win_c;
+            t.epi = p;
+            if ((reinterpret_cast<uintptr_t>(t.in) & 15u) != 0) {
+                return fail("b200_chain_exec: the tiled chain needs a 16-byte aligned input");
+            }
+            if (launch_tile_cols(plan->ctx, t, s, pdl && row0 > 0) != B200_SUCCESS) {
+                return B200_ERROR;
+            }
+            t.in = fft->scratch_a;
+            t.out = reinterpret_cast<float2*>(out + row0 * n);
+            t.table = fft->sub2->twiddle;
+            t.win_re = nullptr;
+            t.win_c = nullptr;
+            if (launch_tile_rows(plan->ctx, t, s, pdl, enable_range ? MODE_AMP_RANGE : MODE_AMP) != B200_SUCCESS) {
+                return B200_ERROR;
+            }
+        }
+        return B200_SUCCESS;
+    }
     const int win = plan->win_re ? WIN_REAL : (plan->win_c ? WIN_COMPLEX : WIN_NONE);
 #define B200_CHAIN_DISPATCH(MODE)                                                   \
     switch (win) {                                                                  \

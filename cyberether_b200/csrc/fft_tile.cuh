@@ -45,6 +45,11 @@ struct TileParams {
     const float2* table;      // pass 1: W_M1^j (j < M1); pass 2: W_256^j
     const float2* stage_tw;   // pass 1: [M1][256] W_n^(k1 n2)
     int hints;                // pass 1: L2 eviction-priority hints (input evict_first, scratch evict_last)
+    // fused spectral chain (spectrum_engine at n = 16384 / 32768 / 65536): window multiply in the column pass's load,
+    // amplitude / range epilogue (epi.amp_scale ... epi.zero_value, as fft4096_kernel) in the row pass's store
+    const float* win_re;      // [n] real window (WIN_REAL)
+    const float2* win_c;      // [n] complex window (WIN_COMPLEX)
+    FftParams epi;
 };
 
 // ---- pass 1: column transforms of length M1 over tiles of C adjacent columns ----------------------------------------
@@ -58,7 +63,7 @@ __host__ __device__ constexpr int cols_smem_bytes(const int n) {
     return kColsStages * kColsStageBytes + ((cols_x1_bytes(n) + 127) / 128) * 128 + 64;
 }
 
-template <int LOG2M1>
+template <int LOG2M1, int WIN = WIN_NONE>
 __global__ void __launch_bounds__(kTileThreads, 2)
     fft_cols_kernel(const TileParams p, const __grid_constant__ CUtensorMap in_map) {
     constexpr int N = 1 << LOG2M1;               // 64, 128, 256
@@ -127,14 +132,31 @@ __global__ void __launch_bounds__(kTileThreads, 2)
         const uint64_t r = tile / kTilesPerTransform;
         const uint32_t c0 = static_cast<uint32_t>(tile % kTilesPerTransform) * C;
         const float2* const land = reinterpret_cast<const float2*>(smem_raw + stage * kColsStageBytes);
+        // window taps of this thread's 16 samples (fused chain): issued before the wait on the landing
+        float wr[WIN == WIN_REAL ? 16 : 1];
+        float2 wc[WIN == WIN_COMPLEX ? 16 : 1];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            if constexpr (WIN == WIN_REAL) {
+                wr[t] = p.win_re[(ja + t * T) * kTileRowLen + c0 + g];
+            } else if constexpr (WIN == WIN_COMPLEX) {
+                wc[t] = p.win_c[(ja + t * T) * kTileRowLen + c0 + g];
+            }
+        }
         mbar_wait(&full[stage], parity);
         float2 v[16];
         // ---- pass A: radix 16 over n1 = ja + t T -------------------------------------------------------
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             float2 x = land[(ja + t * T) * C + g];
-            if (p.inverse) {
-                x = make_float2(x.y, x.x);
+            if constexpr (WIN == WIN_REAL) {
+                x = apply_window<WIN>(x, wr[t], make_float2(0.f, 0.f));
+            } else if constexpr (WIN == WIN_COMPLEX) {
+                x = apply_window<WIN>(x, 0.f, wc[t]);
+            } else {
+                if (p.inverse) {
+                    x = make_float2(x.y, x.x);
+                }
             }
             v[t] = x;
         }
@@ -202,6 +224,7 @@ constexpr int kRows256StageBytes = kTileElems * 8;                              
 constexpr int kRows256X1Bytes = 16 * tile_pitch(kTileRowLen) * 8;                 // 34944
 constexpr int kRows256SmemBytes = kRows256Stages * kRows256StageBytes + kRows256X1Bytes + 64;
 
+template <int MODE = MODE_C2C>
 __global__ void __launch_bounds__(kTileThreads, 2) fft_rows256_kernel(const TileParams p) {
     constexpr int N = kTileRowLen;
     constexpr int P = tile_pitch(N);
@@ -280,14 +303,25 @@ __global__ void __launch_bounds__(kTileThreads, 2) fft_rows256_kernel(const Tile
         }
         twiddle_inputs<16>(v, tw);
         dft16(*reinterpret_cast<float2(*)[16]>(v));
-        float2* const out = p.out + r * n + k1_0 + gb;
+        if constexpr (MODE == MODE_C2C) {
+            float2* const out = p.out + r * n + k1_0 + gb;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            float2 X = v[dft_pos<16>(t)];
-            if (p.inverse) {
-                X = make_float2(X.y, X.x);
+            for (int t = 0; t < 16; ++t) {
+                float2 X = v[dft_pos<16>(t)];
+                if (p.inverse) {
+                    X = make_float2(X.y, X.x);
+                }
+                stg_stream_f2(out + static_cast<uint64_t>(jj + 16 * t) * p.m1, X);
             }
-            stg_stream_f2(out + static_cast<uint64_t>(jj + 16 * t) * p.m1, X);
+        } else {
+            // fused chain: |X| -> dB (-> range), F32; the 16 lanes of a half-warp store 64 contiguous bytes
+            float* const out = reinterpret_cast<float*>(p.out) + r * n + k1_0 + gb;
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) {
+                const float2 res = spectral_epilogue2<MODE>(v[dft_pos<16>(t)], v[dft_pos<16>(t + 1)], p.epi);
+                stg_stream_f1(out + static_cast<uint64_t>(jj + 16 * t) * p.m1, res.x);
+                stg_stream_f1(out + static_cast<uint64_t>(jj + 16 * (t + 1)) * p.m1, res.y);
+            }
         }
         if (++stage == kRows256Stages) {
             stage = 0;

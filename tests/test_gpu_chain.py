@@ -73,13 +73,29 @@ def test_chain_sanity_golden():
     assert abs(float(sc[0].max()) - 0.956732) < 5e-6
 
 
-@pytest.mark.parametrize("n", [8, 64, 256, 1024, 2048, 8192, 16384])
+@pytest.mark.parametrize("n", [8, 64, 256, 1024, 2048, 8192, 16384, 32768, 65536])
 def test_chain_other_sizes(ref, n):
     from cyberether_b200.synthetic import spectral_rows
     x = spectral_rows(7, 5, n=n)
     want = ref.spectrum_engine(x, enable_scale=True, range_min=-100.0, range_max=-10.0)
     got = _run_chain(x, True, -100.0, -10.0)
     assert_db_close(got, want, true_spectrum(x, _window(ref, n)), scale=_range_slope(-100.0, -10.0), floor=3e-7)
+
+
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_chain_tiled_two_pass_in_several_chunks_and_db_mode(ref, n, monkeypatch):
+    """n = 16384 / 32768 / 65536: window multiply fused into the column pass, amplitude (/ range) into the row pass of the
+    tiled two-pass plan (fft_tile.cuh). The chunk is forced down to 2 spectra so 5 spectra run as chunks of 2, 2, 1."""
+    from cyberether_b200.synthetic import spectral_rows
+    monkeypatch.setenv("B200_FFT_TWOPASS_CHUNK_MB", str(max(1, (2 * n * 8) >> 20)))
+    x = spectral_rows(11, 5, n=n)
+    spec = true_spectrum(x, _window(ref, n))
+    assert_db_close(_run_chain(x, False), ref.spectrum_engine(x, enable_scale=False), spec)
+    want = ref.spectrum_engine(x, enable_scale=True, range_min=-90.0, range_max=-20.0)
+    assert_db_close(_run_chain(x, True, -90.0, -20.0), want, spec, scale=_range_slope(-90.0, -20.0), floor=3e-7)
+    zero = np.zeros((3, n), np.complex64)
+    assert np.all(np.isneginf(_run_chain(zero, False)))
+    assert np.array_equal(_run_chain(zero, True), ref.spectrum_engine(zero, enable_scale=True))
 
 
 def test_chain_zero_input(ref):
