@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200_fft_plan_c2c": (c_int, [c_vp, c_u64, c_u64, P(c_vp)]),
     "b200_fft_exec": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b200_fft_plan_destroy": (c_int, [c_vp]),
+    "b200_fft_exec_real": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "b200_fft_real_helper": (c_int, [c_vp, c_int, c_vp, c_vp, c_u64, c_u64, c_vp]),
     "b200_amplitude_cf32": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_vp]),
     "b200_amplitude_f32": (c_int, [c_vp, c_vp, c_vp, c_u64, c_f32, c_vp]),

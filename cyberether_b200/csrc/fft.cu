@@ -13,14 +13,11 @@
 #ifndef B200_FFT4096_DEFAULT_CTAS
 #define B200_FFT4096_DEFAULT_CTAS 2
 #endif
-#ifndef B200_FFT4096_DEFAULT_W
-#define B200_FFT4096_DEFAULT_W 0      // 1: fft4096w_kernel is the CF32 chain kernel unless B200_FFT4096_VARIANT says otherwise
-#endif
+
 
 #include "fft_radix.cuh"
 #include "fft_twopass.cuh"
 #include "fft_tile.cuh"
-#include "fft4096w.cuh"
 
 namespace b200 {
 
@@ -165,7 +162,7 @@ static int fft4096_ctas() {
     return value;
 }
 
-// ---- fft4096w_kernel (warp-local first exchange, 2-D swizzled TMA landing; fft4096w.cuh) -------------------------------
+// ---- tensor maps (2-D TMA tiles of the column pass, fft_tile.cuh) ------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point query: the library does not link libcuda.
 typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -181,40 +178,6 @@ static TensorMapEncodeTiledFn tensor_map_encoder() {
         return reinterpret_cast<TensorMapEncodeTiledFn>(f);
     }();
     return fn;
-}
-
-// B200_FFT4096_VARIANT=w|classic selects the CF32 chain kernel (read per launch: A/B runs in one process).
-static bool fft4096_use_w(const FftParams& p) {
-    const char* env = getenv("B200_FFT4096_VARIANT");
-    const bool want = env ? (env[0] == 'w') : (B200_FFT4096_DEFAULT_W != 0);
-    return want && p.rows * 256ull < (1ull << 31) && (reinterpret_cast<uintptr_t>(p.in) & 15u) == 0 &&
-           tensor_map_encoder() != nullptr;
-}
-
-template <int MODE, int WIN, bool AGC = false, bool COLSUM = false>
-static int launch_4096w(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream, unsigned* grid_out = nullptr) {
-    // the batch as [rows * 256 lines][32 floats]: one box = one 4096-point row = 256 lines of 128 bytes, swizzled
-    CUtensorMap map;
-    const cuuint64_t dims[2] = {32, p.rows * 256ull};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {32, 256};
-    const cuuint32_t elem[2] = {1, 1};
-    const CUresult rc = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(p.in), dims,
-                                             strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-        return fail("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(rc));
-    }
-    auto kernel = fft4096w_kernel<MODE, WIN, AGC, COLSUM>;
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFft4096wSmemBytes));
-    const uint64_t cap = static_cast<uint64_t>(ctx->sms) * 2;
-    const unsigned grid = static_cast<unsigned>(p.rows < cap ? p.rows : cap);
-    if (grid_out) {
-        *grid_out = grid;
-    }
-    kernel<<<grid, kFft4096Threads, kFft4096wSmemBytes, stream>>>(p, map);
-    B200_LAUNCH_CHECK();
-    return B200_SUCCESS;
 }
 
 template <int MODE, int WIN, int CTAS>
@@ -234,11 +197,6 @@ static int launch_4096_ctas(const b200_ctx* ctx, const FftParams& p, cudaStream_
 // Fused complex-integer ingest (cast -> window -> fft -> [agc] -> amplitude -> range in one kernel), real window only.
 template <int MODE, int ITYPE, bool AGC = false, bool COLSUM = false>
 static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream, unsigned* grid_out = nullptr) {
-    if constexpr (ITYPE == IN_CF32) {
-        if (fft4096_use_w(p)) {
-            return launch_4096w<MODE, WIN_REAL, AGC, COLSUM>(ctx, p, stream, grid_out);
-        }
-    }
     auto kernel = fft4096_kernel<MODE, WIN_REAL, 2, ITYPE, AGC, COLSUM>;
     constexpr int smem = ITYPE == IN_CF32 ? fft4096_smem_bytes(2) : fft4096_int_smem_bytes(ITYPE);
     // Set on every launch (a cheap runtime call): the attribute belongs to the CUDA *context*, and a host such as the
@@ -256,9 +214,6 @@ static int launch_4096_int(const b200_ctx* ctx, const FftParams& p, cudaStream_t
 
 template <int MODE, int WIN>
 static int launch_4096(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
-    if (fft4096_use_w(p)) {
-        return launch_4096w<MODE, WIN>(ctx, p, stream);
-    }
     if (fft4096_ctas() == 3) {
         return launch_4096_ctas<MODE, WIN, 3>(ctx, p, stream);
     }
@@ -546,9 +501,44 @@ struct b200_fft_plan {
     int hints = 1;
     // tiled form (n = M1 x 256, fft_tile.cuh): sub1 carries the W_M1 table, sub2 the W_256 table, step_twiddle [M1][256]
     bool tiled = false;
+    float2* real_work = nullptr;      // b200_fft_exec_real: [batch, n] spectra of the even/odd-packed rows
 };
 
 namespace b200 {
+
+// Real input of length 2h through ONE complex transform of length h (b200_fft_exec_real): z[m] = x[2m] + i x[2m+1] is the
+// input array itself viewed as CF32; with Z = FFT_h(z),
+//   X[k] = (Z[k] + conj(Z[h-k])) / 2  +  W_2h^k (Z[k] - conj(Z[h-k])) / (2i),   k = 0 .. h   (Z[h] = Z[0]).
+// layout 0: [batch, h + 1] CF32 (pocketfft::r2c); layout 1: FFTPACK half-complex [Re X0, Re X1, Im X1, ..., Re Xh] F32.
+__global__ void rfft_unpack_kernel(const float2* __restrict__ z, void* __restrict__ out, const uint64_t batch,
+                                   const uint64_t h, const int layout) {
+    const uint64_t per_row = h + 1, total = batch * per_row;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t row = i / per_row, k = i - row * per_row;
+        const float2* const zr = z + row * h;
+        const float2 a = zr[k == h ? 0 : k];
+        const float2 m = zr[k == 0 || k == h ? 0 : h - k];
+        const float2 e = make_float2(0.5f * (a.x + m.x), 0.5f * (a.y - m.y));          // (a + conj m) / 2
+        const float2 o = make_float2(0.5f * (a.y + m.y), -0.5f * (a.x - m.x));         // (a - conj m) / (2i)
+        float sn, cs;
+        sincospif(-static_cast<float>(k) / static_cast<float>(h), &sn, &cs);           // W_2h^k = exp(-i pi k / h)
+        const float2 x = make_float2(e.x + (cs * o.x - sn * o.y), e.y + (cs * o.y + sn * o.x));
+        if (layout == 0) {
+            static_cast<float2*>(out)[i] = x;
+        } else {
+            float* const r = static_cast<float*>(out) + row * (2 * h);
+            if (k == 0) {
+                r[0] = x.x;
+            } else if (k == h) {
+                r[2 * h - 1] = x.x;
+            } else {
+                r[2 * k - 1] = x.x;
+                r[2 * k] = x.y;
+            }
+        }
+    }
+}
 
 constexpr uint64_t kMaxDirectN = 8192;      // single-CTA register-radix kernel (fft_radix.cuh); 16384 via fft_generic_kernel
 
@@ -960,6 +950,36 @@ int b200_fft_exec(b200_fft_plan* plan, const b200_cf32* in, b200_cf32* out, int 
                          as_stream(stream));
 }
 
+int b200_fft_exec_real(b200_fft_plan* half_plan, const float* in, void* out, int layout, b200_stream stream) {
+    B200_REQUIRE(half_plan, "b200_fft_exec_real: null plan");
+    B200_REQUIRE(layout == 0 || layout == 1, "b200_fft_exec_real: layout must be 0 (R2C) or 1 (FFTPACK)");
+    if (half_plan->batch == 0) {
+        return B200_SUCCESS;
+    }
+    B200_REQUIRE(in && out, "b200_fft_exec_real: null buffer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7u) == 0, "b200_fft_exec_real: the real input must be 8-byte aligned");
+    DeviceGuard guard(half_plan->ctx);
+    const uint64_t h = half_plan->n, batch = half_plan->batch;
+    if (!half_plan->real_work) {
+        void* w = nullptr;
+        if (b200_malloc(half_plan->ctx, batch * h * sizeof(float2), &w) != B200_SUCCESS) {
+            return B200_ERROR;
+        }
+        half_plan->real_work = static_cast<float2*>(w);
+        cudaStreamSynchronize(cudaStreamLegacy);
+    }
+    const cudaStream_t s = as_stream(stream);
+    if (fft_exec_impl(half_plan, reinterpret_cast<const float2*>(in), half_plan->real_work, 1, s) != B200_SUCCESS) {
+        return B200_ERROR;
+    }
+    const uint64_t items = batch * (h + 1);
+    const uint64_t blocks = (items + 255) / 256, cap = static_cast<uint64_t>(half_plan->ctx->sms) * 8;
+    rfft_unpack_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(half_plan->real_work, out, batch, h,
+                                                                                       layout);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
 int b200_fft_plan_destroy(b200_fft_plan* plan) {
     if (!plan) {
         return B200_SUCCESS;
@@ -975,6 +995,7 @@ int b200_fft_plan_destroy(b200_fft_plan* plan) {
     cudaFree(plan->chirp_spec_inv);
     cudaFree(plan->scratch_a);
     cudaFree(plan->scratch_b);
+    cudaFree(plan->real_work);
     delete plan;
     return B200_SUCCESS;
 }

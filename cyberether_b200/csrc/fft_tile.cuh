@@ -18,11 +18,22 @@
 // The scratch is one chunk of the batch that stays in the 126 MB L2 between the two launches (fft.cu).
 #pragma once
 
-#include "fft4096w.cuh"
+#include <cuda.h>
+
 #include "fft_radix.cuh"
 #include "fft_twopass.cuh"
 
 namespace b200 {
+
+// 2-D tensor-map TMA tile load (SASS UTMALDG), completion on the mbarrier.
+__device__ __forceinline__ void tma_load_tile_2d(void* smem_dst, const CUtensorMap* map, const int c0, const int c1,
+                                                 uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
 
 constexpr int kTileThreads = 256;
 constexpr int kTileElems = 4096;                         // complex samples per CTA iteration

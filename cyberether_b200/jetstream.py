@@ -19,6 +19,7 @@ Reference interfaces mirrored:
 from __future__ import annotations
 
 import ctypes
+import os
 import enum
 import math
 from dataclasses import dataclass, field
@@ -797,6 +798,7 @@ class Fft(Module):
     def __init__(self):
         super().__init__()
         self._plan_handle = None
+        self._half_plan = None
 
     def validate(self):
         self._axis = None
@@ -881,6 +883,22 @@ class Fft(Module):
             if not ok(self._layout.gather(ctx, self.input.data, self._stage_in, stream)):
                 return Result.ERROR
             src = self._stage_in
+        # 1b. real forward transforms of even length: ONE complex transform of half the length on the row itself (viewed
+        # as even/odd-packed CF32) + one unpack kernel (b200_fft_exec_real) instead of cast -> full C2C -> pack
+        if self._kind != "c2c" and forward and self._n >= 4 and self._n % 2 == 0 and src.data_ptr() % 8 == 0 and \
+                os.environ.get("B200_FFT_REAL_HALF", "1") != "0":
+            if self._half_plan is None:
+                handle = ctypes.c_void_p()
+                if not ok(_call("b200_fft_plan_c2c", ctx.handle, self._n // 2, self._batch, ctypes.byref(handle))):
+                    return Result.ERROR
+                self._half_plan = handle
+            dense_out = self.output.data if self._out_layout.direct else self._stage_out
+            layout = 0 if self._kind == "r2c" else 1
+            if not ok(_call("b200_fft_exec_real", self._half_plan, vp(src), vp(dense_out), layout, stream)):
+                return Result.ERROR
+            if self._out_layout.direct:
+                return Result.SUCCESS
+            return self._out_layout.scatter(ctx, dense_out, self.output.data, self._out_layout.shape_p, stream)
         # 2. to the complex work buffer
         if self._kind == "c2c":
             work_in = src
@@ -919,6 +937,9 @@ class Fft(Module):
         if self._plan_handle is not None:
             _call("b200_fft_plan_destroy", self._plan_handle)
             self._plan_handle = None
+        if self._half_plan is not None:
+            _call("b200_fft_plan_destroy", self._half_plan)
+            self._half_plan = None
         return Result.SUCCESS
 
     def destroy(self):

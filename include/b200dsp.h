@@ -140,6 +140,14 @@ int b200_fft_plan_destroy(b200_fft_plan* plan);
 int b200_fft_real_helper(b200_ctx* ctx, int op, const void* in, void* out, uint64_t batch, uint64_t n,
                          b200_stream stream);
 
+/* Forward transform of REAL rows of even length 2h through one complex transform of length h (the row itself is the
+ * even/odd-packed CF32 input) and one unpack kernel: 16 bytes of traffic per real sample instead of the 40 of
+ * cast -> full C2C -> pack. `half_plan` = b200_fft_plan_c2c(ctx, h, batch); in [batch, 2h] F32 (8-byte aligned);
+ * layout 0: out [batch, h + 1] CF32 (pocketfft::r2c, `complexOutput`), layout 1: out [batch, 2h] F32 FFTPACK
+ * half-complex (pocketfft::r2r_fftpack) — src/domains/dsp/fft/module_impl_native_cpu.cc:142-167. The plan owns the
+ * [batch, h] work buffer (allocated on first use). Odd lengths and the inverse keep the composed path above. */
+int b200_fft_exec_real(b200_fft_plan* half_plan, const float* in, void* out, int layout, b200_stream stream);
+
 /* amplitude — src/domains/dsp/amplitude/module_impl_native_cpu.cc:73-99 with Backend::ApproxLog10
  * (include/jetstream/backend/devices/cpu/helpers.hh:61-74): out = |x|==0 ? -inf :
  * 20*ApproxLog10(|x|) + coeff, coeff = 20*log10f(1/N) (src/domains/dsp/amplitude/module_impl.cc:49-51).

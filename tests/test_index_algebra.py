@@ -291,93 +291,6 @@ def test_two_pass_plan_radix16_columns_then_strided_rows():
             assert np.abs(out - want).max() < 1e-9 * np.abs(want).max()
 
 
-def _wavefronts(byte_addresses, width):
-    """Shared-memory wavefronts of one warp instruction (32 lane addresses in lane order): 64-bit accesses are served one
-    half-warp at a time, 128-bit accesses one quarter-warp at a time; within a group the cost is the largest number of
-    DISTINCT 4-byte words any of the 32 banks has to deliver."""
-    group = {4: 32, 8: 16, 16: 8}[width]
-    total = 0
-    for g0 in range(0, 32, group):
-        words = {}
-        for addr in byte_addresses[g0:g0 + group]:
-            for j in range(width // 4):
-                word = addr // 4 + j
-                words.setdefault(word % 32, set()).add(word)
-        total += max(len(v) for v in words.values())
-    return total
-
-
-def test_fft4096w_warp_local_exchange_scheme():
-    """fft4096w_kernel (fft4096w.cuh): the row lands through a 2-D tensor map ([256 lines][128 B], SWIZZLE_128B:
-    16-byte chunk j of line R is stored at chunk j ^ (R & 7)); lane = 16 q3 + 8 cbit + q (digit = 8 q3 + q, c = 2 warp +
-    cbit), the digit being b in pass 1 and k0 in pass 2, so the first exchange (b <-> k0 for fixed c) stays inside the warp,
-    through one private [k0][b] tile per c (line pitch 144 B, tile stride 2368 B = 64 mod 128); the second exchange and pass 3 are
-    fft4096_kernel's. Every shared-memory instruction must sit at its wavefront floor."""
-    rng = np.random.default_rng(11)
-    x = rng.standard_normal(4096) + 1j * rng.standard_normal(4096)
-    land = np.zeros(4096, complex)                       # 8-byte slots of the swizzled landing buffer
-    for n in range(4096):
-        line, col = n >> 4, n & 15
-        land[line * 16 + (((col >> 1) ^ (line & 7)) << 1) + (col & 1)] = x[n]
-    tile_pitch, tile_stride = 144, 2368                  # 2368 = 64 (mod 128): the two tiles of a warp differ in bank phase
-    x1 = np.zeros(16 * tile_stride // 8, complex)        # 8-byte slots; tile c starts at byte c * 2368
-    stage = np.zeros(16 * 288, complex)
-
-    def tile_slot(c, k0, b):
-        byte = c * tile_stride + k0 * tile_pitch + b * 8
-        return byte // 8, byte
-
-    def lanes_of(w):
-        return [((lane >> 4) * 8 + (lane & 7), 2 * w + ((lane >> 3) & 1)) for lane in range(32)]   # (digit, c)
-
-    # The warps run concurrently: every warp's tile stores happen "before" any tile load here, so overlapping tiles
-    # would corrupt the result.
-    for w in range(8):
-        p1_addr = {a: [] for a in range(16)}
-        x1w_addr = {k: [] for k in range(16)}
-        for lane, (b, c) in enumerate(lanes_of(w)):      # pass 1: digit = b
-            off = b * 16 + (((c >> 1) ^ (b & 7)) << 1) + (c & 1)
-            v = np.array([land[a * 256 + off] for a in range(16)])
-            assert np.array_equal(v, np.array([x[256 * a + 16 * b + c] for a in range(16)]))
-            for a in range(16):
-                p1_addr[a].append(8 * (a * 256 + off))
-            y = dft16(v)
-            for k0 in range(16):                         # exchange 1, store: tile[c][k0][b]
-                slot, byte = tile_slot(c, k0, b)
-                assert x1[slot] == 0                     # nobody else's slot
-                x1[slot] = y[k0] * W(4096, (16 * b + c) * k0)
-                x1w_addr[k0].append(byte)
-        for a in range(16):
-            assert _wavefronts(p1_addr[a], 8) == 2       # 256 B per instruction: 2 is the floor
-            assert _wavefronts(x1w_addr[a], 8) == 2
-    for w in range(8):
-        x1r_addr = {j: [] for j in range(8)}
-        x2w_addr = {k: [] for k in range(16)}
-        for lane, (k0, c) in enumerate(lanes_of(w)):     # exchange 1, load (after __syncwarp): digit = k0, LDS.128
-            v = np.array([x1[tile_slot(c, k0, b)[0]] for b in range(16)])
-            for j in range(8):
-                x1r_addr[j].append(tile_slot(c, k0, 2 * j)[1])
-            y = dft16(v)
-            for k1 in range(16):                         # exchange 2, store: [k1][k0][c]
-                stage[288 * k1 + 18 * k0 + c] = y[k1] * W(256, c * k1)
-                x2w_addr[k1].append(8 * (288 * k1 + 18 * k0 + c))
-        for a in range(16):
-            assert _wavefronts(x2w_addr[a], 8) == 2
-        for j in range(8):
-            assert _wavefronts(x1r_addr[j], 16) == 4     # 512 B per instruction: 4 is the floor
-    out = np.zeros(4096, complex)
-    for w in range(8):                                   # pass 3 as fft4096_kernel: t = k0 + 16 k1
-        for c in range(0, 16, 2):
-            addrs = [8 * (288 * ((32 * w + lane) >> 4) + 18 * (lane & 15) + c) for lane in range(32)]
-            assert _wavefronts(addrs, 16) == 4
-    for t in range(256):
-        k0, k1 = t & 15, t >> 4
-        y = dft16(np.array([stage[288 * k1 + 18 * k0 + c] for c in range(16)]))
-        for k2 in range(16):
-            out[t + 256 * k2] = y[k2]
-    assert np.abs(out - np.fft.fft(x)).max() < 1e-9
-
-
 def test_tiled_two_pass_plan_columns_then_rows():
     """fft_tile.cuh: n = M1 x 256. Pass 1 (fft_cols_kernel): per column, radix 16 (butterfly ja reads ja + t T, writes
     16 ja + t) then radix R = M1 / 16 with Ns = 16 (butterfly jj reads jj + 16 t with W_M1^(jj t), writes k1 = jj + 16 t),
