@@ -366,7 +366,7 @@ static int launch_col16(const b200_ctx* ctx, const Col16Params& p, cudaStream_t 
 
 static bool twopass_tiled(const uint64_t n) {
     const char* env = getenv("B200_FFT_TWOPASS_TILE");
-    return !(env && atoi(env) == 0) && (n == 16384 || n == 32768 || n == 65536);
+    return !(env && atoi(env) == 0) && (n == 16384 || n == 32768 || n == 65536) && tensor_map_encoder() != nullptr;
 }
 
 // Launch with (pdl) or without the programmatic-stream-serialization attribute: with it the kernel may be scheduled while
@@ -510,32 +510,47 @@ namespace b200 {
 // input array itself viewed as CF32; with Z = FFT_h(z),
 //   X[k] = (Z[k] + conj(Z[h-k])) / 2  +  W_2h^k (Z[k] - conj(Z[h-k])) / (2i),   k = 0 .. h   (Z[h] = Z[0]).
 // layout 0: [batch, h + 1] CF32 (pocketfft::r2c); layout 1: FFTPACK half-complex [Re X0, Re X1, Im X1, ..., Re Xh] F32.
+// One thread per mirror pair (k, h - k): both outputs come from the same two inputs and one twiddle,
+//   X[k] = e + w o,  X[h-k] = conj(e - w o),  e = (Z[k] + conj Z[h-k]) / 2,  o = (Z[k] - conj Z[h-k]) / (2i),  w = W_2h^k.
+__device__ __forceinline__ void rfft_store(void* out, const int layout, const uint64_t row, const uint64_t h, const uint64_t k,
+                                           const float2 x) {
+    if (layout == 0) {
+        static_cast<float2*>(out)[row * (h + 1) + k] = x;
+    } else {
+        float* const r = static_cast<float*>(out) + row * (2 * h);
+        if (k == 0) {
+            r[0] = x.x;
+        } else if (k == h) {
+            r[2 * h - 1] = x.x;
+        } else {
+            r[2 * k - 1] = x.x;
+            r[2 * k] = x.y;
+        }
+    }
+}
 __global__ void rfft_unpack_kernel(const float2* __restrict__ z, void* __restrict__ out, const uint64_t batch,
                                    const uint64_t h, const int layout) {
-    const uint64_t per_row = h + 1, total = batch * per_row;
+    const uint64_t per_row = h / 2 + 1, total = batch * per_row;
     for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         const uint64_t row = i / per_row, k = i - row * per_row;
         const float2* const zr = z + row * h;
-        const float2 a = zr[k == h ? 0 : k];
-        const float2 m = zr[k == 0 || k == h ? 0 : h - k];
+        if (k == 0) {
+            const float2 a = zr[0];
+            rfft_store(out, layout, row, h, 0, make_float2(a.x + a.y, 0.0f));
+            rfft_store(out, layout, row, h, h, make_float2(a.x - a.y, 0.0f));
+            continue;
+        }
+        const float2 a = zr[k];
+        const float2 m = zr[h - k];
         const float2 e = make_float2(0.5f * (a.x + m.x), 0.5f * (a.y - m.y));          // (a + conj m) / 2
         const float2 o = make_float2(0.5f * (a.y + m.y), -0.5f * (a.x - m.x));         // (a - conj m) / (2i)
         float sn, cs;
         sincospif(-static_cast<float>(k) / static_cast<float>(h), &sn, &cs);           // W_2h^k = exp(-i pi k / h)
-        const float2 x = make_float2(e.x + (cs * o.x - sn * o.y), e.y + (cs * o.y + sn * o.x));
-        if (layout == 0) {
-            static_cast<float2*>(out)[i] = x;
-        } else {
-            float* const r = static_cast<float*>(out) + row * (2 * h);
-            if (k == 0) {
-                r[0] = x.x;
-            } else if (k == h) {
-                r[2 * h - 1] = x.x;
-            } else {
-                r[2 * k - 1] = x.x;
-                r[2 * k] = x.y;
-            }
+        const float2 t = make_float2(cs * o.x - sn * o.y, cs * o.y + sn * o.x);
+        rfft_store(out, layout, row, h, k, make_float2(e.x + t.x, e.y + t.y));
+        if (2 * k != h) {
+            rfft_store(out, layout, row, h, h - k, make_float2(e.x - t.x, -(e.y - t.y)));
         }
     }
 }
@@ -972,7 +987,7 @@ int b200_fft_exec_real(b200_fft_plan* half_plan, const float* in, void* out, int
     if (fft_exec_impl(half_plan, reinterpret_cast<const float2*>(in), half_plan->real_work, 1, s) != B200_SUCCESS) {
         return B200_ERROR;
     }
-    const uint64_t items = batch * (h + 1);
+    const uint64_t items = batch * (h / 2 + 1);
     const uint64_t blocks = (items + 255) / 256, cap = static_cast<uint64_t>(half_plan->ctx->sms) * 8;
     rfft_unpack_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(half_plan->real_work, out, batch, h,
                                                                                        layout);
@@ -1173,8 +1188,17 @@ static int chain_launch(b200_chain_plan* plan, const float2* x, float* out, uint
             t.win_re = plan->win_re;
             t.win_c = plan->win_c;
             t.epi = p;
-            if ((reinterpret_cast<uintptr_t>(t.in) & 15u) != 0) {
-                return fail("b200_chain_exec: the tiled chain needs a 16-byte aligned input");
+            if ((reinterpret_cast<uintptr_t>(t.in) & 15u) != 0) {      // TMA sources are 16-byte aligned: stage the chunk
+                if (!fft->scratch_b) {
+                    void* b = nullptr;
+                    if (b200_malloc(plan->ctx, fft->chunk_rows * n * sizeof(float2), &b) != B200_SUCCESS) {
+                        return B200_ERROR;
+                    }
+                    fft->scratch_b = static_cast<float2*>(b);
+                }
+                B200_CUDA_CHECK(cudaMemcpyAsync(fft->scratch_b, t.in, t.transforms * n * sizeof(float2),
+                                                cudaMemcpyDeviceToDevice, s));
+                t.in = fft->scratch_b;
             }
             if (launch_tile_cols(plan->ctx, t, s, pdl && row0 > 0) != B200_SUCCESS) {
                 return B200_ERROR;

@@ -42,12 +42,25 @@ report("multiply cf32 [16384,4096] x [1,4096]", timeit(lambda: _native.check(lib
 plan = ctypes.c_void_p(); _native.check(lib.b200_fft_plan_c2c(ctx.handle, n, rows, ctypes.byref(plan)))
 report("fft c2c 4096 x 16384", timeit(lambda: _native.check(lib.b200_fft_exec(plan, x.data_ptr(), y.data_ptr(), 1, sp))), rows * n, 16)
 report("cuFFT (torch.fft.fft) 4096 x 16384 [baseline]", timeit(lambda: torch.fft.fft(x)), rows * n, 16)
-for nn in (256, 1024, 2048, 8192, 16384):
+PLAN = {16384: "tiled two-pass plan 64 x 256", 32768: "tiled two-pass plan 128 x 256", 65536: "tiled two-pass plan 256 x 256",
+        131072: "two-pass plan 16 x 8192"}
+for nn in (256, 1024, 2048, 8192, 16384, 32768, 65536, 131072):
     rr = rows * n // nn
     xx = x.reshape(rr, nn); yy = y.reshape(rr, nn)
     pl = ctypes.c_void_p(); _native.check(lib.b200_fft_plan_c2c(ctx.handle, nn, rr, ctypes.byref(pl)))
-    report(f"fft c2c {nn} x {rr} ({'radix-16 kernel' if nn <= 8192 else 'four-step plan'})", timeit(lambda: _native.check(lib.b200_fft_exec(pl, xx.data_ptr(), yy.data_ptr(), 1, sp))), rr * nn, 16)
+    report(f"fft c2c {nn} x {rr} ({PLAN.get(nn, 'radix-16 kernel')})", timeit(lambda: _native.check(lib.b200_fft_exec(pl, xx.data_ptr(), yy.data_ptr(), 1, sp))), rr * nn, 16)
     report(f"cuFFT {nn} x {rr} [baseline]", timeit(lambda: torch.fft.fft(xx)), rr * nn, 16)
+    lib.b200_fft_plan_destroy(pl)
+# real input (the reference's F32-8192 / F32-65536 benchmark cases): half-length complex transform + unpack; 4 B in +
+# 4 B out per real sample
+xr = torch.view_as_real(x).reshape(-1)
+for nn in (8192, 65536):
+    rr = xr.numel() // nn
+    xx = xr.reshape(rr, nn); oo = torch.empty(rr, nn // 2 + 1, dtype=torch.complex64, device=dev)
+    pl = ctypes.c_void_p(); _native.check(lib.b200_fft_plan_c2c(ctx.handle, nn // 2, rr, ctypes.byref(pl)))
+    report(f"fft r2c {nn} x {rr} (half-length c2c + unpack)", timeit(lambda: _native.check(lib.b200_fft_exec_real(pl, xx.data_ptr(), oo.data_ptr(), 0, sp))), rr * nn, 8)
+    report(f"cuFFT r2c {nn} x {rr} [baseline]", timeit(lambda: torch.fft.rfft(xx)), rr * nn, 8)
+    lib.b200_fft_plan_destroy(pl); del oo
 coeff = cb.amplitude_scaling_coeff(n)
 report("amplitude cf32", timeit(lambda: _native.check(lib.b200_amplitude_cf32(ctx.handle, y.data_ptr(), f.data_ptr(), rows * n, coeff, sp))), rows * n, 12)
 sc, off = cb.range_coefficients(-120.0, 0.0)
@@ -67,6 +80,13 @@ report("unfused chain with cuFFT (reference CUDA structure)", timeit(unfused_cuf
 win = torch.zeros(n, dtype=torch.complex64, device=dev); win.real = torch.rand(n, device=dev)
 cp = ctypes.c_void_p(); torch.cuda.synchronize(); _native.check(lib.b200_chain_plan_create(ctx.handle, n, rows, win.data_ptr(), ctypes.byref(cp)))
 report("fused chain 4096 x 16384", timeit(lambda: _native.check(lib.b200_chain_exec(cp, x.data_ptr(), f.data_ptr(), rows, coeff, 1, sc, off, sp))), rows * n, 12)
+for nn in (8192, 16384, 65536):
+    rr = rows * n // nn
+    wn = torch.zeros(nn, dtype=torch.complex64, device=dev); wn.real = torch.rand(nn, device=dev)
+    cpn = ctypes.c_void_p(); torch.cuda.synchronize(); _native.check(lib.b200_chain_plan_create(ctx.handle, nn, rr, wn.data_ptr(), ctypes.byref(cpn)))
+    cn = cb.amplitude_scaling_coeff(nn)
+    report(f"fused chain {nn} x {rr}", timeit(lambda: _native.check(lib.b200_chain_exec(cpn, x.data_ptr(), f.data_ptr(), rr, cn, 1, sc, off, sp))), rr * nn, 12)
+    lib.b200_chain_plan_destroy(cpn)
 
 # ---- FIR (BASELINE config 3: 2^26 CF32 samples as [8192, 8192] frames)
 frames, T = 8192, 8192
