@@ -19,6 +19,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -51,11 +52,39 @@ struct FirParams {
     float taps_c[kFirConstTapWords];
 };
 
-template <int OB, bool REAL_TAPS, bool CONST_TAPS>
+// PAIR (real taps, even R, odd L, even stream length, 16-byte aligned stream): the same algorithm on 16-byte CHUNKS
+// c[n] = (x[2n], x[2n+1]) with decimation R / 2 and chunk-taps g[c] = (h[2c], h[2c-1]):
+//        y[q] = sum_c  h[2c] * x[qR - 2c]  +  h[2c-1] * x[qR - 2c + 1]  =  sum_c g[c] . chunk[q R/2 - c],
+// i.e. every p.* field below is in chunk units (p.R = R/2, p.L = (L+1)/2, p.n_in = n_in/2). One LDGSTS.128 stages two
+// samples and one LDS.128 feeds 2 OB packed FMAs: half the staging and window-load instructions of the 8-byte form.
+template <uint32_t BYTES>
+__device__ __forceinline__ void cp_async_elem(const uint32_t dst, const void* src) {
+    if constexpr (BYTES == 16) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    }
+}
+template <uint32_t BYTES>
+__device__ __forceinline__ void cp_async_elem_fill(const uint32_t dst, const void* src, const uint32_t bytes) {
+    if constexpr (BYTES == 16) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+}
+
+template <int OB, bool REAL_TAPS, bool CONST_TAPS, bool PAIR = false>
 __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ FirParams p) {
+    static_assert(!PAIR || REAL_TAPS, "chunk pairs exist for real taps");
+    using E = typename std::conditional<PAIR, float4, float2>::type;     // staged element
+    constexpr uint32_t EB = sizeof(E);
+    constexpr int TW = PAIR ? 2 : (REAL_TAPS ? 1 : 2);                   // floats per tap slot
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* const planes = reinterpret_cast<float2*>(smem_raw);
-    const uint32_t tap_words = p.heads * p.R * p.lp_pad * (REAL_TAPS ? 1 : 2);
+    E* const planes = reinterpret_cast<E*>(smem_raw);
+    const E* const xsrc = reinterpret_cast<const E*>(p.x);
+    const E* const hsrc = reinterpret_cast<const E*>(p.hist);
+    const uint32_t tap_words = p.heads * p.R * p.lp_pad * TW;
     float* const taps_s = reinterpret_cast<float*>(planes + static_cast<size_t>(p.R) * p.plane_pitch);
     float2* const out_s = reinterpret_cast<float2*>(taps_s + ((tap_words + 1) & ~1u));
 
@@ -87,30 +116,28 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ 
                 // nthreads % R == 0: a thread stays on one plane, source and destination advance by constants
                 // (3 instructions per request instead of 22 in the generic loop, which was 38 % of all
                 // instructions issued by the first version).
-                const float2* src = p.x + j0 + tid;
-                uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * 8u;
-                const uint32_t dst_step = step_pos * 8u;
+                const E* src = xsrc + j0 + tid;
+                uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * EB;
+                const uint32_t dst_step = step_pos * EB;
                 uint32_t i = tid;
                 for (; i + 3 * nthreads < span; i += 4 * nthreads) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + u * dst_step),
-                                     "l"(src + u * nthreads)
-                                     : "memory");
+                        cp_async_elem<EB>(dst + u * dst_step, src + u * nthreads);
                     }
                     src += 4 * nthreads;
                     dst += 4 * dst_step;
                 }
                 for (; i < span; i += nthreads) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                    cp_async_elem<EB>(dst, src);
                     src += nthreads;
                     dst += dst_step;
                 }
             } else if (interior) {
-                const float2* src = p.x + j0 + tid;
+                const E* src = xsrc + j0 + tid;
                 for (uint32_t i = tid; i < span; i += nthreads) {
-                    const uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * 8u;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                    const uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * EB;
+                    cp_async_elem<EB>(dst, src);
                     src += nthreads;
                     plane += step_plane;
                     pos += step_pos;
@@ -122,20 +149,19 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ 
             } else {
                 for (uint32_t i = tid; i < span; i += nthreads) {
                     const int64_t j = j0 + i;
-                    const float2* src = p.x;
+                    const E* src = xsrc;
                     uint32_t bytes = 0;
                     if (j >= 0) {
                         if (static_cast<uint64_t>(j) < p.n_in) {
-                            src = p.x + j;
-                            bytes = 8;
+                            src = xsrc + j;
+                            bytes = EB;
                         }
                     } else if (j >= -hist_len) {
-                        src = p.hist + (hist_len + j);
-                        bytes = 8;
+                        src = hsrc + (hist_len + j);
+                        bytes = EB;
                     }
-                    const uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * 8u;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes)
-                                 : "memory");
+                    const uint32_t dst = plane_base + (plane * p.plane_pitch + pos) * EB;
+                    cp_async_elem_fill<EB>(dst, src, bytes);
                     plane += step_plane;
                     pos += step_pos;
                     if (plane >= p.R) {
@@ -159,24 +185,33 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ 
             for (uint32_t plane = 0; plane < p.R; ++plane) {
                 // taps of this plane: k = kp0 + m R with kp0 = (R - plane) % R; input row offset D - m
                 const uint32_t d = plane == 0 ? p.hpad : p.hpad - 1;
-                const float2* const xp = planes + static_cast<size_t>(plane) * p.plane_pitch + o0 + d;
-                const float* const hp = taps_s + (static_cast<size_t>(head) * p.R + plane) * p.lp_pad *
-                                                     (REAL_TAPS ? 1 : 2);
-                float2 w[OB];
+                const E* const xp = planes + static_cast<size_t>(plane) * p.plane_pitch + o0 + d;
+                const float* const hp = taps_s + (static_cast<size_t>(head) * p.R + plane) * p.lp_pad * TW;
+                E w[OB];
 #pragma unroll
                 for (int i = 0; i < OB; ++i) {
                     w[i] = xp[i];
                 }
-                const float2* xq = xp;      // xq[-(s+1)] is the element tap (m0 + s + 1) slides in
+                const E* xq = xp;           // xq[-(s+1)] is the element tap (m0 + s + 1) slides in
                 const float* hq = hp;
-                uint32_t hc = (head * p.R + plane) * p.lp_pad * (REAL_TAPS ? 1 : 2);     // index into p.taps_c
+                uint32_t hc = (head * p.R + plane) * p.lp_pad * TW;     // index into p.taps_c
                 // taps actually present in this plane: k = kp0 + m R < L  (the padded tail is skipped, not multiplied)
                 const uint32_t kp0 = plane == 0 ? 0 : p.R - plane;
                 const uint32_t lp_plane = p.lp - (kp0 >= p.lp_thr ? 1u : 0u);      // == ceil((L - kp0) / R), no division
                 const uint32_t full = lp_plane / OB * OB;
                 auto tap_step = [&](const int s) {
                     // logical window element i lives in w[(i - s) mod OB]
-                    if constexpr (REAL_TAPS) {
+                    if constexpr (PAIR) {
+                        const float ha = CONST_TAPS ? p.taps_c[hc + 2 * s] : hq[2 * s];
+                        const float hb = CONST_TAPS ? p.taps_c[hc + 2 * s + 1] : hq[2 * s + 1];
+                        const float2 ga = make_float2(ha, ha), gb = make_float2(hb, hb);
+#pragma unroll
+                        for (int i = 0; i < OB; ++i) {
+                            const float4 v = w[(i - s + OB) % OB];
+                            acc[i] = __ffma2_rn(make_float2(v.x, v.y), ga, acc[i]);
+                            acc[i] = __ffma2_rn(make_float2(v.z, v.w), gb, acc[i]);
+                        }
+                    } else if constexpr (REAL_TAPS) {
                         const float h = CONST_TAPS ? p.taps_c[hc + s] : hq[s];
                         const float2 hh = make_float2(h, h);
 #pragma unroll
@@ -203,8 +238,8 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ 
                         tap_step(s);
                     }
                     xq -= OB;
-                    hq += OB * (REAL_TAPS ? 1 : 2);
-                    hc += OB * (REAL_TAPS ? 1 : 2);
+                    hq += OB * TW;
+                    hc += OB * TW;
                 }
                 const uint32_t rem = lp_plane - full;       // CTA-uniform
 #pragma unroll
@@ -294,6 +329,12 @@ struct b200_fir_plan {
     int ob;
     uint32_t lp_pad, hpad, threads, qt, plane_pitch;
     size_t smem;
+    // chunk-pair form (fir_decim_kernel<.., PAIR>): real taps, even R, odd L; geometry in 16-byte chunks
+    bool pair_ok = false;
+    int pair_ob = 0;
+    uint32_t pair_lp_pad = 0, pair_hpad = 0, pair_threads = 0, pair_qt = 0, pair_pitch = 0;
+    size_t pair_smem = 0;
+    std::vector<float> pair_taps_host;  // [heads][R/2][lp_pad] x (h[2c], h[2c-1])
     float* taps_dev;
     float2* hist[2];
     int cur;
@@ -314,6 +355,80 @@ static int fir_launch_variant(b200_fir_plan* pl, const FirParams& p, unsigned gr
     k<<<grid, pl->threads, pl->smem, s>>>(p);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
+}
+
+template <int OB>
+static int fir_launch_pair(b200_fir_plan* pl, const FirParams& p, unsigned grid, cudaStream_t s) {
+    auto k = fir_decim_kernel<OB, true, true, true>;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl->pair_smem)));
+    k<<<grid, pl->pair_threads, pl->pair_smem, s>>>(p);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+// Tile geometry for a stream of `elem_bytes` elements decimated by R with L taps of `tap_floats` floats each: the largest
+// odd OB (register sliding window) whose staged planes fit the shared-memory budget.
+struct FirGeometry {
+    bool ok = false;
+    int ob = 0;
+    uint32_t threads = 0, lp_pad = 0, hpad = 0, qt = 0, pitch = 0;
+    size_t smem = 0;
+};
+static FirGeometry fir_geometry(const uint32_t L, const uint32_t R, const uint32_t heads, const uint32_t tap_floats,
+                                const uint32_t elem_bytes, const int max_ob) {
+    FirGeometry g;
+    const uint32_t lp = (L + R - 1) / R;
+    const int ob_options[4] = {7, 5, 3, 1};
+    uint32_t thread_options[3] = {128, 64, 32};
+    if (const char* env = getenv("B200_FIR_THREADS")) {          // A/B aid: preferred CTA size
+        const int v = atoi(env);
+        if (v == 32 || v == 64 || v == 128) {
+            thread_options[0] = static_cast<uint32_t>(v);
+        }
+    }
+    const uint32_t period = 128 / elem_bytes;        // elements per 128-byte bank period
+    int largest = max_ob;
+    if (const char* env = getenv("B200_FIR_OB")) {               // A/B aid: largest OB to consider
+        largest = atoi(env);
+    }
+    const int first_ob = largest <= 1 ? 3 : (largest <= 3 ? 2 : (largest <= 5 ? 1 : 0));
+    for (int oi = first_ob; oi < 4 && !g.ok; ++oi) {
+        for (int ti = 0; ti < 3 && !g.ok; ++ti) {
+            const int ob = ob_options[oi];
+            const uint32_t threads = thread_options[ti];
+            const uint32_t lp_pad = (lp + ob - 1) / ob * ob;
+            const uint32_t hpad = lp_pad + 1;                       // rows of history incl. slack for padded taps
+            const uint32_t qt = threads * ob;
+            // A warp stages 32 consecutive elements = R planes x 32/R rows with one cp.async each; the planes of one
+            // conflict group (16 lanes for 8-byte, 8 lanes for 16-byte elements) land on disjoint banks when the pitch is
+            // period / R (mod period) for R | period; an odd pitch otherwise. (The compute phase reads one plane at a
+            // time with a lane stride of OB elements, OB odd: any pitch is fine.)
+            uint32_t pitch = qt + hpad + 1;
+            if (R > 1 && period % R == 0) {
+                const uint32_t want = period / R;
+                pitch += (want + period - pitch % period) % period;
+            } else {
+                pitch |= 1u;
+            }
+            const size_t tap_words = static_cast<size_t>(heads) * R * lp_pad * tap_floats;
+            const size_t smem = static_cast<size_t>(R) * pitch * elem_bytes + ((tap_words + 1) & ~size_t(1)) * 4 +
+                                static_cast<size_t>(qt) * 8;
+            // 128-thread CTAs only while at least four of them fit an SM; otherwise smaller CTAs interleave their
+            // load and FMA phases better (127 taps, R = 8: 64 threads 0.189 ms vs 128 threads 0.207 ms).
+            const size_t limit = (threads == 128 && !getenv("B200_FIR_THREADS")) ? 48 * 1024 : 100 * 1024;
+            if (smem <= limit) {
+                g.ok = true;
+                g.ob = ob;
+                g.threads = threads;
+                g.lp_pad = lp_pad;
+                g.hpad = hpad;
+                g.qt = qt;
+                g.pitch = pitch;
+                g.smem = smem;
+            }
+        }
+    }
+    return g;
 }
 
 template <int OB>
@@ -384,51 +499,16 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
     for (uint64_t i = 0; i < ntaps * heads; ++i) {
         pl->real_taps = pl->real_taps && taps_host[i].im == 0.0f;
     }
-    // Tile geometry: the largest odd OB (register sliding window) whose staged planes fit ~96 KB.
-    const uint32_t lp = (pl->L + pl->R - 1) / pl->R;
-    const int ob_options[4] = {7, 5, 3, 1};
-    uint32_t thread_options[3] = {128, 64, 32};
-    if (const char* env = getenv("B200_FIR_THREADS")) {          // A/B aid: preferred CTA size
-        const int v = atoi(env);
-        if (v == 32 || v == 64 || v == 128) {
-            thread_options[0] = static_cast<uint32_t>(v);
-        }
-    }
-    bool found = false;
-    for (int oi = 0; oi < 4 && !found; ++oi) {
-        for (int ti = 0; ti < 3 && !found; ++ti) {
-            const int ob = ob_options[oi];
-            const uint32_t threads = thread_options[ti];
-            const uint32_t lp_pad = (lp + ob - 1) / ob * ob;
-            const uint32_t hpad = lp_pad + 1;                       // rows of history incl. slack for padded taps
-            const uint32_t qt = threads * ob;
-            // A warp stages 32 consecutive samples = R planes x 32/R rows with 8-byte cp.async; the planes of one
-            // half-warp land on disjoint banks when pitch * 2 words == 32/R (mod 32), i.e. pitch == 16/R (mod 16)
-            // for R | 16; an odd pitch otherwise. (The compute phase reads one plane at a time: any pitch is fine.)
-            uint32_t pitch = qt + hpad + 1;
-            if (pl->R > 1 && 16 % pl->R == 0) {
-                const uint32_t want = 16 / pl->R;
-                pitch += (want + 16 - pitch % 16) % 16;
-            } else {
-                pitch |= 1u;
-            }
-            const size_t tap_words = static_cast<size_t>(pl->heads) * pl->R * lp_pad * (pl->real_taps ? 1 : 2);
-            const size_t smem = static_cast<size_t>(pl->R) * pitch * 8 + ((tap_words + 1) & ~size_t(1)) * 4 +
-                                static_cast<size_t>(qt) * 8;
-            // 128-thread CTAs only while at least four of them fit an SM; otherwise smaller CTAs interleave their
-            // load and FMA phases better (127 taps, R = 8: 64 threads 0.189 ms vs 128 threads 0.207 ms).
-            const size_t limit = (threads == 128 && !getenv("B200_FIR_THREADS")) ? 48 * 1024 : 100 * 1024;
-            if (smem <= limit) {
-                pl->ob = ob;
-                pl->threads = threads;
-                pl->lp_pad = lp_pad;
-                pl->hpad = hpad;
-                pl->qt = qt;
-                pl->plane_pitch = pitch;
-                pl->smem = smem;
-                found = true;
-            }
-        }
+    const FirGeometry geom = fir_geometry(pl->L, pl->R, pl->heads, pl->real_taps ? 1 : 2, 8, 7);
+    const bool found = geom.ok;
+    if (found) {
+        pl->ob = geom.ob;
+        pl->threads = geom.threads;
+        pl->lp_pad = geom.lp_pad;
+        pl->hpad = geom.hpad;
+        pl->qt = geom.qt;
+        pl->plane_pitch = geom.pitch;
+        pl->smem = geom.smem;
     }
     if (!found) {
         delete pl;
@@ -457,6 +537,40 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
     }
     pl->taps_host = host;
     pl->const_taps = host.size() <= kFirConstTapWords && getenv("B200_FIR_SMEM_TAPS") == nullptr;
+    // Chunk-pair form: chunk-taps g[c] = (h[2c], h[2c-1]), c < (L+1)/2, decimation R/2, same plane re-ordering.
+    if (pl->real_taps && pl->const_taps && pl->R % 2 == 0 && pl->L % 2 == 1) {
+        const uint32_t C = (pl->L + 1) / 2, R2 = pl->R / 2;
+        // OB = 5 for chunks (measured, 127 taps, 2^26 samples: R = 8 OB 5 / 128 threads 0.145 ms vs OB 7 / 64 threads
+        // 0.175 ms; R = 16 OB 5 / 64 threads 0.123 vs 0.128): a chunk window element already feeds two packed FMAs per
+        // output, and the smaller tile lets four 128-thread CTAs (16 warps) share an SM
+        const FirGeometry gp = fir_geometry(C, R2, pl->heads, 2, 16, 5);
+        const size_t words = static_cast<size_t>(pl->heads) * R2 * gp.lp_pad * 2;
+        if (gp.ok && words <= kFirConstTapWords) {
+            std::vector<float> pair(words, 0.0f);
+            for (uint32_t h = 0; h < pl->heads; ++h) {
+                for (uint32_t pidx = 0; pidx < R2; ++pidx) {
+                    const uint32_t kp0 = (R2 - pidx) % R2;
+                    for (uint32_t m = 0; m < gp.lp_pad; ++m) {
+                        const uint64_t c = kp0 + static_cast<uint64_t>(m) * R2;
+                        if (c < C) {
+                            const size_t idx = ((static_cast<size_t>(h) * R2 + pidx) * gp.lp_pad + m) * 2;
+                            pair[idx] = taps_host[static_cast<size_t>(h) * pl->L + 2 * c].re;                       // h[2c]
+                            pair[idx + 1] = c > 0 ? taps_host[static_cast<size_t>(h) * pl->L + 2 * c - 1].re : 0.0f;   // h[2c-1]
+                        }
+                    }
+                }
+            }
+            pl->pair_ok = true;
+            pl->pair_ob = gp.ob;
+            pl->pair_lp_pad = gp.lp_pad;
+            pl->pair_hpad = gp.hpad;
+            pl->pair_threads = gp.threads;
+            pl->pair_qt = gp.qt;
+            pl->pair_pitch = gp.pitch;
+            pl->pair_smem = gp.smem;
+            pl->pair_taps_host = pair;
+        }
+    }
     void* dev = nullptr;
     if (b200_malloc(ctx, host.size() * sizeof(float), &dev) != B200_SUCCESS) {
         delete pl;
@@ -624,17 +738,46 @@ int b200_fir_exec(b200_fir_plan* plan, const b200_cf32* x, b200_cf32* y, uint64_
         p.rot = plan->rot_dev;
         p.corr = plan->corr_dev;
     }
-    const uint64_t tiles = (p.n_out + p.qt - 1) / p.qt;
-    const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(8, (220 * 1024) / (plan->smem + 1024)));
-    const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * per_sm;
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, cap));
     const cudaStream_t s = as_stream(stream);
     int rc = B200_SUCCESS;
-    switch (plan->ob) {
-        case 7: rc = fir_launch<7>(plan, p, grid, s); break;
-        case 5: rc = fir_launch<5>(plan, p, grid, s); break;
-        case 3: rc = fir_launch<3>(plan, p, grid, s); break;
-        default: rc = fir_launch<1>(plan, p, grid, s); break;
+    const char* pair_env = getenv("B200_FIR_PAIR");
+    // measured (127 taps, 2^26 samples, chunk form vs 8-byte form): R = 16 0.123 vs 0.161 ms, R = 8 0.145 vs 0.180,
+    // R = 4 0.230 vs 0.229, R = 2 0.376 vs 0.388
+    const bool use_pair = plan->pair_ok && n_in % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                          !(pair_env && atoi(pair_env) == 0);
+    if (use_pair) {
+        // the same launch in 16-byte chunk units (see fir_decim_kernel<.., PAIR>)
+        FirParams q = p;
+        std::copy(plan->pair_taps_host.begin(), plan->pair_taps_host.end(), q.taps_c);
+        q.n_in = n_in / 2;
+        q.L = (plan->L + 1) / 2;
+        q.R = plan->R / 2;
+        q.lp_pad = plan->pair_lp_pad;
+        q.hpad = plan->pair_hpad;
+        q.qt = plan->pair_qt;
+        q.plane_pitch = plan->pair_pitch;
+        q.lp = (q.L + q.R - 1) / q.R;
+        q.lp_thr = q.L - (q.lp - 1) * q.R;
+        const uint64_t tiles = (q.n_out + q.qt - 1) / q.qt;
+        const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(8, (220 * 1024) / (plan->pair_smem + 1024)));
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(plan->ctx->sms) * per_sm));
+        switch (plan->pair_ob) {
+            case 7: rc = fir_launch_pair<7>(plan, q, grid, s); break;
+            case 5: rc = fir_launch_pair<5>(plan, q, grid, s); break;
+            case 3: rc = fir_launch_pair<3>(plan, q, grid, s); break;
+            default: rc = fir_launch_pair<1>(plan, q, grid, s); break;
+        }
+    } else {
+        const uint64_t tiles = (p.n_out + p.qt - 1) / p.qt;
+        const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(8, (220 * 1024) / (plan->smem + 1024)));
+        const uint64_t cap = static_cast<uint64_t>(plan->ctx->sms) * per_sm;
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, cap));
+        switch (plan->ob) {
+            case 7: rc = fir_launch<7>(plan, p, grid, s); break;
+            case 5: rc = fir_launch<5>(plan, p, grid, s); break;
+            case 3: rc = fir_launch<3>(plan, p, grid, s); break;
+            default: rc = fir_launch<1>(plan, p, grid, s); break;
+        }
     }
     if (rc != B200_SUCCESS) {
         return rc;

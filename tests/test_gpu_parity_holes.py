@@ -319,3 +319,37 @@ def test_fft_8192_roundtrip_and_reference(ref):
     assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
     back = _fft_c2c(got, forward=False) / 8192
     assert np.abs(back - x).max() <= 1e-5 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("taps,decimation,heads", [(127, 8, 1), (129, 8, 3), (41, 2, 1), (161, 40, 1)])
+def test_fir_chunk_pair_form_equals_the_sample_form(taps, decimation, heads, monkeypatch):
+    """fir_decim_kernel<.., PAIR> (16-byte chunks, decimation R/2, chunk-taps (h[2c], h[2c-1])) against the 8-byte form of
+    the same plan over three calls with carried history: same products, a different summation order."""
+    torch, _native, lib, ctx, dev = _env()
+    rng = np.random.default_rng(taps)
+    centers = (ctypes.c_double * heads)(*([0.0] * heads))
+    host = np.zeros((heads, taps), np.complex64)
+    _native.check(lib.b200_filter_taps_host(8e6, 8e6 / decimation / 2, centers, heads, taps, host.ctypes.data_as(ctypes.c_void_p)))
+    if heads > 1:
+        host *= rng.uniform(0.5, 1.5, (heads, 1)).astype(np.float32)
+    frames, frame_len = 6, 40 * decimation * 3
+    cycles = [(rng.standard_normal((frames, frame_len)) + 1j * rng.standard_normal((frames, frame_len))).astype(np.complex64)
+              for _ in range(3)]
+    results = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200_FIR_PAIR", mode)
+        plan = ctypes.c_void_p()
+        _native.check(lib.b200_fir_plan_create(ctx.handle, host.ctypes.data_as(ctypes.c_void_p), taps, heads, decimation,
+                                               ctypes.byref(plan)))
+        s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        outs = []
+        for x in cycles:
+            xd = torch.from_numpy(x).to(dev)
+            yd = torch.empty(frames, heads, frame_len // decimation, dtype=torch.complex64, device=dev)
+            _native.check(lib.b200_fir_exec(plan, xd.data_ptr(), yd.data_ptr(), frames, frame_len, s))
+            torch.cuda.synchronize()
+            outs.append(yd.cpu().numpy())
+        _native.check(lib.b200_fir_plan_destroy(plan))
+        results[mode] = np.stack(outs)
+    scale = np.abs(results["0"]).max()
+    assert scale > 0 and np.abs(results["1"] - results["0"]).max() <= 2e-6 * scale

@@ -142,6 +142,40 @@ def test_fir_polyphase_plane_indexing():
             assert abs(acc - want) < 1e-9
 
 
+def test_fir_chunk_pair_form():
+    """fir_decim_kernel<.., PAIR>: the same plane algebra on 16-byte chunks (x[2n], x[2n+1]) with decimation R / 2 and
+    chunk-taps g[c] = (h[2c], h[2c-1]): y[q] = sum_c h[2c] x[qR - 2c] + h[2c-1] x[qR - 2c + 1]."""
+    rng = np.random.default_rng(6)
+    for (L, R, qt, ob) in [(127, 8, 21, 7), (129, 8, 14, 7), (33, 4, 10, 5), (41, 40, 6, 1), (7, 2, 9, 3), (161, 40, 7, 7)]:
+        C, R2 = (L + 1) // 2, R // 2
+        lp = -(-C // R2)
+        lp_pad = -(-lp // ob) * ob
+        hpad = lp_pad + 1
+        h = rng.standard_normal(L)
+        g = np.zeros((C, 2))
+        for c in range(C):
+            g[c, 0] = h[2 * c]
+            g[c, 1] = h[2 * c - 1] if c > 0 else 0.0
+        xs = rng.standard_normal((qt + hpad) * R)            # stream; tile starts at q0 R = hpad R
+        chunks = xs.reshape(-1, 2)                           # chunk n = (x[2n], x[2n+1])
+        span = (qt - 1) * R2 + hpad * R2 + 1
+        planes = np.zeros((R2, qt + hpad + 1, 2))
+        for i in range(span):
+            planes[i % R2, i // R2] = chunks[i]
+        for o in range(qt):
+            acc = 0.0
+            for plane in range(R2):
+                kp0 = (R2 - plane) % R2
+                d = hpad if plane == 0 else hpad - 1
+                for m in range(lp_pad):
+                    c = kp0 + m * R2
+                    if c < C:
+                        v = planes[plane, o + d - m]
+                        acc += g[c, 0] * v[0] + g[c, 1] * v[1]
+            want = sum(h[k] * xs[(o + hpad) * R - k] for k in range(L))
+            assert abs(acc - want) < 1e-9, (L, R, o)
+
+
 def _radices(log2n):
     rem, out = 1 << log2n, []
     while rem > 1:
