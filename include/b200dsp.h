@@ -123,7 +123,9 @@ int b200_multiply_constant_f32(b200_ctx* ctx, const float* in, float* out, uint6
 /* fft — src/domains/dsp/fft/module_impl_native_cpu.cc:129-140 (pocketfft::c2c, scale 1.0 in both
  * directions, forward sign exp(-j2*pi*kn/N)). Batched 1-D C2C over the last (contiguous) axis:
  * in/out [batch, n] CF32; in == out allowed. Any n >= 1: powers of two up to 8192 run the single-pass TMA-staged
- * register-radix kernel; larger powers of two a four-step plan (transposes + two batched sub-transforms); every
+ * register-radix kernel; 16384 / 32768 / 65536 a tiled two-pass plan (column tiles by 2-D TMA + 256-point rows with
+ * 128-byte transposed runs over an L2-resident scratch), 131072 a radix-16 column pass + 8192-point rows, larger powers
+ * of two a four-step plan (transposes + two batched sub-transforms); every
  * other length Bluestein's chirp-z through a power-of-two convolution (pocketfft does the same for large primes). Replaces cufftMakePlanMany64 + cufftExecC2C of
  * src/domains/dsp/fft/module_impl_native_cuda.cc:321-333,433. */
 int b200_fft_plan_c2c(b200_ctx* ctx, uint64_t n, uint64_t batch, b200_fft_plan** plan);
@@ -217,9 +219,11 @@ int b200_cast_int(b200_ctx* ctx, const void* in, int in_dtype, void* out, uint64
  * produce (already sign-flipped); it is captured at plan creation (static, settled output).
  *   x   : [batch, n] CF32 contiguous, 16-byte aligned       out : [batch, n] F32
  *   amp_coeff = 20*log10f(1/n); enable_range != 0 applies range(scale, offset).
- * Powers of two 2 <= n <= 16384 run ONE fused kernel (n == 4096: fft4096_kernel; 16..8192: fft_radix_kernel;
- * 2..8, 16384: fft_generic_kernel). Any other length runs the module sequence multiply -> fft -> amplitude ->
- * range through a plan-owned scratch (exec must then use batch == max_batch). */
+ * Powers of two 2 <= n <= 8192 run ONE fused kernel (n == 4096: fft4096_kernel; 16..8192: fft_radix_kernel;
+ * 2..8: fft_generic_kernel); n = 16384 / 32768 / 65536 run TWO fused kernels over the tiled two-pass plan (window in the
+ * column pass, amplitude / range in the row pass; any batch <= or > max_batch, processed in 64 MB chunks). Any other
+ * length runs the module sequence multiply -> fft -> amplitude -> range through a plan-owned scratch (exec must then
+ * use batch == max_batch). */
 int b200_chain_plan_create(b200_ctx* ctx, uint64_t n, uint64_t max_batch, const b200_cf32* window_dev,
                            b200_chain_plan** plan);
 int b200_chain_exec(b200_chain_plan* plan, const b200_cf32* x, float* out, uint64_t batch,

@@ -1,7 +1,7 @@
 """SASS opcode histogram of the hot kernels in cyberether_b200/libb200dsp.so (cuobjdump -sass, no GPU needed):
 per kernel the counts of the opcodes the design notes argue with — TMA bulk copies (UBLKCP), mbarrier (SYNCS), packed
-FP32 (FFMA2 / FADD2 / FMUL2), MUFU, shared-memory traffic, barriers — and the absence of tensor-core / tensor-map opcodes
-(UTCMMA / UTMALDG / LDTM), which this path has no use for. Usage: python tools/sass_histogram.py > profiles/rNN_sass_histogram.txt"""
+FP32 (FFMA2 / FADD2 / FMUL2), MUFU, shared-memory traffic, barriers, 2-D tensor-map TMA (UTMALDG: the column tiles of the
+tiled two-pass FFT) — and the absence of tensor-core opcodes (UTCMMA / LDTM), which this path has no use for. Usage: python tools/sass_histogram.py > profiles/rNN_sass_histogram.txt"""
 import collections
 import os
 import re
@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cyberether_b200", "libb200dsp.so")
-HOT = ("fft4096_kernel", "fft_radix_kernel", "fir_decim_kernel", "fm_narrow_fused_kernel", "scan_tile_kernel",
+HOT = ("fft4096_kernel", "fft_radix_kernel", "fft_cols_kernel", "fft_rows256_kernel", "fft_col16_kernel", "fir_decim_kernel", "fm_narrow_fused_kernel", "scan_tile_kernel",
        "scan_replay_kernel", "scan_tiles_kernel", "fm_wide_phase_table_kernel", "colsum_partial_kernel",
        "lineplot_finalize_kernel", "waterfall_write_kernel")
 WATCH = ("UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "MUFU", "LDS", "STS", "LDG", "STG", "LDGSTS",
