@@ -353,3 +353,39 @@ def test_fir_chunk_pair_form_equals_the_sample_form(taps, decimation, heads, mon
         results[mode] = np.stack(outs)
     scale = np.abs(results["0"]).max()
     assert scale > 0 and np.abs(results["1"] - results["0"]).max() <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("n", [8, 12, 4096, 8192, 65536, 6 * 1000])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_fft_exec_real_half_length_path(ref, n, layout):
+    """b200_fft_exec_real: real rows of even length 2h through one h-point complex transform on the row itself + the mirror-pair
+    unpack kernel; layout 0 = pocketfft::r2c ([h + 1] CF32), layout 1 = FFTPACK half-complex ([2h] F32). h even, odd (n = 12:
+    h = 6; 6000: h = 3000 -> Bluestein) and tiled (65536: h = 32768)."""
+    torch, _native, lib, ctx, dev = _env()
+    rng = np.random.default_rng(n + layout)
+    batch = 5
+    x = rng.standard_normal((batch, n)).astype(np.float32)
+    plan = ctypes.c_void_p()
+    _native.check(lib.b200_fft_plan_c2c(ctx.handle, n // 2, batch, ctypes.byref(plan)))
+    xd = torch.from_numpy(x).to(dev)
+    out = torch.empty((batch, n // 2 + 1), dtype=torch.complex64, device=dev) if layout == 0 else \
+        torch.empty((batch, n), dtype=torch.float32, device=dev)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):          # the second call reuses the plan-owned work buffer
+        _native.check(lib.b200_fft_exec_real(plan, xd.data_ptr(), out.data_ptr(), layout, s))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    spec = np.fft.rfft(x.astype(np.float64), axis=1)
+    if layout == 0:
+        want = spec
+    else:
+        want = np.empty((batch, n))
+        want[:, 0] = spec[:, 0].real
+        want[:, 1:n - 1:2] = spec[:, 1:n // 2].real
+        want[:, 2:n - 1:2] = spec[:, 1:n // 2].imag
+        want[:, n - 1] = spec[:, n // 2].real
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(spec).max()
+    # an input that is only 4-byte aligned is refused (the caller falls back to the composed path)
+    base = torch.zeros(batch * n + 1, dtype=torch.float32, device=dev)
+    assert lib.b200_fft_exec_real(plan, base[1:].data_ptr(), out.data_ptr(), layout, s) != 0
+    _native.check(lib.b200_fft_plan_destroy(plan))
