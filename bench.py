@@ -27,6 +27,7 @@ from __future__ import annotations
 import argparse
 import ctypes
 import json
+import math
 import os
 import sys
 import threading
@@ -566,6 +567,63 @@ def bench_fir(env, steps, warmup, with_cpu=False):
     return out
 
 
+# ---- the reference's own fft module benchmark cases (src/domains/dsp/fft/module_benchmarks.cc:7-50) ----------------------
+
+def bench_fft(env, steps, warmup):
+    """CF32-8192, CF32-65536 (C2C) and F32-8192, F32-65536 (real input, `complexOutput`) as batches of 2^26 samples, plus the
+    fused spectral chain at n = 65536: b200_fft_exec / b200_fft_exec_real / b200_chain_exec, device-resident. Algorithmic
+    bytes: 16 per complex sample (C2C), 8 per real sample (R2C: 4 in + 4 out), 12 per sample (chain)."""
+    torch, lib = env.torch, env.lib
+    total = 1 << 26
+    g = torch.Generator(device=env.dev)
+    g.manual_seed(55 + env.rank)
+    x = torch.view_as_complex(torch.randn(total, 2, device=env.dev, generator=g)).contiguous()
+    y = torch.empty_like(x)
+    xr = torch.view_as_real(x).reshape(-1)
+    cases, launches = {}, 0
+
+    def record(name, ms, samples, bytes_per_sample, kernel):
+        achieved = samples * bytes_per_sample / (ms * 1e-3) / 1e9
+        cases[name] = {"value": samples * env.world / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
+                       "roofline": {"bound": "hbm", "achieved": achieved, "peak": env.peak, "unit": "GB/s",
+                                    "frac": achieved / env.peak, "algorithmic_bytes_per_launch": samples * bytes_per_sample,
+                                    "kernel": kernel}}
+    for n, kernel in ((8192, "fft_radix_kernel<13>"), (65536, "fft_cols_kernel<8> + fft_rows256_kernel (tiled two-pass, L2-resident scratch)")):
+        rows = total // n
+        plan = ctypes.c_void_p()
+        env.check(lib.b200_fft_plan_c2c(env.ctx.handle, n, rows, ctypes.byref(plan)))
+        ms, ms_max, _, _ = env.timed(lambda: env.check(lib.b200_fft_exec(plan, x.data_ptr(), y.data_ptr(), 1, env.sp)), steps, warmup)
+        record(f"CF32-{n}", ms_max, total, 16, kernel)
+        env.check(lib.b200_fft_plan_destroy(plan))
+        launches += steps
+        rrows = xr.numel() // n
+        half = ctypes.c_void_p()
+        env.check(lib.b200_fft_plan_c2c(env.ctx.handle, n // 2, rrows, ctypes.byref(half)))
+        out = torch.empty(rrows, n // 2 + 1, dtype=torch.complex64, device=env.dev)
+        ms, ms_max, _, _ = env.timed(lambda: env.check(lib.b200_fft_exec_real(half, xr.data_ptr(), out.data_ptr(), 0, env.sp)), steps, warmup)
+        record(f"F32-{n}", ms_max, xr.numel(), 8, "half-length c2c + rfft_unpack_kernel")
+        env.check(lib.b200_fft_plan_destroy(half))
+        del out
+        launches += 2 * steps
+    n = 65536
+    rows = total // n
+    win = torch.zeros(n, dtype=torch.complex64, device=env.dev)
+    win.real = torch.rand(n, device=env.dev, generator=g)
+    torch.cuda.synchronize()
+    cplan = ctypes.c_void_p()
+    env.check(lib.b200_chain_plan_create(env.ctx.handle, n, rows, win.data_ptr(), ctypes.byref(cplan)))
+    f = torch.empty(rows, n, dtype=torch.float32, device=env.dev)
+    coeff = float(20.0 * math.log10(1.0 / n))
+    ms, ms_max, _, _ = env.timed(lambda: env.check(lib.b200_chain_exec(cplan, x.data_ptr(), f.data_ptr(), rows, ctypes.c_float(coeff), 1,
+                                                                      ctypes.c_float(1.0 / 120.0), ctypes.c_float(1.0), env.sp)), steps, warmup)
+    record("chain-65536", ms_max, total, 12, "fft_cols_kernel<8, window> + fft_rows256_kernel<amplitude, range>")
+    env.check(lib.b200_chain_plan_destroy(cplan))
+    launches += 2 * steps
+    return {"metric": "CF32 / F32 Msamples/sec through the fft module (the reference's module_benchmarks cases) and the fused chain at n = 65536",
+            "unit": UNIT, "steps": steps, "gpu_launches": launches, "cases": cases,
+            "config": {"workload": "2^26 samples per step as [2^26 / n, n] batches", "l2": "inputs larger than L2 (512 MiB per step)"}}
+
+
 # ---- BASELINE configs[3]: FM-broadcast flowgraph at 10 MS/s ---------------------------------------------
 
 def bench_fm(env, steps, warmup, with_cpu=False):
@@ -796,6 +854,7 @@ def main_chain(env, args):
         if world == 1:
             workloads["fir"] = guarded(bench_fir, env, 50, 5)
             workloads["fm"] = guarded(bench_fm, env, 50, 5)
+            workloads["fft"] = guarded(bench_fft, env, 20, 3)
         for w in workloads.values():
             if isinstance(w, dict):
                 launches += int(w.get("gpu_launches", 0) or 0)
