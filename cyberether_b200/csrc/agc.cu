@@ -11,8 +11,10 @@
 // Three launches: tile gains (one CTA per tile, 8 B/sample read), the sequential per-lane rate-limit chain (one thread
 // per lane, tiles steps), apply (8 B/sample read + 8 written for CF32). HBM-bound; algorithmic bytes 16 (CF32) /
 // 8 (F32) per sample, moved 24 / 12 because the input is read twice.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -171,6 +173,102 @@ __global__ void __launch_bounds__(256) agc_apply_kernel(const T* __restrict__ in
     }
 }
 
+// ---- fused form: one CTA per lane, the tile's samples stay in registers between the power sum and the apply ------------
+// Every sample is read once and written once (16 B per CF32 sample instead of 24). A CTA walks the tiles of its lane in
+// order: tile t is applied with the gain running from `start` to the rate-limited target of tile t + 1, so tile t + 1 is
+// loaded and summed (registers `nxt`) before tile t (registers `cur`) is written. Tiles of up to 256 x K samples, lanes >=
+// the number of CTAs the GPU holds (otherwise the three-kernel form above has more parallelism).
+constexpr int kAgcFusedThreads = 256;
+constexpr int kAgcFusedPerThread = 16;
+
+template <typename T>
+__device__ __forceinline__ double agc_block_sum(double sum, double* partial) {
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1) {
+        sum = __dadd_rn(sum, __shfl_down_sync(0xffffffffu, sum, offset));
+    }
+    __syncthreads();                           // partial[] of the previous reduction has been consumed
+    if ((threadIdx.x & 31) == 0) {
+        partial[threadIdx.x >> 5] = sum;
+    }
+    __syncthreads();
+    double total = partial[0];
+#pragma unroll
+    for (int w = 1; w < kAgcFusedThreads / 32; ++w) {
+        total = __dadd_rn(total, partial[w]);
+    }
+    return total;                              // every thread holds the same value
+}
+
+// SINGLE: one tile per lane (the spectrum_engine use, and the benchmarked [16384, 4096] / tile 4096 case): no look-ahead
+// tile, half the registers.
+template <typename T, int K, bool SINGLE>
+__global__ void __launch_bounds__(kAgcFusedThreads) agc_fused_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                     const AgcParams p) {
+    __shared__ double partial[kAgcFusedThreads / 32];
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t lane = blockIdx.x; lane < p.lanes; lane += gridDim.x) {
+        const T* const src = in + lane * p.samples;
+        T* const dst = out + lane * p.samples;
+        auto tile_length = [&](const uint64_t tile) {
+            const uint64_t start = tile * p.tile;
+            return p.samples - start < p.tile ? p.samples - start : p.tile;
+        };
+        auto load_tile = [&](const uint64_t tile, T (&v)[K]) {
+            const uint64_t length = tile_length(tile);
+            const T* const s = src + tile * p.tile;
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < K; ++u) {
+                const uint64_t idx = tid + static_cast<uint64_t>(u) * kAgcFusedThreads;
+                if (idx < length) {
+                    v[u] = s[idx];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < K; ++u) {
+                const uint64_t idx = tid + static_cast<uint64_t>(u) * kAgcFusedThreads;
+                if (idx < length) {
+                    acc = __dadd_rn(acc, sample_power(v[u]));
+                }
+            }
+            const double total_power = agc_block_sum<T>(acc, partial);
+            const double mean = __ddiv_rn(total_power, static_cast<double>(length));
+            return clamp_like_std(__ddiv_rn(p.reference, __dsqrt_rn(__dadd_rn(mean, p.epsilon))), p.min_gain, p.max_gain);
+        };
+        T cur[K], nxt[SINGLE ? 1 : K];
+        double start = load_tile(0, cur);
+        for (uint64_t tile = 0; tile < (SINGLE ? 1 : p.tiles); ++tile) {
+            double end = start;
+            if constexpr (!SINGLE) if (tile + 1 < p.tiles) {
+                const double target = load_tile(tile + 1, nxt);
+                const double lowest = max_like_std(p.min_gain, __ddiv_rn(start, p.max_change));
+                const double highest = start > __ddiv_rn(p.max_gain, p.max_change) ? p.max_gain
+                                                                                   : __dmul_rn(start, p.max_change);
+                end = clamp_like_std(target, lowest, highest);
+            }
+            const uint64_t length = tile_length(tile);
+            const double step = __ddiv_rn(__dsub_rn(end, start), static_cast<double>(length));
+            T* const d = dst + tile * p.tile;
+#pragma unroll
+            for (int u = 0; u < K; ++u) {
+                const uint64_t idx = tid + static_cast<uint64_t>(u) * kAgcFusedThreads;
+                if (idx < length) {
+                    const double gain = __dadd_rn(start, __dmul_rn(step, static_cast<double>(idx)));
+                    d[idx] = apply_gain(cur[u], gain);
+                }
+            }
+            if constexpr (!SINGLE) if (tile + 1 < p.tiles) {
+#pragma unroll
+                for (int u = 0; u < K; ++u) {
+                    cur[u] = nxt[u];
+                }
+            }
+            start = end;
+        }
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -218,6 +316,31 @@ int b200_agc(b200_ctx* ctx, const void* in, void* out, int is_complex, uint64_t 
     const uint64_t items = lanes * p.tiles;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(items, static_cast<uint64_t>(ctx->sms) * 8));
     const cudaStream_t s = as_stream(stream);
+    // Fused form (every sample read once): tiles that fit the registers of one CTA and at least one lane per resident CTA.
+    const char* fused_env = getenv("B200_AGC_FUSED");
+    // Measured on [16384, 4096] CF32: tile 1024 (4 samples per thread, 4 CTAs/SM) 0.358 -> 0.303 ms; tile 4096 (16 per
+    // thread: 80 registers alone, 122 with a look-ahead tile) 0.284 -> 0.318 ms, so long tiles keep the three-kernel form
+    // (B200_AGC_FUSED=1 forces the fused form up to 16 samples per thread, =0 disables it).
+    const uint64_t per_thread = (std::min(tile_size, samples) + kAgcFusedThreads - 1) / kAgcFusedThreads;
+    const uint64_t fused_limit = fused_env ? (atoi(fused_env) != 0 ? kAgcFusedPerThread : 0) : 4;
+    if (per_thread <= fused_limit && lanes >= static_cast<uint64_t>(ctx->sms) * 2) {
+        const unsigned fgrid = static_cast<unsigned>(std::min<uint64_t>(lanes, static_cast<uint64_t>(ctx->sms) * 4));
+        const int k = static_cast<int>((std::min(tile_size, samples) + kAgcFusedThreads - 1) / kAgcFusedThreads);
+#define B200_AGC_FUSED(T, K)                                                                                              \
+    if (p.tiles == 1) {                                                                                                   \
+        agc_fused_kernel<T, K, true><<<fgrid, kAgcFusedThreads, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), p);  \
+    } else {                                                                                                              \
+        agc_fused_kernel<T, K, false><<<fgrid, kAgcFusedThreads, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), p); \
+    }
+        if (is_complex) {
+            if (k <= 4) { B200_AGC_FUSED(float2, 4); } else if (k <= 8) { B200_AGC_FUSED(float2, 8); } else { B200_AGC_FUSED(float2, 16); }
+        } else {
+            if (k <= 4) { B200_AGC_FUSED(float, 4); } else if (k <= 8) { B200_AGC_FUSED(float, 8); } else { B200_AGC_FUSED(float, 16); }
+        }
+#undef B200_AGC_FUSED
+        B200_LAUNCH_CHECK();
+        return B200_SUCCESS;
+    }
     if (is_complex) {
         agc_tile_gain_kernel<float2><<<grid, 256, 0, s>>>(static_cast<const float2*>(in), target, p);
     } else {

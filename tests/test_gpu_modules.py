@@ -1,6 +1,8 @@
 """GPU parity of the standalone modules (one C-ABI call each, through the host mirror's TestContext) against
 the reference CPU modules (oracle/_ref), plus the reference's own known-answer cases restated
 (src/domains/**/module_tests.cc)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -455,3 +457,37 @@ def test_cast_rejects_invalid_output_spelling(spelling):
     ctx.set_config(outputType=spelling)
     assert ctx.run() == cb.Result.ERROR
     assert "Invalid output type" in cb.last_error()
+
+
+@pytest.mark.parametrize("complex_input", [True, False])
+@pytest.mark.parametrize("lanes,samples,tile", [(600, 3000, 1024), (400, 4096, 4096), (320, 777, 256), (512, 2048, 2048)])
+def test_agc_fused_one_cta_per_lane_form(ref, complex_input, lanes, samples, tile):
+    """agc_fused_kernel (enough lanes to fill the GPU, tiles that fit one CTA's registers): every sample read once, the
+    tile kept in registers between its power sum and its apply. Against the numpy restatement of the reference and the
+    three-kernel form; a level jump per lane exercises the rate limit, the last tile is ragged."""
+    import cyberether_b200 as cb
+    from oracle import port
+    rng = np.random.default_rng(lanes + samples + tile)
+    step = 1 + 7 * (np.arange(samples) > samples // 2)[None, :]
+    env = np.exp(rng.uniform(-6, 6, size=(lanes, 1))) * step
+    x = rng.standard_normal((lanes, samples)) * env
+    x = (x + 1j * rng.standard_normal((lanes, samples)) * env).astype(np.complex64) if complex_input else x.astype(np.float32)
+
+    def run():
+        ctx = cb.TestContext("agc")
+        ctx.set_input("signal", x, sampleAxis=1, batchAxis=0)
+        ctx.set_config(tileSize=tile)
+        assert ctx.run() == cb.Result.SUCCESS, cb.last_error()
+        return ctx.output("signal")
+    results = {}
+    for mode in ("1", "0"):              # 1: fused form up to 16 samples per thread, 0: three kernels
+        os.environ["B200_AGC_FUSED"] = mode
+        try:
+            results[mode] = run()
+        finally:
+            del os.environ["B200_AGC_FUSED"]
+    fused, three = results["1"], results["0"]
+    want = port.agc(x, tile_size=tile, axis=1)
+    _assert_agc_equal(fused, want)
+    _assert_agc_equal(three, want)
+    _assert_agc_equal(fused, three)

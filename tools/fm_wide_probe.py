@@ -6,7 +6,7 @@ from cyberether_b200 import _native
 from cyberether_b200.jetstream import Context
 lib = _native.load(); dev = torch.device("cuda:0"); ctx = Context.get(dev)
 sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-frames, lanes, fl = 64, 1, 8192
+frames, lanes, fl = (int(sys.argv[1]) if len(sys.argv) > 1 else 64), (int(sys.argv[2]) if len(sys.argv) > 2 else 1), 8192
 x = torch.view_as_complex(torch.randn(frames, lanes, fl, 2, device=dev))
 out = torch.empty(frames, lanes, fl, 2, dtype=torch.float32, device=dev)
 plan = ctypes.c_void_p()
@@ -15,4 +15,4 @@ for _ in range(2): _native.check(lib.b200_fm_exec(plan, x.data_ptr(), out.data_p
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); _native.check(lib.b200_fm_exec(plan, x.data_ptr(), out.data_ptr(), frames, fl, sp)); e1.record(); torch.cuda.synchronize()
-print(f"fm wide 2^19 samples: {e0.elapsed_time(e1):.3f} ms")
+ms = e0.elapsed_time(e1); print(f"fm wide {frames*lanes*fl} samples ({frames} frames x {lanes} lanes): {ms:.3f} ms {frames*lanes*fl/ms*1e-6:.2f} GS/s")
