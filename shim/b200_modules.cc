@@ -137,20 +137,37 @@ struct MultiplyImplB200 : public MultiplyImpl, public NativeCudaRuntimeContext, 
 JST_REGISTER_MODULE(MultiplyImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
 
 // ---- fft ----------------------------------------------------------------------------------------------
+// CF32 -> CF32 (either direction) through b200_fft_exec; F32 input, forward (pocketfft::r2c with `complexOutput`, else
+// r2r_fftpack: src/domains/dsp/fft/module_impl_native_cpu.cc:142-167) through b200_fft_exec_real — one complex transform of
+// half the length on the real row itself plus the unpack kernel.
 struct FftImplB200 : public FftImpl, public NativeCudaRuntimeContext, public Scheduler::Context {
     Result create() final {
         JST_CHECK(FftImpl::create());
-        if (input.dtype() != DataType::CF32 || !input.contiguous() || resolvedAxis + 1 != input.rank()) {
-            JST_ERROR("[MODULE_FFT_B200] This provider implements contiguous CF32 transforms along the innermost axis.");
+        if (!input.contiguous() || resolvedAxis + 1 != input.rank()) {
+            JST_ERROR("[MODULE_FFT_B200] This provider implements contiguous transforms along the innermost axis.");
+            return Result::ERROR;
+        }
+        const U64 n = input.shape(resolvedAxis);
+        realInput = input.dtype() == DataType::F32;
+        if (input.dtype() != DataType::CF32 && !realInput) {
+            JST_ERROR("[MODULE_FFT_B200] Unsupported input data type.");
+            return Result::ERROR;
+        }
+        if (realInput && (!forward || n < 4 || n % 2 != 0)) {
+            JST_ERROR("[MODULE_FFT_B200] Real input: this provider implements the forward transform of even lengths >= 4.");
             return Result::ERROR;
         }
         return Result::SUCCESS;
     }
     Result computeInitialize() override {
         const U64 n = input.shape(resolvedAxis);
-        return Check(b200_fft_plan_c2c(B200Ctx(), n, input.size() / n, &plan), "FFT");
+        return Check(b200_fft_plan_c2c(B200Ctx(), realInput ? n / 2 : n, input.size() / n, &plan), "FFT");
     }
     Result computeSubmit(const cudaStream_t& stream) override {
+        if (realInput) {
+            return Check(b200_fft_exec_real(plan, DevicePtr<float>(input), DevicePtr<void>(output), complexOutput ? 0 : 1, stream),
+                         "FFT");
+        }
         return Check(b200_fft_exec(plan, DevicePtr<b200_cf32>(input), DevicePtr<b200_cf32>(output), forward ? 1 : 0,
                                    stream), "FFT");
     }
@@ -160,6 +177,7 @@ struct FftImplB200 : public FftImpl, public NativeCudaRuntimeContext, public Sch
         return result;
     }
     b200_fft_plan* plan = nullptr;
+    bool realInput = false;
 };
 JST_REGISTER_MODULE(FftImplB200, DeviceType::CUDA, RuntimeType::NATIVE, "b200");
 

@@ -214,6 +214,27 @@ def test_unfused_modules_still_reachable(sb):
     assert np.abs(got[1] - want[1]).max() <= 1e-3
 
 
+@pytest.mark.parametrize("n", [1024, 8192, 65536])
+@pytest.mark.parametrize("complex_output", [True, False])
+def test_real_input_fft_block_on_provider_b200(sb, n, complex_output):
+    """The reference's F32 `fft` cases (module_benchmarks.cc: F32-8192 / F32-65536): forward transform of real rows,
+    pocketfft::r2c (`complexOutput`) or FFTPACK half-complex, in the reference's own Flowgraph on the CPU provider and on
+    provider b200 (b200_fft_exec_real: one half-length complex transform + unpack)."""
+    rng = np.random.default_rng(n + int(complex_output))
+    x = rng.standard_normal((3, n)).astype(np.float32)
+    outs = {}
+    for target in (sb.CPU, sb.B200):
+        with sb.Session() as s:
+            s.add_source("src", x.shape, "F32", target=target, sampleAxis=1, batchAxis=0)
+            s.add_block("f", "fft", {"forward": True, "complexOutput": complex_output}, {"signal": "src.signal"}, target=target)
+            s.write_source("src", x)
+            s.compute()
+            outs[target[1]] = s.read("f", "signal")
+    want, got = outs["generic"], outs["b200"]
+    assert got.shape == want.shape == ((3, n // 2 + 1) if complex_output else (3, n)) and got.dtype == want.dtype
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
 @pytest.mark.parametrize("rows,decimation", [(48, 1), (700, 2)])
 def test_spectrum_analyzer_flowgraph_with_consumers(sb, rows, decimation):
     """examples/flowgraphs/spectrum-analyzer.yml in small: source -> spectrum_engine -> lineplot + waterfall, every
