@@ -109,6 +109,21 @@ def test_spectrum_engine_block_f32_input_and_reconfigure(sb):
     assert results["b200"][2]["runtime:spectral_chain"][0] == 2          # same module instance computed both cycles
 
 
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_spectrum_engine_block_large_spectra_run_the_tiled_chain(sb, n):
+    """n = 16384 / 65536 in the reference's own Flowgraph: on provider b200 the block still creates ONE spectral_chain
+    module, which runs the two fused kernels of the tiled two-pass plan (window in the column pass, amplitude / range in
+    the row pass)."""
+    from cyberether_b200.synthetic import spectral_rows
+    cycles = [spectral_rows(5 * k, 3, n=n) for k in range(2)]
+    cpu, gpu, mods, cpu_mods, _ = _both(sb, "spectrum_engine", {"enableScale": True, "rangeMin": -100.0, "rangeMax": -10.0},
+                                        "buffer", "buffer", cycles, {"sampleAxis": 1, "batchAxis": 0})
+    assert "runtime:spectral_chain" in mods and "runtime:fft" not in mods and "runtime:fft" in cpu_mods
+    w = _window(n)
+    for x, want, got in zip(cycles, cpu, gpu):
+        assert_db_close(got, want, true_spectrum(x, w), scale=2.0 / 90.0, floor=3e-7)
+
+
 def test_spectrum_engine_block_other_length_uses_reference_wiring_for_agc(sb):
     """enableAgc with n != 4096: the block takes the reference wiring on this provider's per-module kernels."""
     from cyberether_b200.synthetic import spectral_rows
