@@ -52,7 +52,7 @@ struct FirParams {
     float taps_c[kFirConstTapWords];
 };
 
-// PAIR (real taps, even R, odd L, even stream length, 16-byte aligned stream): the same algorithm on 16-byte CHUNKS
+// PAIR (even R, odd L, even stream length, 16-byte aligned stream; real or complex taps): the same algorithm on 16-byte CHUNKS
 // c[n] = (x[2n], x[2n+1]) with decimation R / 2 and chunk-taps g[c] = (h[2c], h[2c-1]):
 //        y[q] = sum_c  h[2c] * x[qR - 2c]  +  h[2c-1] * x[qR - 2c + 1]  =  sum_c g[c] . chunk[q R/2 - c],
 // i.e. every p.* field below is in chunk units (p.R = R/2, p.L = (L+1)/2, p.n_in = n_in/2). One LDGSTS.128 stages two
@@ -76,10 +76,9 @@ __device__ __forceinline__ void cp_async_elem_fill(const uint32_t dst, const voi
 
 template <int OB, bool REAL_TAPS, bool CONST_TAPS, bool PAIR = false>
 __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ FirParams p) {
-    static_assert(!PAIR || REAL_TAPS, "chunk pairs exist for real taps");
     using E = typename std::conditional<PAIR, float4, float2>::type;     // staged element
     constexpr uint32_t EB = sizeof(E);
-    constexpr int TW = PAIR ? 2 : (REAL_TAPS ? 1 : 2);                   // floats per tap slot
+    constexpr int TW = (PAIR ? 2 : 1) * (REAL_TAPS ? 1 : 2);             // floats per tap slot
     extern __shared__ __align__(16) unsigned char smem_raw[];
     E* const planes = reinterpret_cast<E*>(smem_raw);
     const E* const xsrc = reinterpret_cast<const E*>(p.x);
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ 
                 const uint32_t full = lp_plane / OB * OB;
                 auto tap_step = [&](const int s) {
                     // logical window element i lives in w[(i - s) mod OB]
-                    if constexpr (PAIR) {
+                    if constexpr (PAIR && REAL_TAPS) {
                         const float ha = CONST_TAPS ? p.taps_c[hc + 2 * s] : hq[2 * s];
                         const float hb = CONST_TAPS ? p.taps_c[hc + 2 * s + 1] : hq[2 * s + 1];
                         const float2 ga = make_float2(ha, ha), gb = make_float2(hb, hb);
@@ -210,6 +209,22 @@ __global__ void __launch_bounds__(128) fir_decim_kernel(const __grid_constant__ 
                             const float4 v = w[(i - s + OB) % OB];
                             acc[i] = __ffma2_rn(make_float2(v.x, v.y), ga, acc[i]);
                             acc[i] = __ffma2_rn(make_float2(v.z, v.w), gb, acc[i]);
+                        }
+                    } else if constexpr (PAIR) {
+                        // complex chunk-taps (frequency-translating heads): (h[2c], h[2c-1]) as four floats
+                        const float ar = CONST_TAPS ? p.taps_c[hc + 4 * s] : hq[4 * s];
+                        const float ai = CONST_TAPS ? p.taps_c[hc + 4 * s + 1] : hq[4 * s + 1];
+                        const float br = CONST_TAPS ? p.taps_c[hc + 4 * s + 2] : hq[4 * s + 2];
+                        const float bi = CONST_TAPS ? p.taps_c[hc + 4 * s + 3] : hq[4 * s + 3];
+                        const float2 gar = make_float2(ar, ar), gai = make_float2(-ai, ai);
+                        const float2 gbr = make_float2(br, br), gbi = make_float2(-bi, bi);
+#pragma unroll
+                        for (int i = 0; i < OB; ++i) {
+                            const float4 v = w[(i - s + OB) % OB];
+                            acc[i] = __ffma2_rn(make_float2(v.x, v.y), gar, acc[i]);
+                            acc[i] = __ffma2_rn(make_float2(v.y, v.x), gai, acc[i]);
+                            acc[i] = __ffma2_rn(make_float2(v.z, v.w), gbr, acc[i]);
+                            acc[i] = __ffma2_rn(make_float2(v.w, v.z), gbi, acc[i]);
                         }
                     } else if constexpr (REAL_TAPS) {
                         const float h = CONST_TAPS ? p.taps_c[hc + s] : hq[s];
@@ -359,7 +374,7 @@ static int fir_launch_variant(b200_fir_plan* pl, const FirParams& p, unsigned gr
 
 template <int OB>
 static int fir_launch_pair(b200_fir_plan* pl, const FirParams& p, unsigned grid, cudaStream_t s) {
-    auto k = fir_decim_kernel<OB, true, true, true>;
+    void (*k)(FirParams) = pl->real_taps ? fir_decim_kernel<OB, true, true, true> : fir_decim_kernel<OB, false, true, true>;
     B200_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl->pair_smem)));
     k<<<grid, pl->pair_threads, pl->pair_smem, s>>>(p);
     B200_LAUNCH_CHECK();
@@ -538,13 +553,14 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
     pl->taps_host = host;
     pl->const_taps = host.size() <= kFirConstTapWords && getenv("B200_FIR_SMEM_TAPS") == nullptr;
     // Chunk-pair form: chunk-taps g[c] = (h[2c], h[2c-1]), c < (L+1)/2, decimation R/2, same plane re-ordering.
-    if (pl->real_taps && pl->const_taps && pl->R % 2 == 0 && pl->L % 2 == 1) {
+    if (pl->const_taps && pl->R % 2 == 0 && pl->L % 2 == 1) {
         const uint32_t C = (pl->L + 1) / 2, R2 = pl->R / 2;
+        const uint32_t tf = pl->real_taps ? 2 : 4;          // floats per chunk-tap
         // OB = 5 for chunks (measured, 127 taps, 2^26 samples: R = 8 OB 5 / 128 threads 0.145 ms vs OB 7 / 64 threads
         // 0.175 ms; R = 16 OB 5 / 64 threads 0.123 vs 0.128): a chunk window element already feeds two packed FMAs per
         // output, and the smaller tile lets four 128-thread CTAs (16 warps) share an SM
-        const FirGeometry gp = fir_geometry(C, R2, pl->heads, 2, 16, 5);
-        const size_t words = static_cast<size_t>(pl->heads) * R2 * gp.lp_pad * 2;
+        const FirGeometry gp = fir_geometry(C, R2, pl->heads, tf, 16, 5);
+        const size_t words = static_cast<size_t>(pl->heads) * R2 * gp.lp_pad * tf;
         if (gp.ok && words <= kFirConstTapWords) {
             std::vector<float> pair(words, 0.0f);
             for (uint32_t h = 0; h < pl->heads; ++h) {
@@ -553,9 +569,19 @@ int b200_fir_plan_create(b200_ctx* ctx, const b200_cf32* taps_host, uint64_t nta
                     for (uint32_t m = 0; m < gp.lp_pad; ++m) {
                         const uint64_t c = kp0 + static_cast<uint64_t>(m) * R2;
                         if (c < C) {
-                            const size_t idx = ((static_cast<size_t>(h) * R2 + pidx) * gp.lp_pad + m) * 2;
-                            pair[idx] = taps_host[static_cast<size_t>(h) * pl->L + 2 * c].re;                       // h[2c]
-                            pair[idx + 1] = c > 0 ? taps_host[static_cast<size_t>(h) * pl->L + 2 * c - 1].re : 0.0f;   // h[2c-1]
+                            const size_t idx = ((static_cast<size_t>(h) * R2 + pidx) * gp.lp_pad + m) * tf;
+                            const b200_cf32 ta = taps_host[static_cast<size_t>(h) * pl->L + 2 * c];                    // h[2c]
+                            const b200_cf32 tb = c > 0 ? taps_host[static_cast<size_t>(h) * pl->L + 2 * c - 1]       // h[2c-1]
+                                                       : b200_cf32{0.0f, 0.0f};
+                            if (pl->real_taps) {
+                                pair[idx] = ta.re;
+                                pair[idx + 1] = tb.re;
+                            } else {
+                                pair[idx] = ta.re;
+                                pair[idx + 1] = ta.im;
+                                pair[idx + 2] = tb.re;
+                                pair[idx + 3] = tb.im;
+                            }
                         }
                     }
                 }

@@ -321,15 +321,17 @@ def test_fft_8192_roundtrip_and_reference(ref):
     assert np.abs(back - x).max() <= 1e-5 * np.abs(x).max()
 
 
-@pytest.mark.parametrize("taps,decimation,heads", [(127, 8, 1), (129, 8, 3), (41, 2, 1), (161, 40, 1)])
-def test_fir_chunk_pair_form_equals_the_sample_form(taps, decimation, heads, monkeypatch):
+@pytest.mark.parametrize("taps,decimation,heads,offset", [(127, 8, 1, 0.0), (129, 8, 3, 0.0), (41, 2, 1, 0.0), (161, 40, 1, 0.0),
+                                                         (129, 8, 3, 7e5), (63, 4, 2, -1.1e6)])
+def test_fir_chunk_pair_form_equals_the_sample_form(taps, decimation, heads, offset, monkeypatch):
     """fir_decim_kernel<.., PAIR> (16-byte chunks, decimation R/2, chunk-taps (h[2c], h[2c-1])) against the 8-byte form of
     the same plan over three calls with carried history: same products, a different summation order."""
     torch, _native, lib, ctx, dev = _env()
     rng = np.random.default_rng(taps)
-    centers = (ctypes.c_double * heads)(*([0.0] * heads))
+    centers = (ctypes.c_double * heads)(*[offset * (k + 1) for k in range(heads)])     # offset != 0: complex taps
     host = np.zeros((heads, taps), np.complex64)
     _native.check(lib.b200_filter_taps_host(8e6, 8e6 / decimation / 2, centers, heads, taps, host.ctypes.data_as(ctypes.c_void_p)))
+    assert (np.abs(host.imag).max() > 0) == (offset != 0.0)
     if heads > 1:
         host *= rng.uniform(0.5, 1.5, (heads, 1)).astype(np.float32)
     frames, frame_len = 6, 40 * decimation * 3

@@ -151,15 +151,15 @@ def test_fir_chunk_pair_form():
         lp = -(-C // R2)
         lp_pad = -(-lp // ob) * ob
         hpad = lp_pad + 1
-        h = rng.standard_normal(L)
-        g = np.zeros((C, 2))
+        h = rng.standard_normal(L) + 1j * rng.standard_normal(L)      # complex taps: a frequency-translating head
+        g = np.zeros((C, 2), complex)
         for c in range(C):
             g[c, 0] = h[2 * c]
             g[c, 1] = h[2 * c - 1] if c > 0 else 0.0
-        xs = rng.standard_normal((qt + hpad) * R)            # stream; tile starts at q0 R = hpad R
+        xs = rng.standard_normal((qt + hpad) * R) + 1j * rng.standard_normal((qt + hpad) * R)   # tile starts at q0 R = hpad R
         chunks = xs.reshape(-1, 2)                           # chunk n = (x[2n], x[2n+1])
         span = (qt - 1) * R2 + hpad * R2 + 1
-        planes = np.zeros((R2, qt + hpad + 1, 2))
+        planes = np.zeros((R2, qt + hpad + 1, 2), complex)
         for i in range(span):
             planes[i % R2, i // R2] = chunks[i]
         for o in range(qt):
