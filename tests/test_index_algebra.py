@@ -391,3 +391,36 @@ def test_tiled_two_pass_plan_columns_then_rows():
         for t in range(16):
             e = jj + 16 * t
             assert len({(gb * pitch + e + e // 16) % 16 for gb in range(16)}) == 16
+
+
+def test_real_fft_through_half_length_complex_transform():
+    """b200_fft_exec_real / rfft_unpack_kernel: z[m] = x[2m] + i x[2m+1] is the real row itself viewed as complex; with
+    Z = FFT_h(z), one thread per mirror pair: e = (Z[k] + conj Z[h-k]) / 2, o = (Z[k] - conj Z[h-k]) / (2i), w = W_2h^k,
+    X[k] = e + w o, X[h-k] = conj(e - w o); k = 0 gives X[0] and X[h] from Z[0]; FFTPACK layout [Re X0, Re X1, Im X1, ..., Re Xh]."""
+    rng = np.random.default_rng(12)
+    for h in (2, 3, 8, 9, 50, 4096):
+        x = rng.standard_normal(2 * h)
+        z = np.fft.fft(x[0::2] + 1j * x[1::2])
+        spec = np.zeros(h + 1, complex)
+        for k in range(h // 2 + 1):
+            if k == 0:
+                spec[0] = z[0].real + z[0].imag
+                spec[h] = z[0].real - z[0].imag
+                continue
+            a, m = z[k], z[h - k]
+            e = complex(0.5 * (a.real + m.real), 0.5 * (a.imag - m.imag))
+            o = complex(0.5 * (a.imag + m.imag), -0.5 * (a.real - m.real))
+            t = np.exp(-1j * np.pi * k / h) * o
+            spec[k] = e + t
+            if 2 * k != h:
+                spec[h - k] = np.conj(e - t)
+        want = np.fft.rfft(x)
+        assert np.abs(spec - want).max() < 1e-9 * max(1.0, np.abs(want).max())
+        packed = np.empty(2 * h)
+        packed[0] = spec[0].real
+        packed[1:2 * h - 1:2] = spec[1:h].real
+        packed[2:2 * h - 1:2] = spec[1:h].imag
+        packed[2 * h - 1] = spec[h].real
+        # pocketfft r2r_fftpack layout == scipy.fft.rfft's "halfcomplex" ordering (r0, r1, i1, ..., r_h)
+        import scipy.fft
+        assert np.abs(packed - scipy.fft.rfft(x).view(float)[[0] + list(range(2, 2 * h + 1))]).max() < 1e-9 * max(1.0, np.abs(want).max())
