@@ -601,7 +601,8 @@ def bench_fft(env, steps, warmup):
         env.check(lib.b200_fft_plan_c2c(env.ctx.handle, n // 2, rrows, ctypes.byref(half)))
         out = torch.empty(rrows, n // 2 + 1, dtype=torch.complex64, device=env.dev)
         ms, ms_max, _, _ = env.timed(lambda: env.check(lib.b200_fft_exec_real(half, xr.data_ptr(), out.data_ptr(), 0, env.sp)), steps, warmup)
-        record(f"F32-{n}", ms_max, xr.numel(), 8, "half-length c2c + rfft_unpack_kernel")
+        record(f"F32-{n}", ms_max, xr.numel(), 8, "fft_radix_kernel<MODE_R2C> (transform + unpack in one kernel)" if n // 2 <= 8192
+               else "half-length tiled c2c + rfft_unpack_kernel")
         env.check(lib.b200_fft_plan_destroy(half))
         del out
         launches += 2 * steps

@@ -293,6 +293,22 @@ static int try_launch_radix(const b200_ctx* ctx, const FftParams& p, cudaStream_
     return B200_SUCCESS;
 }
 
+// Real rows of length 2h, 32 <= h <= 8192: the h-point kernel unpacks in its own epilogue (MODE_R2C, fft_radix.cuh).
+static int launch_radix_real(const b200_ctx* ctx, const FftParams& p, cudaStream_t stream) {
+    switch (p.n) {
+        case 32: return launch_radix<5, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 64: return launch_radix<6, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 128: return launch_radix<7, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 256: return launch_radix<8, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 512: return launch_radix<9, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 1024: return launch_radix<10, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 2048: return launch_radix<11, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 4096: return launch_radix<12, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        case 8192: return launch_radix<13, MODE_R2C, WIN_NONE>(ctx, p, stream);
+        default: return fail("fused real transform: unsupported half length %u", p.n);
+    }
+}
+
 static bool fft4096_use_generic() {
     static const bool value = [] {
         const char* env = getenv("B200_FFT4096_GENERIC");
@@ -975,6 +991,21 @@ int b200_fft_exec_real(b200_fft_plan* half_plan, const float* in, void* out, int
     B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7u) == 0, "b200_fft_exec_real: the real input must be 8-byte aligned");
     DeviceGuard guard(half_plan->ctx);
     const uint64_t h = half_plan->n, batch = half_plan->batch;
+    // Single-kernel lengths: transform and unpack in ONE kernel (4 bytes in + 4 out per real sample, no intermediate).
+    const char* fused_env = getenv("B200_FFT_REAL_FUSED");
+    if (half_plan->kind == FFT_DIRECT && is_pow2(h) && h >= 32 && h <= kMaxDirectN &&
+        (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && !(fused_env && atoi(fused_env) == 0)) {
+        FftParams p{};
+        p.in = reinterpret_cast<const float2*>(in);
+        p.out = nullptr;
+        p.rows = batch;
+        p.n = static_cast<uint32_t>(h);
+        p.inverse = 0;
+        p.twiddle = half_plan->twiddle;
+        p.real_out = out;
+        p.real_layout = layout;
+        return launch_radix_real(half_plan->ctx, p, as_stream(stream));
+    }
     if (!half_plan->real_work) {
         void* w = nullptr;
         if (b200_malloc(half_plan->ctx, batch * h * sizeof(float2), &w) != B200_SUCCESS) {

@@ -9,7 +9,9 @@ namespace b200 {
 // MODE_C2C_T (fft_radix_kernel only): the second pass of the two-pass plan (fft_twopass.cuh) — rows are [transform][k1 < 16]
 // slabs of a 16x longer transform; X[k2] of row r goes to out[(r / 16) * 16 n + (r % 16) + 16 k2], no input swap for the
 // inverse (the first pass did it), output swap as MODE_C2C.
-enum : int { MODE_C2C = 0, MODE_AMP = 1, MODE_AMP_RANGE = 2, MODE_C2C_T = 3 };
+// MODE_R2C (fft_radix_kernel, 32 <= N <= 8192): the rows are REAL rows of length 2N viewed as N complex samples; the epilogue
+// unpacks the N-point spectrum into the 2N-point real-input spectrum (real_out, real_layout) without leaving the CTA.
+enum : int { MODE_C2C = 0, MODE_AMP = 1, MODE_AMP_RANGE = 2, MODE_C2C_T = 3, MODE_R2C = 4 };
 enum : int { WIN_NONE = 0, WIN_REAL = 1, WIN_COMPLEX = 2 };
 
 struct FftParams {
@@ -34,6 +36,9 @@ struct FftParams {
     // the epilogue results of its rows in registers and writes one [n] partial at the end; colsum_partial is
     // [gridDim.x, n], reduced in CTA order afterwards (deterministic for a given grid).
     float* colsum_partial;
+    // MODE_R2C: [rows, N + 1] CF32 (real_layout 0, pocketfft::r2c) or [rows, 2N] F32 FFTPACK half-complex (real_layout 1)
+    void* real_out;
+    int real_layout;
 };
 
 // ---- butterflies (forward sign) ------------------------------------------------------------

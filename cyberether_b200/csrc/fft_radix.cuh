@@ -117,6 +117,24 @@ __device__ __forceinline__ TwiddleSet load_twiddles_n(const float2* __restrict__
     return s;
 }
 
+// X[k] of real row `row` (length 2N): layout 0 = [rows, N + 1] CF32, layout 1 = FFTPACK [Re X0, Re X1, Im X1, ..., Re XN].
+template <int N>
+__device__ __forceinline__ void real_store(void* out, const int layout, const uint64_t row, const uint32_t k, const float2 x) {
+    if (layout == 0) {
+        static_cast<float2*>(out)[row * (N + 1) + k] = x;
+    } else {
+        float* const r = static_cast<float*>(out) + row * (2ull * N);
+        if (k == 0) {
+            r[0] = x.x;
+        } else if (k == N) {
+            r[2 * N - 1] = x.x;
+        } else {
+            r[2 * k - 1] = x.x;
+            r[2 * k] = x.y;
+        }
+    }
+}
+
 template <int LOG2N, int MODE, int WIN>
 __global__ void __launch_bounds__(radix_threads(LOG2N), radix_threads(LOG2N) > 256 ? 1 : 2)
     fft_radix_kernel(const FftParams p) {
@@ -331,7 +349,52 @@ __global__ void __launch_bounds__(radix_threads(LOG2N), radix_threads(LOG2N) > 2
         }
 
         // ---- epilogue: the last pass has Ns = N / RL, so k = j and output index = j + t Ns --------------------
-        if (row_valid) {
+        if constexpr (MODE == MODE_R2C) {
+            // The row is a REAL row of length 2N (z[m] = x[2m] + i x[2m+1]); with Z = FFT_N(z) in registers,
+            //   X[k] = e + w o, X[N-k] = conj(e - w o), e = (Z[k] + conj Z[N-k]) / 2, o = (Z[k] - conj Z[N-k]) / (2i), w = W_2N^k.
+            // Z goes through the exchange buffer the last pass did NOT read (linear layout), one thread per mirror pair.
+            static_assert(PASSES >= 2, "the fused real unpack needs a free exchange buffer");
+            constexpr int NS_LAST = N / RL;
+            float2* const zbuf = (PASSES % 2 == 1) ? x1 : sbuf;
+#pragma unroll
+            for (int b = 0; b < CL; ++b) {
+#pragma unroll
+                for (int t = 0; t < RL; ++t) {
+                    zbuf[g * N + lt + b * T + t * NS_LAST] = v[b * RL + dft_pos<RL>(t)];
+                }
+            }
+            __syncthreads();
+            if (row_valid) {
+                const float2* const zr = zbuf + g * N;
+#pragma unroll
+                for (int j = 0; j <= 8; ++j) {
+                    const uint32_t k = lt + j * T;
+                    if (j == 8 && lt != 0) {
+                        break;                                   // k = N / 2 belongs to lt == 0 only
+                    }
+                    if (k == 0) {
+                        const float2 a = zr[0];
+                        real_store<N>(p.real_out, p.real_layout, row, 0, make_float2(a.x + a.y, 0.0f));
+                        real_store<N>(p.real_out, p.real_layout, row, N, make_float2(a.x - a.y, 0.0f));
+                        continue;
+                    }
+                    const float2 a = zr[k];
+                    const float2 m = zr[N - k];
+                    const float2 e = make_float2(0.5f * (a.x + m.x), 0.5f * (a.y - m.y));
+                    const float2 o = make_float2(0.5f * (a.y + m.y), -0.5f * (a.x - m.x));
+                    float sn, cs;
+                    sincospif(-static_cast<float>(k) * (1.0f / static_cast<float>(N)), &sn, &cs);
+                    const float2 tt = make_float2(cs * o.x - sn * o.y, cs * o.y + sn * o.x);
+                    real_store<N>(p.real_out, p.real_layout, row, k, make_float2(e.x + tt.x, e.y + tt.y));
+                    if (2 * k != N) {
+                        real_store<N>(p.real_out, p.real_layout, row, N - k, make_float2(e.x - tt.x, -(e.y - tt.y)));
+                    }
+                }
+            }
+            if constexpr (PASSES % 2 == 1) {
+                __syncthreads();      // zbuf = X1: the next block's pass 0 rewrites it before its first barrier
+            }
+        } else if (row_valid) {
             constexpr int NS_LAST = N / RL;
             if constexpr (MODE == MODE_C2C || MODE == MODE_C2C_T) {
                 // MODE_C2C_T: row = 16 * transform + k1, element k2 lands at k1 + 16 k2 of the 16 N-point transform

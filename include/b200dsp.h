@@ -146,8 +146,10 @@ int b200_fft_real_helper(b200_ctx* ctx, int op, const void* in, void* out, uint6
  * even/odd-packed CF32 input) and one unpack kernel: 16 bytes of traffic per real sample instead of the 40 of
  * cast -> full C2C -> pack. `half_plan` = b200_fft_plan_c2c(ctx, h, batch); in [batch, 2h] F32 (8-byte aligned);
  * layout 0: out [batch, h + 1] CF32 (pocketfft::r2c, `complexOutput`), layout 1: out [batch, 2h] F32 FFTPACK
- * half-complex (pocketfft::r2r_fftpack) — src/domains/dsp/fft/module_impl_native_cpu.cc:142-167. The plan owns the
- * [batch, h] work buffer (allocated on first use). Odd lengths and the inverse keep the composed path above. */
+ * half-complex (pocketfft::r2r_fftpack) — src/domains/dsp/fft/module_impl_native_cpu.cc:142-167. For power-of-two
+ * 32 <= h <= 8192 and a 16-byte aligned input the unpack runs in the transform kernel's own epilogue (one kernel, 8 bytes
+ * of traffic per real sample); otherwise the plan owns a [batch, h] work buffer (allocated on first use). Odd lengths and
+ * the inverse keep the composed path above. */
 int b200_fft_exec_real(b200_fft_plan* half_plan, const float* in, void* out, int layout, b200_stream stream);
 
 /* amplitude — src/domains/dsp/amplitude/module_impl_native_cpu.cc:73-99 with Backend::ApproxLog10

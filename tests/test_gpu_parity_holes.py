@@ -357,12 +357,13 @@ def test_fir_chunk_pair_form_equals_the_sample_form(taps, decimation, heads, off
     assert scale > 0 and np.abs(results["1"] - results["0"]).max() <= 2e-6 * scale
 
 
-@pytest.mark.parametrize("n", [8, 12, 4096, 8192, 65536, 6 * 1000])
+@pytest.mark.parametrize("n", [8, 12, 64, 512, 1024, 4096, 8192, 16384, 65536, 6 * 1000])
 @pytest.mark.parametrize("layout", [0, 1])
 def test_fft_exec_real_half_length_path(ref, n, layout):
     """b200_fft_exec_real: real rows of even length 2h through one h-point complex transform on the row itself + the mirror-pair
     unpack kernel; layout 0 = pocketfft::r2c ([h + 1] CF32), layout 1 = FFTPACK half-complex ([2h] F32). h even, odd (n = 12:
-    h = 6; 6000: h = 3000 -> Bluestein) and tiled (65536: h = 32768)."""
+    h = 6; 6000: h = 3000 -> Bluestein), tiled (65536: h = 32768) and, for 32 <= h <= 8192, fused into the transform kernel's
+    epilogue (MODE_R2C: two, three and four register passes; 5 rows leave a partial last block)."""
     torch, _native, lib, ctx, dev = _env()
     rng = np.random.default_rng(n + layout)
     batch = 5

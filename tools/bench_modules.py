@@ -58,7 +58,7 @@ for nn in (8192, 65536):
     rr = xr.numel() // nn
     xx = xr.reshape(rr, nn); oo = torch.empty(rr, nn // 2 + 1, dtype=torch.complex64, device=dev)
     pl = ctypes.c_void_p(); _native.check(lib.b200_fft_plan_c2c(ctx.handle, nn // 2, rr, ctypes.byref(pl)))
-    report(f"fft r2c {nn} x {rr} (half-length c2c + unpack)", timeit(lambda: _native.check(lib.b200_fft_exec_real(pl, xx.data_ptr(), oo.data_ptr(), 0, sp))), rr * nn, 8)
+    report(f"fft r2c {nn} x {rr} ({'fused MODE_R2C kernel' if nn // 2 <= 8192 else 'half-length c2c + unpack'})", timeit(lambda: _native.check(lib.b200_fft_exec_real(pl, xx.data_ptr(), oo.data_ptr(), 0, sp))), rr * nn, 8)
     report(f"cuFFT r2c {nn} x {rr} [baseline]", timeit(lambda: torch.fft.rfft(xx)), rr * nn, 8)
     lib.b200_fft_plan_destroy(pl); del oo
 coeff = cb.amplitude_scaling_coeff(n)
