@@ -424,3 +424,26 @@ def test_real_fft_through_half_length_complex_transform():
         # pocketfft r2r_fftpack layout == scipy.fft.rfft's "halfcomplex" ordering (r0, r1, i1, ..., r_h)
         import scipy.fft
         assert np.abs(packed - scipy.fft.rfft(x).view(float)[[0] + list(range(2, 2 * h + 1))]).max() < 1e-9 * max(1.0, np.abs(want).max())
+
+
+def test_fused_real_unpack_thread_assignment():
+    """fft_radix_kernel<MODE_R2C>: the T = N / 16 threads of a row unpack the mirror pairs k = lt + j T (j < 8; k = N / 2 by
+    lt = 0 alone): every k in [0, N / 2] exactly once, hence every output bin X[0 .. N] exactly once; Z goes through the
+    exchange buffer the last register pass did NOT read (X1 for an odd number of passes, the stage buffer otherwise)."""
+    for log2n in range(5, 14):
+        n = 1 << log2n
+        t = n // 16
+        seen, outputs = [], []
+        for lt in range(t):
+            for j in range(9):
+                if j == 8 and lt != 0:
+                    break
+                k = lt + j * t
+                seen.append(k)
+                outputs += [0, n] if k == 0 else ([k] if 2 * k == n else [k, n - k])
+        assert sorted(seen) == list(range(n // 2 + 1))
+        assert sorted(outputs) == list(range(n + 1))
+        passes = (log2n + 3) // 4
+        last_pass_reads = "stage" if passes % 2 == 1 else "x1"          # pass q reads the stage buffer for even q
+        zbuf = "x1" if passes % 2 == 1 else "stage"
+        assert zbuf != last_pass_reads
